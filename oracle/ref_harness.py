@@ -1,0 +1,40 @@
+"""Imports the LIVE reference (only where /root/reference exists, i.e. the build container)
+and wires the Philox `StreamShim` into it.  TEST INFRASTRUCTURE ONLY.
+
+Nothing here travels to the GPU box: tests that use it are skipped when the
+reference tree is absent, and oracle/make_golden.py bakes its outputs into
+tests/golden/ so they can be checked anywhere.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("G2048_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "environment", "game_2048.py"))
+
+
+def load(shim):
+    """Returns (game_module, agent_module) of the unmodified reference with `random` := shim."""
+    if not available():
+        raise RuntimeError("reference tree not present")
+    sys.dont_write_bytecode = True          # the tree is read-only
+    # a drop-in copy of these module names (dropin/) may already be imported: evict it
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k in ("environment", "agents") or k.startswith(("environment.", "agents."))}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        game = importlib.import_module("environment.game_2048")
+        agent = importlib.import_module("agents.beam_search_agent")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k in ("environment", "agents") or k.startswith(("environment.", "agents."))]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
+    game.random = shim       # game_2048.py:2   `import random`
+    agent.random = shim      # beam_search_agent.py:3
+    return game, agent

@@ -1,0 +1,86 @@
+"""C oracle (oracle/orc2048.c) against vectors produced by the live reference (tests/golden)."""
+import numpy as np
+
+
+def test_rows(orc, golden):
+    for r in golden["rows"]:
+        b = np.zeros(16, np.int32)
+        b[8:12] = r["row"]
+        out, score = orc.env_move(b, 0)
+        assert out[8:12].tolist() == r["out"] and score == r["score"], r
+        assert not out[:8].any() and not out[12:].any()
+
+
+def test_board_moves_legality_and_evals(orc, golden):
+    for rec in golden["boards"]:
+        b = np.array(rec["board"], np.int32)
+        for a in range(4):
+            out, score = orc.env_move(b, a)
+            assert out.tolist() == rec["env"][a]["out"] and score == rec["env"][a]["score"]
+            aout, ascore, avalid = orc.agent_move(b, a)
+            assert aout.tolist() == rec["agent"][a]["out"]
+            assert ascore == rec["agent"][a]["score"] and avalid == rec["agent"][a]["valid"]
+        assert [bool(orc.env_legal_mask(b) >> k & 1) for k in range(4)] == rec["env_legal"]
+        assert [bool(orc.agent_legal_mask(b) >> k & 1) for k in range(4)] == rec["agent_legal"]
+        if "fast_eval" in rec:
+            assert orc.fast_eval(b) == float.fromhex(rec["fast_eval"])
+            for ph in range(3):
+                assert orc.full_eval(b, ph) == float.fromhex(rec["full_eval"][ph])
+
+
+def test_agent_down_quirk_is_rot180_of_env_down(orc, golden):
+    # beam_search_agent.py:251-253 undoes the pre-rotation in the wrong order
+    n = 0
+    for rec in golden["boards"]:
+        env_down = rec["env"][3]["out"]
+        assert rec["agent"][3]["out"] == env_down[::-1]
+        n += rec["agent_legal"][3] and not rec["env_legal"][3]
+    assert n > 0      # the quirk is actually exercised (fake-valid DOWN)
+
+
+def test_step_kats(orc, golden):
+    for k in golden["step_kats"]:
+        env = orc.Env(golden["seed"], 0, ctor_reset=False)
+        env.set_board(k["board"], score=0, highest_tile=k["highest_tile"])
+        s, r, d, info = env.step(k["action"], inject=k["inject"])
+        assert s.tolist() == k["out"]
+        assert r == float.fromhex(k["reward"]), (k, r)
+        assert d == k["done"] and info["score"] == k["score"] and info["valid_move"] == k["valid"]
+        assert info["highest_tile"] == k["highest_after"]
+
+
+def test_env_trajectories(orc, golden):
+    seed = golden["seed"]
+    for tr in golden["trajectories"]:
+        env = orc.Env(seed, tr["game"])        # ctor reset, as Game2048Env.__init__ does
+        assert env.reset().tolist() == tr["start"]
+        for t, st in enumerate(tr["steps"]):
+            a = orc.lib().orc_random_action(seed, tr["game"], t)
+            assert a == st["a"]
+            s, r, d, info = env.step(a)
+            assert s.tolist() == st["board"], (tr["game"], t)
+            assert r == float.fromhex(st["reward"]), (tr["game"], t)
+            assert d == st["done"] and info["score"] == st["score"]
+            assert info["valid_move"] == st["valid"] and info["highest_tile"] == st["highest"]
+            assert [bool(orc.env_legal_mask(s) >> k & 1) for k in range(4)] == st["legal"]
+            if d:
+                assert env.reset().tolist() == st["reset_to"]
+        assert env.s.spawn_ctr == tr["spawns"]
+
+
+def test_beam_get_action(orc, golden):
+    seed = golden["seed"]
+    for c in golden["beam"]:
+        vm = c["valid_moves"]
+        mask = None if vm is None else sum(int(v) << k for k, v in enumerate(vm))
+        o = orc.beam_get_action(c["board"], mask, c["W"], c["D"], seed, c["game"], c["call"])
+        assert (o.action, o.prob) == (c["action"], c["prob"]), c
+        assert o.spawns == c["spawns"] and c["odd_draw"] == 0
+
+
+def test_full_games(orc, golden):
+    seed = golden["seed"]
+    for g in golden["games"]:
+        o = orc.play_game(seed, g["game"], g["W"], g["D"], max_moves=g["max_moves"])
+        assert (o.score, o.highest_tile, o.moves, o.valid_moves, o.invalid_moves) == \
+            (g["score"], g["highest_tile"], g["moves"], g["valid"], g["invalid"])

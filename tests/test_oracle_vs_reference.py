@@ -1,0 +1,73 @@
+"""Differential test: C oracle vs the LIVE reference under the same injected Philox streams.
+
+Runs only where /root/reference exists (the build container); on the GPU box the
+committed golden vectors (test_oracle_golden.py) carry the pin.
+"""
+import numpy as np
+import pytest
+
+from oracle import philox as P
+from oracle import ref_harness as R
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="live reference tree not present")
+
+SEED = 0x5EED0001CAFE
+
+
+@pytest.fixture(scope="module")
+def ref():
+    shim = P.StreamShim(SEED)
+    game, agent = R.load(shim)
+    return shim, game, agent
+
+
+def test_env_random_policy(orc, ref):
+    shim, game, _ = ref
+    for g in range(100, 112):
+        shim.select(P.DOM_ENV, g, 0, 0)
+        env = game.Game2048Env()
+        s = env.reset()
+        o = orc.Env(SEED, g)
+        assert (o.reset() == s).all()
+        for t in range(300):
+            a = P.random_action(SEED, g, t)
+            s, r, d, info = env.step(a)
+            ob, orw, od, oi = o.step(a)
+            assert (s == ob).all() and float(r) == orw and d == od
+            assert int(info["score"]) == oi["score"] and bool(info["valid_move"]) == oi["valid_move"]
+            assert int(info["highest_tile"]) == oi["highest_tile"]
+            if d:
+                assert (env.reset() == o.reset()).all()
+
+
+def test_agent_primitives_on_synthetic_boards(orc, ref):
+    _, _, agent = ref
+    ag = agent.BeamSearchAgent(15, 20)
+    for g in range(400):
+        b = orc.synthetic_board(SEED, g)
+        b2 = b.reshape(4, 4)
+        for a in range(4):
+            nb, sc, v = ag._make_move(b2.copy(), a)
+            ob, osc, ov = orc.agent_move(b, a)
+            assert (nb.flatten() == ob).all() and int(sc) == osc and bool(v) == ov
+        if b.max() > 0:
+            assert float(ag._fast_evaluate(b2, "early")) == orc.fast_eval(b)
+            for ph, name in enumerate(("early", "mid", "late")):
+                assert float(ag._evaluate_state(b2, name)) == orc.full_eval(b, ph)
+
+
+@pytest.mark.parametrize("W,D", [(15, 20), (20, 40), (5, 9)])
+def test_get_action(orc, ref, W, D):
+    shim, game, agent = ref
+    for g in range(6):
+        b = orc.synthetic_board(SEED, 3000 + 17 * g + W)
+        for vm_mode in (None, "env"):
+            shim.select(P.DOM_BEAM, g, 11, 0)
+            vm = None
+            if vm_mode:
+                vm = [bool(orc.env_legal_mask(b) >> k & 1) for k in range(4)]
+            a, p = agent.BeamSearchAgent(W, D).get_action(b.copy(), vm)
+            mask = None if vm is None else sum(int(x) << k for k, x in enumerate(vm))
+            o = orc.beam_get_action(b, mask, W, D, SEED, g, 11)
+            assert (int(a), float(p)) == (o.action, o.prob)
+            assert shim.draw == 2 * o.spawns
