@@ -1,0 +1,391 @@
+// beam.cu -- BeamSearchAgent.get_action (agents/beam_search_agent.py:71-181) as a warp-per-game
+// search, and the whole-game driver (evaluate_beam_search.py:16-98) built on it.
+//
+// One warp owns one root board.  Per level:
+//   A  parent-per-lane : lane p holds beam entry p in registers, makes its four children with
+//                        the row table in shared memory (agent's DOWN quirk included) and
+//                        writes the valid ones, compacted in (rank, action) order, to scratch.
+//   B  child-per-lane  : each valid child draws its spawn (ordinal = ballot prefix over
+//                        "has an empty cell", exactly the reference's sequential draw order),
+//                        is evaluated and gets a sort key (score, -generation index, first action).
+//   C  top-k           : warp-shuffle bitonic sort of each 32-key row + bitonic top-32 merges;
+//                        lane i < k picks up rank i.  Ties keep generation order (Python's
+//                        stable sort, agent:131,174).
+#include "common.cuh"
+#include "env.cuh"
+
+namespace g2048 {
+
+constexpr int kBeamWarps = 16;                              // roots in flight per block
+constexpr int kBeamThreads = kBeamWarps * 32;
+constexpr int kMaxCand = 4 * G2048_MAX_BEAM_WIDTH;          // 128 children per level at most
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+struct __align__(16) WarpScratch {
+    uint64_t cand[kMaxCand];     // children of this level, generation order
+    double score[kMaxCand];      // float64 scores of the full-evaluation levels
+    uint8_t first[kMaxCand];     // first action of the path each child belongs to
+};
+constexpr size_t kBeamSmemBytes = kRowTableBytes + kBeamWarps * sizeof(WarpScratch);
+
+struct BeamParams {
+    int width, depth;
+    int early_thr, mid_thr;
+    uint32_t k0, k1;
+};
+struct BeamResult {
+    uint32_t action;
+    float prob;
+    double best;
+    int nodes;
+};
+
+// ---- warp-wide sorting network on unique uint32 keys, descending (lane 0 = largest) --------
+__device__ __forceinline__ uint32_t exchange(uint32_t v, int j, bool keep_max)
+{
+    uint32_t o = __shfl_xor_sync(FULL, v, j);
+    return keep_max ? max(v, o) : min(v, o);
+}
+__device__ __forceinline__ uint32_t sort_desc32(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            bool lower = (lane & j) == 0;
+            bool desc = (lane & k) == 0;             // k == 32: every lane
+            v = exchange(v, j, lower == desc);
+        }
+    }
+    return v;
+}
+// a, b sorted descending -> the 32 largest of their union, sorted descending
+__device__ __forceinline__ uint32_t merge_top32(uint32_t a, uint32_t b, uint32_t lane)
+{
+    uint32_t v = max(a, __shfl_sync(FULL, b, 31 - lane));   // bitonic
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) v = exchange(v, j, (lane & j) == 0);
+    return v;
+}
+
+// BeamSearchAgent._make_move (agent:194-258) for one direction.  DOWN returns the true DOWN
+// result rotated by 180 degrees (agent:251-253 undoes agent:210 in the wrong order).
+__device__ __forceinline__ Board agent_child_any(Board b, uint32_t action, const uint16_t *row)
+{
+    Board r = from_line(move_left<true>(to_line(b, action), row), action);
+    return select(action == 3u, rot180(r), r);
+}
+__device__ __forceinline__ void agent_children(Board b, const uint16_t *row, Board c[4])
+{
+    Board t = transpose(b);
+    c[0] = move_left<true>(b, row);
+    c[2] = flip_rows(move_left<true>(flip_rows(b), row));
+    c[1] = transpose(move_left<true>(t, row));
+    // rot180(T(flip(L(flip(T b))))) == T(flipud(L(flip(T b))))
+    c[3] = transpose(flip_row_order(move_left<true>(flip_rows(t), row)));
+}
+
+__device__ __forceinline__ int tile_value(uint32_t e) { return e ? (1 << e) : 0; }
+
+// All 32 lanes call this with the same root / parameters.
+__device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamParams &P, uint32_t game,
+                                       uint32_t call, const uint16_t *row, WarpScratch &ws)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    BeamResult res;
+    res.nodes = 0;
+    res.best = 0.0;
+
+    // agent:82-93 -- legality and the two fast exits
+    Board root_child = agent_child_any(root, lane & 3u, row);
+    bool root_child_valid = root_child != root;
+    uint32_t agent_mask = __ballot_sync(FULL, root_child_valid) & 15u;
+    uint32_t vm = legal_given >= 0 ? ((uint32_t)legal_given & 15u) : agent_mask;
+    if (vm == 0u) { res.action = 0u; res.prob = 0.5f; return res; }
+    if ((vm & (vm - 1u)) == 0u) { res.action = (uint32_t)__ffs((int)vm) - 1u; res.prob = 1.0f; return res; }
+
+    // agent:96-106 -- phase from the root's max tile, adaptive depth from its empty count
+    const int root_max = tile_value(max_exponent(root));
+    const int phase = root_max < P.early_thr ? 0 : root_max < P.mid_thr ? 1 : 2;
+    const int n0 = count_empty(root);
+    const int depth = n0 <= 4 ? min(P.depth + 5, 25) : n0 >= 10 ? min(P.depth - 5, 10) : P.depth;
+
+    Board mine(0u, 0u);          // beam entry of rank `lane`
+    uint32_t my_first = 0u;
+    int nb = 0;                  // beam entries alive
+    uint32_t spawn_base = 0u;    // spawns drawn so far in this call
+
+    for (int d = 0; d < depth; ++d) {
+        // ---- A: expand ----------------------------------------------------------------------
+        int n_valid;
+        if (d == 0) {                                                   // agent:112-123
+            bool is_cand = lane < 4u && ((vm >> lane) & 1u) && root_child_valid;
+            uint32_t bal = __ballot_sync(FULL, is_cand);
+            if (is_cand) {
+                int pos = __popc(bal & lt_mask);
+                ws.cand[pos] = root_child.u64();
+                ws.first[pos] = (uint8_t)lane;
+            }
+            n_valid = __popc(bal);
+        } else {                                                        // agent:142-167
+            Board c[4];
+            uint32_t v = 0u;
+            if ((int)lane < nb) {
+                agent_children(mine, row, c);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) v |= (c[a] != mine) ? (1u << a) : 0u;
+            }
+            int incl = __popc(v);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            n_valid = __shfl_sync(FULL, incl, 31);
+            int pos = incl - __popc(v);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if ((v >> a) & 1u) {
+                    ws.cand[pos] = c[a].u64();
+                    ws.first[pos] = (uint8_t)my_first;
+                    ++pos;
+                }
+            }
+        }
+        __syncwarp();
+        if (n_valid == 0) {
+            if (d > 0) break;                                           // agent:170-171 keeps the old beam
+            // agent:126-128: random.choice among the caller's valid moves, one draw
+            Philox4 p = philox4x32_10(0u, call, game, DOM_BEAM, P.k0, P.k1);
+            int pick = (int)__umulhi(p.w[0], (uint32_t)__popc(vm));
+            uint32_t m = vm;
+            for (int i = 0; i < pick; ++i) m &= m - 1u;
+            res.action = (uint32_t)__ffs((int)m) - 1u;
+            res.prob = 0.5f;
+            return res;
+        }
+        res.nodes += n_valid;
+
+        // ---- B: spawn + evaluate ---------------------------------------------------------------
+        const bool full_level = d >= 1 && d <= 3;                       // agent:139,158-161
+        uint32_t key[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r * 32 < n_valid) {
+                const int c = r * 32 + (int)lane;
+                const bool active = c < n_valid;
+                Board b = active ? Board(ws.cand[c]) : Board(0u, 0u);
+                int n_empty = count_empty(b);
+                const bool draws = active && n_empty > 0;               // agent:262-263: no draw on a full board
+                uint32_t bal = __ballot_sync(FULL, draws);
+                if (draws) {
+                    SpawnWords w = spawn_words(P.k0, P.k1, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lt_mask));
+                    place_tile(b, w.pos, w.val);
+                    n_empty -= 1;
+                }
+                spawn_base += (uint32_t)__popc(bal);
+                if (active) {
+                    const uint32_t emax = max_exponent(b);
+                    const uint32_t tail = ((uint32_t)(127 - c) << 2) | ws.first[c];
+                    ws.cand[c] = b.u64();
+                    if (full_level) {
+                        ws.score[c] = full_eval(b, n_empty, emax, phase);
+                        key[r] = tail;                                  // rank field filled in below
+                    } else {
+                        key[r] = ((uint32_t)fast_eval(b, n_empty, emax) << 9) | tail;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (full_level) {
+            // float64 scores: rank = #candidates with a strictly larger score; equal scores are
+            // separated by the generation index already in the key (stable sort).
+            int rank[4] = {0, 0, 0, 0};
+            double mine_s[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = r * 32 + (int)lane;
+                mine_s[r] = c < n_valid ? ws.score[c] : 0.0;
+            }
+            for (int j = 0; j < n_valid; ++j) {
+                const double s = ws.score[j];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) rank[r] += (s > mine_s[r]) ? 1 : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = r * 32 + (int)lane;
+                if (c < n_valid) key[r] |= (uint32_t)(n_valid - rank[r]) << 9;
+            }
+        }
+
+        // ---- C: stable top-k ------------------------------------------------------------------------
+        uint32_t top = sort_desc32(key[0], lane);
+#pragma unroll
+        for (int r = 1; r < 4; ++r)
+            if (r * 32 < n_valid) top = merge_top32(top, sort_desc32(key[r], lane), lane);
+        nb = min(P.width, n_valid);                                     // agent:132,175
+        const int pick = 127 - (int)((top >> 2) & 127u);
+        if ((int)lane < nb) {
+            mine = Board(ws.cand[pick]);
+            my_first = top & 3u;
+        }
+        const int pick0 = __shfl_sync(FULL, pick, 0);
+        const uint32_t top0 = __shfl_sync(FULL, top, 0);
+        res.best = full_level ? ws.score[pick0] : (double)(top0 >> 9);
+        __syncwarp();                                                   // scratch is rewritten next level
+    }
+    res.action = __shfl_sync(FULL, my_first, 0);                        // agent:178
+    res.prob = 1.0f;
+    return res;
+}
+
+__device__ __forceinline__ void stage_row_table(uint8_t *smem, const uint16_t *row)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(row);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < kRowTableBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+struct BeamArgs {
+    const uint64_t *roots; const uint8_t *legal; const uint32_t *call; uint32_t call0;
+    uint8_t *action; float *prob; double *best; int32_t *nodes;
+    int64_t n; BeamParams P; uint32_t game0; const uint16_t *row;
+};
+
+__global__ void __launch_bounds__(kBeamThreads, 1) beam_search_kernel(BeamArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int warp = threadIdx.x >> 5;
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (int64_t i = (int64_t)blockIdx.x * kBeamWarps + warp; i < a.n; i += (int64_t)gridDim.x * kBeamWarps) {
+        Board root(a.roots[i]);
+        int legal = a.legal ? (int)a.legal[i] : -1;
+        uint32_t call = a.call ? a.call[i] : a.call0;
+        BeamResult r = beam_search_warp(root, legal, a.P, a.game0 + (uint32_t)i, call, row, ws);
+        if (lane == 0) {
+            a.action[i] = (uint8_t)r.action;
+            if (a.prob) a.prob[i] = r.prob;
+            if (a.best) a.best[i] = r.best;
+            if (a.nodes) a.nodes[i] = r.nodes;
+        }
+        __syncwarp();
+    }
+}
+
+struct GamesArgs {
+    int64_t n; BeamParams P; int max_moves; uint32_t game0;
+    int32_t *score; uint8_t *highest; int32_t *moves; int32_t *valid; int32_t *invalid;
+    int32_t *milestone; int64_t *nodes; uint64_t *final_board;
+    const uint16_t *row; const uint8_t *code; unsigned long long *overflow; unsigned int *work;
+};
+
+// Whole games (evaluate_beam_search.py:16-98): one warp plays one game from Game2048Env() to
+// game over, fetching the next game id from a global queue so long games do not strand SMs.
+__global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int warp = threadIdx.x >> 5;
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned int g = 0;
+        if (lane == 0) g = atomicAdd(a.work, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if ((int64_t)g >= a.n) break;
+        const uint32_t game = a.game0 + g;
+        EnvState s;
+        s.spawn_ctr = 0u;
+        env_reset(s, a.P.k0, a.P.k1, game);      // Game2048Env() -> __init__ calls reset (env:27)
+        env_reset(s, a.P.k0, a.P.k1, game);      // state = env.reset() (evaluate_beam_search.py:30)
+        int moves = 0, n_valid = 0, n_invalid = 0;
+        long long nodes = 0;
+        int ms[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) ms[m] = -1;
+        bool done = false;
+        while (!done && moves < a.max_moves) {
+            BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)moves, row, ws);
+            nodes += r.nodes;
+            StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.k0, a.P.k1, game, nullptr, a.overflow);
+            done = st.done;
+            ++moves;
+            if (st.valid) ++n_valid; else ++n_invalid;
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) ms[m] = moves;
+        }
+        if (lane == 0) {
+            if (a.score) a.score[g] = s.score;
+            if (a.highest) a.highest[g] = (uint8_t)s.highest;
+            if (a.moves) a.moves[g] = moves;
+            if (a.valid) a.valid[g] = n_valid;
+            if (a.invalid) a.invalid[g] = n_invalid;
+            if (a.milestone)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) a.milestone[8 * g + m] = ms[m];
+            if (a.nodes) a.nodes[g] = nodes;
+            if (a.final_board) a.final_board[g] = s.board.u64();
+        }
+        __syncwarp();
+    }
+}
+
+static int g_attr_done[kMaxDevices];
+
+static int ensure_attrs()
+{
+    int dev = 0;
+    G2048_CUDA(cudaGetDevice(&dev));
+    if (!g_attr_done[dev]) {
+        G2048_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        g_attr_done[dev] = 1;
+    }
+    return G2048_OK;
+}
+
+int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *legal, const uint32_t *call,
+                       uint32_t call0, uint8_t *action, float *prob, double *best_score, int32_t *nodes,
+                       int64_t n, int beam_width, int search_depth, int early_thr, int mid_thr,
+                       uint64_t seed, uint32_t game0, cudaStream_t stream)
+{
+    int rc = ensure_attrs();
+    if (rc != G2048_OK) return rc;
+    BeamArgs a{roots, legal, call, call0, action, prob, best_score, nodes, n,
+               BeamParams{beam_width, search_depth, early_thr, mid_thr, (uint32_t)seed, (uint32_t)(seed >> 32)},
+               game0, st->row};
+    int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
+    int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
+    beam_search_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "beam_search_kernel");
+}
+
+int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_depth, int early_thr, int mid_thr,
+                      int max_moves, uint64_t seed, uint32_t game0, int32_t *score, uint8_t *highest_exp,
+                      int32_t *moves, int32_t *valid, int32_t *invalid, int32_t *milestone, int64_t *nodes,
+                      uint64_t *final_board, cudaStream_t stream)
+{
+    int rc = ensure_attrs();
+    if (rc != G2048_OK) return rc;
+    G2048_CUDA(cudaMemsetAsync(st->work_counter, 0, sizeof(unsigned int), stream));
+    GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, (uint32_t)seed, (uint32_t)(seed >> 32)},
+                max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
+                st->row, st->code, st->overflow, st->work_counter};
+    int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
+    int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
+    play_games_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "play_games_kernel");
+}
+
+}  // namespace g2048

@@ -1,0 +1,388 @@
+// board.cuh -- device primitives on packed 2048 boards (sm_100a).
+//
+// A board is 16 nibble exponents in a uint64 (cell (r,c) = nibble 4r+c, 0 = empty),
+// held in registers as two 32-bit halves: lo = rows 0,1, hi = rows 2,3.  Everything
+// here is branch-free integer SWAR sized for the ALU pipe (LOP3 / SHF / PRMT / IADD3 /
+// POPC); the only memory operation is the row-table lookup of move_left().
+#pragma once
+#include <stdint.h>
+#ifndef G2048_HOST_EMUL   // tests/host_emul compiles this header with g++ and intrinsic stand-ins
+#include <cuda_runtime.h>
+#endif
+
+namespace g2048 {
+
+struct Board {
+    uint32_t lo, hi;
+    __device__ __forceinline__ Board() {}
+    __device__ __forceinline__ Board(uint32_t l, uint32_t h) : lo(l), hi(h) {}
+    __device__ __forceinline__ explicit Board(uint64_t b) : lo((uint32_t)b), hi((uint32_t)(b >> 32)) {}
+    __device__ __forceinline__ uint64_t u64() const { return ((uint64_t)hi << 32) | lo; }
+};
+__device__ __forceinline__ bool operator==(const Board &a, const Board &b) { return ((a.lo ^ b.lo) | (a.hi ^ b.hi)) == 0; }
+__device__ __forceinline__ bool operator!=(const Board &a, const Board &b) { return ((a.lo ^ b.lo) | (a.hi ^ b.hi)) != 0; }
+
+constexpr uint32_t LSB4 = 0x11111111u;   // bit 0 of every nibble
+constexpr uint32_t MSB4 = 0x88888888u;   // bit 3 of every nibble
+
+// bit 4i set  <=>  nibble i of x is non-zero
+__device__ __forceinline__ uint32_t nz_flags(uint32_t x)
+{
+    uint32_t t = x | (x >> 1);
+    t |= t >> 2;
+    return t & LSB4;
+}
+// bit 4i set  <=>  nibble i of x is zero
+__device__ __forceinline__ uint32_t zero_flags(uint32_t x) { return ~nz_flags(x) & LSB4; }
+
+// ---- geometry -------------------------------------------------------------
+// 4x4 nibble transpose: swap inside 2x2 blocks (per half), then swap the two
+// off-diagonal 2x2 blocks (a byte permutation across the halves).
+__device__ __forceinline__ Board transpose(Board b)
+{
+    uint32_t l = (b.lo & 0xF0F00F0Fu) | ((b.lo << 12) & 0x0F0F0000u) | ((b.lo >> 12) & 0x0000F0F0u);
+    uint32_t h = (b.hi & 0xF0F00F0Fu) | ((b.hi << 12) & 0x0F0F0000u) | ((b.hi >> 12) & 0x0000F0F0u);
+    return Board(__byte_perm(l, h, 0x6240), __byte_perm(l, h, 0x7351));
+}
+__device__ __forceinline__ uint32_t swap_nibbles_in_bytes(uint32_t x)
+{
+    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+}
+// np.fliplr: reverse the 4 nibbles of every row
+__device__ __forceinline__ Board flip_rows(Board b)
+{
+    return Board(swap_nibbles_in_bytes(__byte_perm(b.lo, 0, 0x2301)),
+                 swap_nibbles_in_bytes(__byte_perm(b.hi, 0, 0x2301)));
+}
+// np.flipud: reverse the order of the rows
+__device__ __forceinline__ Board flip_row_order(Board b)
+{
+    return Board(__byte_perm(b.hi, 0, 0x1032), __byte_perm(b.lo, 0, 0x1032));
+}
+// np.rot90(b, 2): reverse all 16 nibbles
+__device__ __forceinline__ Board rot180(Board b)
+{
+    return Board(swap_nibbles_in_bytes(__byte_perm(b.hi, 0, 0x0123)),
+                 swap_nibbles_in_bytes(__byte_perm(b.lo, 0, 0x0123)));
+}
+
+// ---- row tables -------------------------------------------------------------
+// row[r]  : the row r (4 nibbles) after a LEFT move (env:116-168 / agent:213-242)
+// code[r] : the (at most two) merges of that move, one nibble each: 0 = none, else
+//           merged exponent - 1, i.e. the merge scored 2 << nibble.
+struct RowTables {
+    const uint16_t *row;
+    const uint8_t *code;
+};
+
+template <bool kShared>
+__device__ __forceinline__ uint32_t lut16(const uint16_t *t, uint32_t i)
+{
+    if (kShared) return t[i];
+    return __ldg(t + i);
+}
+template <bool kShared>
+__device__ __forceinline__ uint32_t lut8(const uint8_t *t, uint32_t i)
+{
+    if (kShared) return t[i];
+    return __ldg(t + i);
+}
+
+// LEFT move of all four rows.
+template <bool kShared>
+__device__ __forceinline__ Board move_left(Board b, const uint16_t *row)
+{
+    uint32_t r0 = lut16<kShared>(row, b.lo & 0xFFFFu);
+    uint32_t r1 = lut16<kShared>(row, b.lo >> 16);
+    uint32_t r2 = lut16<kShared>(row, b.hi & 0xFFFFu);
+    uint32_t r3 = lut16<kShared>(row, b.hi >> 16);
+    return Board(__byte_perm(r0, r1, 0x5410), __byte_perm(r2, r3, 0x5410));
+}
+// merge codes of the same move, one byte per row
+template <bool kShared>
+__device__ __forceinline__ uint32_t merge_codes(Board b, const uint8_t *code)
+{
+    uint32_t c0 = lut8<kShared>(code, b.lo & 0xFFFFu);
+    uint32_t c1 = lut8<kShared>(code, b.lo >> 16);
+    uint32_t c2 = lut8<kShared>(code, b.hi & 0xFFFFu);
+    uint32_t c3 = lut8<kShared>(code, b.hi >> 16);
+    return __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+}
+// Sum of the merged tile values encoded by 8 code nibbles; *sat gets bit 16 set when a
+// merge produced 2^16 (nibble saturation, counted by the caller).
+__device__ __forceinline__ uint32_t decode_score(uint32_t codes, uint32_t *sat)
+{
+    uint32_t total = 0, any = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = (2u << ((codes >> (4 * i)) & 15u)) & ~3u;   // code 0 -> 2 -> masked to 0
+        total += v;
+        any |= v;
+    }
+    *sat = any;
+    return total;
+}
+
+// Direction wrappers.  `to_line` brings the rows the tiles travel along into LEFT-move
+// position, `from_line` undoes it.  Lane-varying actions use selects, not branches.
+__device__ __forceinline__ Board select(bool p, Board a, Board b) { return Board(p ? a.lo : b.lo, p ? a.hi : b.hi); }
+
+__device__ __forceinline__ Board to_line(Board b, uint32_t action)
+{
+    Board t = select(action & 1u, transpose(b), b);        // UP/DOWN travel along columns
+    return select(action & 2u, flip_rows(t), t);           // RIGHT/DOWN travel towards index 3
+}
+__device__ __forceinline__ Board from_line(Board m, uint32_t action)
+{
+    Board t = select(action & 2u, flip_rows(m), m);
+    return select(action & 1u, transpose(t), t);
+}
+
+// env._execute_move (env:97-114).  action outside 0..3 leaves the board alone.
+template <bool kShared>
+__device__ __forceinline__ Board env_move(Board b, uint32_t action, const uint16_t *row)
+{
+    Board m = from_line(move_left<kShared>(to_line(b, action), row), action);
+    return select(action < 4u, m, b);
+}
+
+// ---- legality without tables ------------------------------------------------
+// Bit a set <=> env action a changes the board (env:69-95): some tile can slide into an
+// empty neighbour in that direction or two equal neighbours along it can merge.
+__device__ __forceinline__ uint32_t eq_flags(uint32_t a, uint32_t b) { return zero_flags(a ^ b); }
+
+__device__ __forceinline__ uint32_t env_legal_mask(Board b)
+{
+    const uint32_t nl = nz_flags(b.lo), nh = nz_flags(b.hi);
+    // horizontal pairs (c, c+1): flag sits on nibble c, c = 0..2 of each row
+    const uint32_t HP = 0x01110111u;
+    uint32_t nl1 = nl >> 4, nh1 = nh >> 4;                       // occupancy of the right neighbour
+    uint32_t mh = ((eq_flags(b.lo, b.lo >> 4) & nl) | (eq_flags(b.hi, b.hi >> 4) & nh)) & HP;
+    uint32_t sl = ((~nl & nl1) | (~nh & nh1)) & HP;              // empty cell, tile to its right  -> LEFT slides
+    uint32_t sr = ((nl & ~nl1) | (nh & ~nh1)) & HP;              // tile, empty cell to its right  -> RIGHT slides
+    // vertical pairs (r, r+1): flag sits on row r, r = 0..2
+    uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16);         // rows 1,2 aligned under rows 0,1
+    uint32_t below_hi = b.hi >> 16;                              // row 3 aligned under row 2
+    uint32_t nbl = __funnelshift_r(nl, nh, 16), nbh = nh >> 16;
+    const uint32_t VH = 0x00001111u;                             // only row 2 has a row below it in `hi`
+    uint32_t mv = (eq_flags(b.lo, below_lo) & nl) | (eq_flags(b.hi, below_hi) & nh & VH);
+    uint32_t su = (~nl & nbl) | (~nh & nbh & VH);                // empty cell, tile below -> UP slides
+    uint32_t sd = (nl & ~nbl & LSB4) | (nh & ~nbh & VH);         // tile, empty cell below -> DOWN slides
+    uint32_t mask = 0;
+    mask |= ((mh | sl) != 0u) ? 1u : 0u;
+    mask |= ((mv | su) != 0u) ? 2u : 0u;
+    mask |= ((mh | sr) != 0u) ? 4u : 0u;
+    mask |= ((mv | sd) != 0u) ? 8u : 0u;
+    return mask;
+}
+// is_game_over (env:279-288): no empty cell and no equal neighbours
+__device__ __forceinline__ bool env_game_over(Board b) { return env_legal_mask(b) == 0u; }
+
+// ---- counting ----------------------------------------------------------------
+__device__ __forceinline__ int count_empty(Board b) { return __popc(zero_flags(b.lo)) + __popc(zero_flags(b.hi)); }
+
+// largest nibble of the board
+__device__ __forceinline__ uint32_t max_exponent(Board b)
+{
+    const uint32_t M = 0x000F000Fu;
+    uint32_t m0 = __vmaxu2(b.lo & M, (b.lo >> 4) & M);
+    uint32_t m1 = __vmaxu2((b.lo >> 8) & M, (b.lo >> 12) & M);
+    uint32_t m2 = __vmaxu2(b.hi & M, (b.hi >> 4) & M);
+    uint32_t m3 = __vmaxu2((b.hi >> 8) & M, (b.hi >> 12) & M);
+    uint32_t m = __vmaxu2(__vmaxu2(m0, m1), __vmaxu2(m2, m3));
+    return max(m & 0xFFFFu, m >> 16);
+}
+// does any nibble of the board equal v (1..15)?
+__device__ __forceinline__ bool has_exponent(Board b, uint32_t v)
+{
+    uint32_t rep = v * LSB4;
+    return (zero_flags(b.lo ^ rep) | zero_flags(b.hi ^ rep)) != 0u;
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------------
+struct Philox4 { uint32_t w[4]; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
+
+enum : uint32_t { DOM_ENV = 0, DOM_BEAM = 1, DOM_ACTION = 2, DOM_BOARD = 3 };
+
+struct SpawnWords { uint32_t pos, val; };
+// spawn i of stream (seed, game, call, domain): words 2(i&1), 2(i&1)+1 of block i>>1
+__device__ __forceinline__ SpawnWords spawn_words(uint32_t k0, uint32_t k1, uint32_t game, uint32_t call,
+                                                  uint32_t domain, uint32_t i)
+{
+    Philox4 p = philox4x32_10(i >> 1, call, game, domain, k0, k1);
+    SpawnWords s;
+    s.pos = (i & 1u) ? p.w[2] : p.w[0];
+    s.val = (i & 1u) ? p.w[3] : p.w[1];
+    return s;
+}
+__device__ __forceinline__ uint32_t random_action(uint32_t k0, uint32_t k1, uint32_t game, uint32_t t)
+{
+    Philox4 p = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, k0, k1);
+    uint32_t s = (t >> 4) & 3u;
+    uint32_t w = s == 0 ? p.w[0] : s == 1 ? p.w[1] : s == 2 ? p.w[2] : p.w[3];
+    return (w >> (2u * (t & 15u))) & 3u;
+}
+
+// ---- spawn (env:59-67, agent:260-269) ----------------------------------------------
+// Puts exponent 1 (word < 0.9*2^32) or 2 into the k-th empty cell in row-major order,
+// k = (pos_word * n_empty) >> 32.  No-op on a full board.  Returns n_empty before.
+__device__ __forceinline__ int place_tile(Board &b, uint32_t pos_word, uint32_t val_word)
+{
+    uint32_t zl = zero_flags(b.lo), zh = zero_flags(b.hi);
+    int cl = __popc(zl), n = cl + __popc(zh);
+    uint32_t k = __umulhi(pos_word, (uint32_t)n);
+    bool in_hi = k >= (uint32_t)cl;
+    uint32_t kk = in_hi ? k - (uint32_t)cl : k;
+    uint32_t z = in_hi ? zh : zl;
+    uint32_t prefix = z * LSB4;                       // nibble j = #empty among nibbles 0..j (<= 8)
+    uint32_t s = prefix + (7u - kk) * LSB4;           // bit 3 of nibble j set <=> prefix_j > kk
+    uint32_t bit = __ffs((int)(s & MSB4)) - 1;        // 4j+3 of the first such nibble
+    uint32_t tile = (val_word < 3865470567u ? 1u : 2u) << ((bit - 3u) & 31u);
+    tile = n > 0 ? tile : 0u;
+    b.lo |= in_hi ? 0u : tile;
+    b.hi |= in_hi ? tile : 0u;
+    return n;
+}
+
+// ---- heuristics -----------------------------------------------------------------------
+// Sum over a set of cells of 2^e (0 for an empty cell); `cells` has bit 4i set for cell i.
+__device__ __forceinline__ uint32_t tile_sum_half(uint32_t x, uint32_t cells)
+{
+    uint32_t total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if ((cells >> (4 * i)) & 1u) total += (1u << ((x >> (4 * i)) & 15u)) & ~1u;
+    return total;
+}
+
+// #equal non-empty neighbour pairs (agent:302-312) and the sum of their exponents (agent:387-403)
+__device__ __forceinline__ void merge_pairs(Board b, int *pairs, int *exponent_sum)
+{
+    const uint32_t nl = nz_flags(b.lo), nh = nz_flags(b.hi);
+    uint32_t hl = eq_flags(b.lo, b.lo >> 4) & nl & 0x01110111u;
+    uint32_t hh = eq_flags(b.hi, b.hi >> 4) & nh & 0x01110111u;
+    uint32_t vl = eq_flags(b.lo, __funnelshift_r(b.lo, b.hi, 16)) & nl;
+    uint32_t vh = eq_flags(b.hi, b.hi >> 16) & nh & 0x00001111u;
+    *pairs = __popc(hl) + __popc(hh) + __popc(vl) + __popc(vh);
+    if (exponent_sum) {
+        // keep the exponent of the first cell of every pair, then add all nibbles up
+        uint32_t a = b.lo & (hl * 15u), c = b.hi & (hh * 15u), d = b.lo & (vl * 15u), e = b.hi & (vh * 15u);
+        // nibble sums: split even/odd nibbles into bytes, bytes never overflow (<= 4 * 15)
+        uint32_t ev = (a & 0x0F0F0F0Fu) + (c & 0x0F0F0F0Fu) + (d & 0x0F0F0F0Fu) + (e & 0x0F0F0F0Fu);
+        uint32_t od = ((a >> 4) & 0x0F0F0F0Fu) + ((c >> 4) & 0x0F0F0F0Fu) + ((d >> 4) & 0x0F0F0F0Fu) + ((e >> 4) & 0x0F0F0F0Fu);
+        *exponent_sum = (int)__vsadu4(ev, 0u) + (int)__vsadu4(od, 0u);
+    }
+}
+
+// BeamSearchAgent._fast_evaluate (agent:280-314): always an exact integer.
+__device__ __forceinline__ int fast_eval(Board b, int n_empty, uint32_t emax)
+{
+    uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
+    int corner_score = corner ? (int)(2u << corner) : 0;          // 2 * tile value of the best corner
+    int pairs;
+    merge_pairs(b, &pairs, nullptr);
+    return n_empty * 10 + (int)emax * 2 + corner_score + pairs * 2;
+}
+
+// BeamSearchAgent._evaluate_state (agent:316-373) in float64 with the reference's operation
+// order and no FMA contraction: bit-exact.  phase 0 early, 1 mid, 2 late.
+__device__ __forceinline__ double full_eval(Board b, int n_empty, uint32_t emax, int phase)
+{
+    const double w_empty  = phase == 0 ? 15.0 : phase == 1 ? 10.0 : 8.0;
+    const double w_max    = phase == 0 ? 1.0  : phase == 1 ? 1.5  : 2.0;
+    const double w_corner = phase == 0 ? 2.0  : phase == 1 ? 2.5  : 3.0;
+    const double w_merge  = phase == 0 ? 2.0  : phase == 1 ? 1.5  : 1.0;
+    double empty_score = __dmul_rn((double)n_empty, w_empty);
+    if (n_empty <= 2) empty_score = __dadd_rn(empty_score, -10.0);
+    double max_score = __dmul_rn((double)emax, w_max);
+    if (emax >= 9)  max_score = __dmul_rn(max_score, 1.2);
+    if (emax >= 10) max_score = __dmul_rn(max_score, 1.5);
+    if (emax >= 11) max_score = __dmul_rn(max_score, 2.0);
+    uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
+    double corner_bonus = __dmul_rn(__dmul_rn((double)corner, 2.0), w_corner);
+    int pairs, esum;
+    merge_pairs(b, &pairs, &esum);
+    double merge_potential = __dmul_rn((double)esum, w_merge);
+    // snake weights 15 14 13 12 / 8 9 10 11 / 7 6 5 4 / 0 1 2 3 (agent:37-42), exact in int
+    int snake = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int wl = i < 4 ? 15 - i : 4 + i;          // rows 0,1
+        const int wh = i < 4 ? 7 - i : i - 4;           // rows 2,3
+        snake += (int)((b.lo >> (4 * i)) & 15u) * wl + (int)((b.hi >> (4 * i)) & 15u) * wh;
+    }
+    double snake_score = __ddiv_rn((double)snake, 100.0);
+    return __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(empty_score, max_score), corner_bonus), merge_potential), snake_score);
+}
+
+// ---- shaped reward (env:212-277), float64, fixed operation order, no FMA ------------------
+// #(both non-empty and next >= previous) per row / per column, packed one nibble per line.
+__device__ __forceinline__ uint32_t ge_flags(uint32_t next, uint32_t prev)
+{
+    // per-nibble unsigned next >= prev, result on bit 3 of every nibble
+    uint32_t t = (next | MSB4) - (prev & ~MSB4);
+    return ((next & ~prev) | (~(next ^ prev) & t)) & MSB4;
+}
+
+__device__ __forceinline__ void ordered_pairs(Board b, int line[4])
+{
+    // line[i] = row_ordered_i + col_ordered_i of env:267-275; a pair's flag sits on bit 3 of
+    // the nibble of its FIRST cell (left cell of a row pair, upper cell of a column pair).
+    const uint32_t nl = nz_flags(b.lo) << 3, nh = nz_flags(b.hi) << 3;      // occupancy on bit 3
+    uint32_t hl = ge_flags(b.lo >> 4, b.lo) & nl & (nl >> 4) & 0x08880888u;  // rows 0,1
+    uint32_t hh = ge_flags(b.hi >> 4, b.hi) & nh & (nh >> 4) & 0x08880888u;  // rows 2,3
+    uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16), nbl = __funnelshift_r(nl, nh, 16);
+    uint32_t vl = ge_flags(below_lo, b.lo) & nl & nbl;                       // row pairs (0,1), (1,2)
+    uint32_t vh = ge_flags(b.hi >> 16, b.hi) & nh & (nh >> 16) & 0x00008888u; // row pair (2,3)
+    uint32_t v = vl | (vh << 1);              // (2,3) flags parked on bit 0 of the next nibble
+    line[0] = __popc(hl & 0x0000FFFFu) + __popc(v & 0x00080018u);
+    line[1] = __popc(hl & 0xFFFF0000u) + __popc(v & 0x00800180u);
+    line[2] = __popc(hh & 0x0000FFFFu) + __popc(v & 0x08001800u);
+    line[3] = __popc(hh & 0xFFFF0000u) + __popc(v & 0x80018000u);
+}
+
+__device__ __forceinline__ double shaped_reward(bool valid, int empty_before, Board cur, int empty_after,
+                                                uint32_t score_delta, uint32_t highest_exp_before,
+                                                uint32_t prev_max_exp)
+{
+    double reward = __dmul_rn((double)score_delta, 0.25);                  // / 4.0 (exact either way)
+    if (highest_exp_before > prev_max_exp) {                               // env:229-241 (dead inside step)
+        reward = __dadd_rn(reward, __dmul_rn(2.0, (double)highest_exp_before));
+        if (highest_exp_before >= 8)  reward = __dadd_rn(reward, 50.0);
+        if (highest_exp_before >= 9)  reward = __dadd_rn(reward, 100.0);
+        if (highest_exp_before >= 10) reward = __dadd_rn(reward, 200.0);
+        if (highest_exp_before >= 11) reward = __dadd_rn(reward, 500.0);
+    }
+    if (!valid) reward = __dadd_rn(reward, -2.0);
+    reward = __dadd_rn(reward, __dmul_rn((double)(empty_after - empty_before), 0.5));
+    // edge_sum = rows 0,3 + columns 0,3 (corners twice) = total - inner 2x2 + corners
+    uint32_t total = tile_sum_half(cur.lo, LSB4) + tile_sum_half(cur.hi, LSB4);
+    uint32_t inner = tile_sum_half(cur.lo, 0x01100000u) + tile_sum_half(cur.hi, 0x00000110u);
+    uint32_t corners = tile_sum_half(cur.lo, 0x00001001u) + tile_sum_half(cur.hi, 0x10010000u);
+    uint32_t edge = total - inner + corners;
+    reward = __dadd_rn(reward, __dmul_rn(__ddiv_rn((double)edge, (double)total), 1.0));
+    if (empty_after <= 2) reward = __dadd_rn(reward, -2.0);
+    int line[4];
+    ordered_pairs(cur, line);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reward = __dadd_rn(reward, __dmul_rn((double)line[i], 0.1));
+    return reward;
+}
+
+}  // namespace g2048

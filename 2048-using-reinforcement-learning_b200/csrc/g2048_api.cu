@@ -1,0 +1,782 @@
+// g2048_api.cu -- C ABI of libg2048 (include/g2048.h): table construction, environment
+// kernels, board-format kernels, statistics, and the host-buffer entry points.
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "env.cuh"
+#include "row_tables.h"
+
+namespace g2048 {
+
+// ------------------------------------------------------------------------------------------
+// host state
+// ------------------------------------------------------------------------------------------
+static DeviceState g_dev[kMaxDevices];
+static std::mutex g_mutex;
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return G2048_OK;
+    return set_error(G2048_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+DeviceState *current_device_state()
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        set_error(G2048_ENODEVICE, "no CUDA device (libg2048 has no CPU fallback)");
+        return nullptr;
+    }
+    if (!g_dev[dev].ready) {
+        set_error(G2048_ENOTINIT, "g2048_init(%d) has not been called", dev);
+        return nullptr;
+    }
+    return &g_dev[dev];
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+constexpr int kEnvThreads = 256;
+constexpr int kEnvSharedThreads = 512;   // one 192 KiB block per SM
+
+// Copies both row tables into dynamic shared memory (192 KiB), 16 bytes per thread per trip.
+__device__ __forceinline__ void stage_tables(uint8_t *smem, const uint16_t *row, const uint8_t *code, bool with_code)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(row);
+    uint4 *dst = reinterpret_cast<uint4 *>(smem);
+    for (uint32_t i = threadIdx.x; i < kRowTableBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (with_code) {
+        const uint4 *src2 = reinterpret_cast<const uint4 *>(code);
+        uint4 *dst2 = reinterpret_cast<uint4 *>(smem + kRowTableBytes);
+        for (uint32_t i = threadIdx.x; i < kCodeTableBytes / 16; i += blockDim.x) dst2[i] = __ldg(src2 + i);
+    }
+    __syncthreads();
+}
+
+struct StepArgs {
+    uint64_t *boards; const uint8_t *actions; const uint32_t *inject;
+    int32_t *score; uint8_t *highest; uint32_t *spawn_ctr;
+    double *reward; float *reward32; int32_t *score_delta; uint8_t *valid; uint8_t *legal; uint8_t *done;
+    int64_t n; uint32_t k0, k1, game0;
+    const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
+};
+
+// Game2048Env.step for n envs, one env per thread, one launch per step.
+template <bool kShared, int kThreads>
+__global__ void __launch_bounds__(kThreads) env_step_kernel(StepArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint16_t *row = a.row;
+    const uint8_t *code = a.code;
+    if (kShared) {
+        stage_tables(smem, a.row, a.code, true);
+        row = reinterpret_cast<const uint16_t *>(smem);
+        code = smem + kRowTableBytes;
+    }
+    const bool want_reward = a.reward != nullptr || a.reward32 != nullptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        EnvState s;
+        s.board = Board(a.boards[i]);
+        s.score = a.score ? a.score[i] : 0;
+        s.highest = a.highest ? a.highest[i] : 0u;
+        s.spawn_ctr = a.spawn_ctr ? a.spawn_ctr[i] : 0u;
+        const uint32_t action = a.actions[i];
+        uint32_t inj[2];
+        if (a.inject) { inj[0] = a.inject[2 * i]; inj[1] = a.inject[2 * i + 1]; }
+        StepResult r = want_reward
+            ? env_step<kShared, kShared, true>(s, action, row, code, a.k0, a.k1, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow)
+            : env_step<kShared, kShared, false>(s, action, row, code, a.k0, a.k1, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow);
+        a.boards[i] = s.board.u64();
+        if (a.score) a.score[i] = s.score;
+        if (a.highest) a.highest[i] = (uint8_t)s.highest;
+        if (a.spawn_ctr) a.spawn_ctr[i] = s.spawn_ctr;
+        if (a.reward) a.reward[i] = r.reward;
+        if (a.reward32) a.reward32[i] = (float)r.reward;
+        if (a.score_delta) a.score_delta[i] = (int32_t)r.score_delta;
+        if (a.valid) a.valid[i] = r.valid;
+        if (a.legal) a.legal[i] = (uint8_t)env_legal_mask(s.board);
+        if (a.done) a.done[i] = r.done;
+    }
+}
+
+__global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(uint64_t *boards, int32_t *score, uint8_t *highest,
+                                                                 uint32_t *spawn_ctr, int64_t n, uint32_t k0,
+                                                                 uint32_t k1, uint32_t game0)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        EnvState s;
+        s.spawn_ctr = spawn_ctr ? spawn_ctr[i] : 0u;
+        env_reset(s, k0, k1, game0 + (uint32_t)i);
+        boards[i] = s.board.u64();
+        if (score) score[i] = 0;
+        if (highest) highest[i] = (uint8_t)s.highest;
+        if (spawn_ctr) spawn_ctr[i] = s.spawn_ctr;
+    }
+}
+
+struct RolloutArgs {
+    uint64_t *boards; int32_t *score; uint8_t *highest; uint32_t *spawn_ctr;
+    double *reward_sum; int32_t *episodes;
+    int64_t n; int32_t steps; uint32_t t0; uint32_t k0, k1, game0;
+    const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
+};
+
+// `steps` env.step calls per env with the board in registers; random-policy actions from the
+// Philox action stream (one block = 64 actions), auto-reset on game over.
+constexpr int kRolloutThreads = 512;
+__global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(RolloutArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_tables(smem, a.row, a.code, true);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const uint8_t *code = smem + kRowTableBytes;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t game = a.game0 + (uint32_t)i;
+        EnvState s;
+        s.board = Board(a.boards[i]);
+        s.score = a.score[i];
+        s.highest = a.highest[i];
+        s.spawn_ctr = a.spawn_ctr[i];
+        double rsum = a.reward_sum ? a.reward_sum[i] : 0.0;
+        int32_t episodes = a.episodes ? a.episodes[i] : 0;
+        Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
+        for (int32_t step = 0; step < a.steps; ++step) {
+            const uint32_t t = a.t0 + (uint32_t)step;
+            if ((t & 63u) == 0u && step != 0) act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
+            const uint32_t sel = (t >> 4) & 3u;
+            const uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
+            const uint32_t action = (word >> (2u * (t & 15u))) & 3u;
+            StepResult r = env_step<true, true, true>(s, action, row, code, a.k0, a.k1, game, nullptr, a.overflow);
+            rsum = __dadd_rn(rsum, r.reward);
+            if (r.done) { ++episodes; env_reset(s, a.k0, a.k1, game); }
+        }
+        a.boards[i] = s.board.u64();
+        a.score[i] = s.score;
+        a.highest[i] = (uint8_t)s.highest;
+        a.spawn_ctr[i] = s.spawn_ctr;
+        if (a.reward_sum) a.reward_sum[i] = rsum;
+        if (a.episodes) a.episodes[i] = episodes;
+    }
+}
+
+__global__ void legal_masks_kernel(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n,
+                                   const uint16_t *row)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        Board b(boards[i]);
+        uint32_t m = env_legal_mask(b);
+        if (env_legal) env_legal[i] = (uint8_t)m;
+        if (agent_legal) {
+            // agent:209-210 vs :251-253: the DOWN result comes back rotated by 180 degrees and is
+            // compared with the input in that state
+            Board down = rot180(env_move<false>(b, 3u, row));
+            agent_legal[i] = (uint8_t)((m & 7u) | (down != b ? 8u : 0u));
+        }
+    }
+}
+
+__global__ void pack_kernel(const int32_t *values, uint64_t *boards, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 *v = reinterpret_cast<const int4 *>(values + 16 * i);
+        uint64_t b = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int4 x = v[q];
+            int t[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t e = t[j] > 0 ? 31u - (uint32_t)__clz(t[j]) : 0u;     // log2 of a power of two
+                b |= (uint64_t)(e & 15u) << (4 * (4 * q + j));
+            }
+        }
+        boards[i] = b;
+    }
+}
+
+__global__ void unpack_kernel(const uint64_t *boards, int32_t *values, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = boards[i];
+        int4 *v = reinterpret_cast<int4 *>(values + 16 * i);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t e = (uint32_t)(b >> (4 * (4 * q + j))) & 15u;
+                t[j] = e ? (1 << e) : 0;
+            }
+            v[q] = make_int4(t[0], t[1], t[2], t[3]);
+        }
+    }
+}
+
+// ppo_agent.py:184-195: log2(tile)/15 for tile > 0, else 0
+__global__ void observe_kernel(const uint64_t *boards, float *obs, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = boards[i];
+        float4 *o = reinterpret_cast<float4 *>(obs + 16 * i);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = (float)((uint32_t)(b >> (4 * (4 * q + j))) & 15u) / 15.0f;
+            o[q] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    }
+}
+
+__global__ void synthetic_kernel(uint64_t *boards, int64_t n, uint32_t k0, uint32_t k1, uint32_t game0)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = 0;
+#pragma unroll
+        for (uint32_t blk = 0; blk < 4; ++blk) {
+            Philox4 p = philox4x32_10(blk, 0u, game0 + (uint32_t)i, DOM_BOARD, k0, k1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t x = p.w[j];
+                uint32_t e = 1u + (((x >> 16) * 11u) >> 16);
+                e = (x & 0xFFFFu) < 19661u ? 0u : e;
+                b |= (uint64_t)e << (4 * (4 * blk + j));
+            }
+        }
+        boards[i] = b;
+    }
+}
+
+__global__ void evaluate_kernel(const uint64_t *boards, int32_t *fast, double *full, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        Board b(boards[i]);
+        int n0 = count_empty(b);
+        uint32_t emax = max_exponent(b);
+        if (fast) fast[i] = fast_eval(b, n0, emax);
+        if (full) {
+            full[3 * i + 0] = full_eval(b, n0, emax, 0);
+            full[3 * i + 1] = full_eval(b, n0, emax, 1);
+            full[3 * i + 2] = full_eval(b, n0, emax, 2);
+        }
+    }
+}
+
+// Per-rank game statistics; added into `stats` so that ranks can all-reduce the vector.
+__global__ void stats_kernel(const int32_t *score, const uint8_t *highest, const int32_t *moves, const int32_t *valid,
+                             const int32_t *invalid, const int32_t *milestone, const int64_t *nodes, int64_t n,
+                             unsigned long long *stats)
+{
+    __shared__ unsigned long long acc[G2048_STATS_LEN];
+    for (int j = threadIdx.x; j < G2048_STATS_LEN; j += blockDim.x) acc[j] = 0ull;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t h = highest ? highest[i] : 0u;
+        atomicAdd(&acc[h < 18u ? h : 17u], 1ull);
+        if (score) {
+            atomicAdd(&acc[18], (unsigned long long)(long long)score[i]);
+            atomicMax(reinterpret_cast<long long *>(&acc[G2048_STATS_MAXSCORE]), (long long)score[i]);
+        }
+        if (moves) atomicAdd(&acc[19], (unsigned long long)moves[i]);
+        if (valid) atomicAdd(&acc[20], (unsigned long long)valid[i]);
+        if (invalid) atomicAdd(&acc[21], (unsigned long long)invalid[i]);
+        atomicAdd(&acc[22], 1ull);
+        if (milestone)
+            for (int m = 0; m < 8; ++m)
+                if (milestone[8 * i + m] >= 0) atomicAdd(&acc[24 + m], 1ull);
+        if (nodes) atomicAdd(&acc[32], (unsigned long long)nodes[i]);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < G2048_STATS_LEN; j += blockDim.x) {
+        if (j == G2048_STATS_MAXSCORE) atomicMax(reinterpret_cast<long long *>(&stats[j]), (long long)acc[j]);
+        else if (acc[j]) atomicAdd(&stats[j], acc[j]);
+    }
+}
+
+static int grid_for(int64_t n, int threads, int sm_count, int blocks_per_sm)
+{
+    int64_t want = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count * blocks_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+// Large batches amortise staging 192 KiB of tables per block; small ones read the tables
+// through L1/L2 instead.
+static bool use_shared_tables(int64_t n, int sm_count) { return n >= (int64_t)sm_count * 4096; }
+
+}  // namespace g2048
+
+using namespace g2048;
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int g2048_abi_version(void) { return G2048_ABI_VERSION; }
+const char *g2048_last_error(void) { return g_error; }
+uint64_t g2048_launch_count(void) { return g_launches.load(); }
+
+int g2048_init(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return set_error(G2048_ENODEVICE, "no CUDA device (libg2048 has no CPU fallback)");
+    if (device < 0 || device >= count || device >= kMaxDevices) return set_error(G2048_EINVAL, "bad device %d", device);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    G2048_CUDA(cudaSetDevice(device));
+    DeviceState &st = g_dev[device];
+    if (st.ready) return G2048_OK;
+    std::vector<uint16_t> row(kRowEntries);
+    std::vector<uint8_t> code(kRowEntries);
+    build_row_tables(row.data(), code.data());
+    G2048_CUDA(cudaMalloc(&st.row, kRowTableBytes));
+    G2048_CUDA(cudaMalloc(&st.code, kCodeTableBytes));
+    G2048_CUDA(cudaMalloc(&st.overflow, sizeof(unsigned long long)));
+    G2048_CUDA(cudaMalloc(&st.work_counter, sizeof(unsigned int)));
+    G2048_CUDA(cudaMemcpy(st.row, row.data(), kRowTableBytes, cudaMemcpyHostToDevice));
+    G2048_CUDA(cudaMemcpy(st.code, code.data(), kCodeTableBytes, cudaMemcpyHostToDevice));
+    G2048_CUDA(cudaMemset(st.overflow, 0, sizeof(unsigned long long)));
+    G2048_CUDA(cudaMemset(st.work_counter, 0, sizeof(unsigned int)));
+    G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
+    const int smem = (int)(kRowTableBytes + kCodeTableBytes);
+    G2048_CUDA(cudaFuncSetAttribute(env_step_kernel<true, kEnvSharedThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    G2048_CUDA(cudaFuncSetAttribute(env_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    st.ready = true;
+    return G2048_OK;
+}
+
+int g2048_set_device(int device)
+{
+    if (device < 0 || device >= kMaxDevices || !g_dev[device].ready)
+        return set_error(G2048_ENOTINIT, "g2048_init(%d) has not been called", device);
+    G2048_CUDA(cudaSetDevice(device));
+    return G2048_OK;
+}
+
+int g2048_overflow_count(uint64_t *count, void *stream)
+{
+    DeviceState *st = current_device_state();
+    if (!st) return G2048_ENOTINIT;
+    if (!count) return set_error(G2048_EINVAL, "count is NULL");
+    unsigned long long v = 0;
+    G2048_CUDA(cudaMemcpyAsync(&v, st->overflow, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    G2048_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *count = v;
+    return G2048_OK;
+}
+
+#define G2048_ENTER(required_ok)                                                   \
+    DeviceState *st = current_device_state();                                      \
+    if (!st) return G2048_ENOTINIT;                                                \
+    if (n < 0 || !(required_ok)) return set_error(G2048_EINVAL, "%s: bad argument", __func__); \
+    if (n == 0) return G2048_OK;                                                   \
+    cudaStream_t s = (cudaStream_t)stream
+
+#define G2048_LAUNCHED()                                      \
+    count_launch();                                           \
+    return check_cuda(cudaGetLastError(), __func__)
+
+int g2048_pack(const int32_t *values, uint64_t *boards, int64_t n, void *stream)
+{
+    G2048_ENTER(values && boards);
+    pack_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(values, boards, n);
+    G2048_LAUNCHED();
+}
+
+int g2048_unpack(const uint64_t *boards, int32_t *values, int64_t n, void *stream)
+{
+    G2048_ENTER(values && boards);
+    unpack_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(boards, values, n);
+    G2048_LAUNCHED();
+}
+
+int g2048_observe(const uint64_t *boards, float *obs, int64_t n, void *stream)
+{
+    G2048_ENTER(boards && obs);
+    observe_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(boards, obs, n);
+    G2048_LAUNCHED();
+}
+
+int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards);
+    synthetic_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(boards, n, (uint32_t)seed, (uint32_t)(seed >> 32), game0);
+    G2048_LAUNCHED();
+}
+
+int g2048_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                    int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards);
+    env_reset_kernel<<<grid_for(n, kEnvThreads, st->sm_count, 8), kEnvThreads, 0, s>>>(
+        boards, score, highest_exp, spawn_ctr, n, (uint32_t)seed, (uint32_t)(seed >> 32), game0);
+    G2048_LAUNCHED();
+}
+
+int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
+                   int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                   double *reward, float *reward32, int32_t *score_delta,
+                   uint8_t *valid, uint8_t *legal, uint8_t *done,
+                   int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards && actions);
+    StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
+               valid, legal, done, n, (uint32_t)seed, (uint32_t)(seed >> 32), game0, st->row, st->code, st->overflow};
+    if (use_shared_tables(n, st->sm_count)) {
+        env_step_kernel<true, kEnvSharedThreads><<<st->sm_count, kEnvSharedThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
+    } else {
+        env_step_kernel<false, kEnvThreads><<<grid_for(n, kEnvThreads, st->sm_count, 8), kEnvThreads, 0, s>>>(a);
+    }
+    G2048_LAUNCHED();
+}
+
+int g2048_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n, void *stream)
+{
+    G2048_ENTER(boards);
+    legal_masks_kernel<<<grid_for(n, 256, st->sm_count, 8), 256, 0, s>>>(boards, env_legal, agent_legal, n, st->row);
+    G2048_LAUNCHED();
+}
+
+int g2048_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                      double *reward_sum, int32_t *episodes,
+                      int64_t n, int32_t steps, uint32_t t0, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards && score && highest_exp && spawn_ctr && steps >= 0);
+    RolloutArgs a{boards, score, highest_exp, spawn_ctr, reward_sum, episodes, n, steps, t0,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), game0, st->row, st->code, st->overflow};
+    int grid = grid_for(n, kRolloutThreads, st->sm_count, 1);
+    env_rollout_kernel<<<grid, kRolloutThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
+    G2048_LAUNCHED();
+}
+
+int g2048_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t n, void *stream)
+{
+    G2048_ENTER(boards);
+    evaluate_kernel<<<grid_for(n, 256, st->sm_count, 8), 256, 0, s>>>(boards, fast, full, n);
+    G2048_LAUNCHED();
+}
+
+int g2048_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_t *call, uint32_t call0,
+                      uint8_t *action, float *prob, double *best_score, int32_t *nodes,
+                      int64_t n, int32_t beam_width, int32_t search_depth,
+                      int32_t early_thr, int32_t mid_thr, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(roots && action && beam_width >= 1 && beam_width <= G2048_MAX_BEAM_WIDTH && search_depth >= 1);
+    return launch_beam_search(st, roots, legal, call, call0, action, prob, best_score, nodes, n, beam_width,
+                              search_depth, early_thr, mid_thr, seed, game0, s);
+}
+
+int g2048_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
+                     int32_t early_thr, int32_t mid_thr, int32_t max_moves, uint64_t seed, uint32_t game0,
+                     int32_t *score, uint8_t *highest_exp, int32_t *moves, int32_t *valid, int32_t *invalid,
+                     int32_t *milestone, int64_t *nodes, uint64_t *final_board, void *stream)
+{
+    G2048_ENTER(beam_width >= 1 && beam_width <= G2048_MAX_BEAM_WIDTH && search_depth >= 1 && max_moves >= 0);
+    return launch_play_games(st, n, beam_width, search_depth, early_thr, mid_thr, max_moves, seed, game0, score,
+                             highest_exp, moves, valid, invalid, milestone, nodes, final_board, s);
+}
+
+int g2048_stats_reduce(const int32_t *score, const uint8_t *highest_exp, const int32_t *moves,
+                       const int32_t *valid, const int32_t *invalid, const int32_t *milestone,
+                       const int64_t *nodes, int64_t n, int64_t *stats, void *stream)
+{
+    G2048_ENTER(stats);
+    stats_kernel<<<grid_for(n, 256, st->sm_count, 2), 256, 0, s>>>(score, highest_exp, moves, valid, invalid, milestone,
+                                                                  nodes, n, reinterpret_cast<unsigned long long *>(stats));
+    G2048_LAUNCHED();
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry points: H2D, kernels, D2H on the library's own stream
+// ------------------------------------------------------------------------------------------
+namespace g2048 {
+
+// A grow-only device arena per device; the host_* calls carve their temporaries out of it.
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaStream_t stream = nullptr;
+};
+static Arena g_arena[kMaxDevices];
+static std::mutex g_host_mutex;
+
+static int arena_begin(Arena **out, size_t need)
+{
+    int dev = 0;
+    G2048_CUDA(cudaGetDevice(&dev));
+    Arena &a = g_arena[dev];
+    if (!a.stream) G2048_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    if (need > a.cap) {
+        if (a.base) { G2048_CUDA(cudaStreamSynchronize(a.stream)); G2048_CUDA(cudaFree(a.base)); a.base = nullptr; }
+        size_t cap = need + need / 4 + (1u << 16);
+        G2048_CUDA(cudaMalloc(&a.base, cap));
+        a.cap = cap;
+    }
+    a.used = 0;
+    *out = &a;
+    return G2048_OK;
+}
+template <typename T>
+static T *arena_take(Arena *a, int64_t count)
+{
+    size_t bytes = ((size_t)count * sizeof(T) + 255u) & ~(size_t)255u;
+    T *p = reinterpret_cast<T *>(a->base + a->used);
+    a->used += bytes;
+    return p;
+}
+template <typename T>
+static size_t arena_bytes(int64_t count) { return ((size_t)count * sizeof(T) + 255u) & ~(size_t)255u; }
+
+template <typename T>
+static int to_device(Arena *a, T **dptr, const T *host, int64_t count, bool copy)
+{
+    *dptr = arena_take<T>(a, count);
+    if (copy && host) G2048_CUDA(cudaMemcpyAsync(*dptr, host, (size_t)count * sizeof(T), cudaMemcpyHostToDevice, a->stream));
+    return G2048_OK;
+}
+template <typename T>
+static int to_host(Arena *a, T *host, const T *dptr, int64_t count)
+{
+    if (host) G2048_CUDA(cudaMemcpyAsync(host, dptr, (size_t)count * sizeof(T), cudaMemcpyDeviceToHost, a->stream));
+    return G2048_OK;
+}
+
+}  // namespace g2048
+
+#define G2048_TRY(expr)                        \
+    do {                                       \
+        int _rc = (expr);                      \
+        if (_rc != G2048_OK) return _rc;       \
+    } while (0)
+
+extern "C" {
+
+int g2048_host_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                         int64_t n, uint64_t seed, uint32_t game0)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_env_reset: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<int32_t>(n) + arena_bytes<uint8_t>(n) + arena_bytes<uint32_t>(n)));
+    uint64_t *d_b; int32_t *d_s; uint8_t *d_h; uint32_t *d_c;
+    G2048_TRY(to_device(a, &d_b, boards, n, false));
+    G2048_TRY(to_device(a, &d_s, score, n, false));
+    G2048_TRY(to_device(a, &d_h, highest_exp, n, false));
+    G2048_TRY(to_device(a, &d_c, spawn_ctr, n, true));
+    if (!spawn_ctr) G2048_CUDA(cudaMemsetAsync(d_c, 0, (size_t)n * sizeof(uint32_t), a->stream));
+    G2048_TRY(g2048_env_reset(d_b, d_s, d_h, d_c, n, seed, game0, a->stream));
+    G2048_TRY(to_host(a, boards, d_b, n));
+    G2048_TRY(to_host(a, score, d_s, n));
+    G2048_TRY(to_host(a, highest_exp, d_h, n));
+    G2048_TRY(to_host(a, spawn_ctr, d_c, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
+                        int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                        double *reward, int32_t *score_delta, uint8_t *valid, uint8_t *legal, uint8_t *done,
+                        int64_t n, uint64_t seed, uint32_t game0)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards || !actions) return set_error(G2048_EINVAL, "g2048_host_env_step: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<uint32_t>(2 * n) + 2 * arena_bytes<int32_t>(n) +
+                                  arena_bytes<uint32_t>(n) + arena_bytes<double>(n) + 5 * arena_bytes<uint8_t>(n)));
+    uint64_t *d_b; uint8_t *d_a; uint32_t *d_inj = nullptr; int32_t *d_s; uint8_t *d_h; uint32_t *d_c;
+    double *d_r = nullptr; int32_t *d_sd = nullptr; uint8_t *d_v = nullptr, *d_l = nullptr, *d_d = nullptr;
+    G2048_TRY(to_device(a, &d_b, (const uint64_t *)boards, n, true));
+    G2048_TRY(to_device(a, &d_a, actions, n, true));
+    if (spawn_inject) G2048_TRY(to_device(a, &d_inj, spawn_inject, 2 * n, true));
+    G2048_TRY(to_device(a, &d_s, (const int32_t *)score, n, true));
+    if (!score) G2048_CUDA(cudaMemsetAsync(d_s, 0, (size_t)n * sizeof(int32_t), a->stream));
+    G2048_TRY(to_device(a, &d_h, (const uint8_t *)highest_exp, n, true));
+    if (!highest_exp) G2048_CUDA(cudaMemsetAsync(d_h, 0, (size_t)n, a->stream));
+    G2048_TRY(to_device(a, &d_c, (const uint32_t *)spawn_ctr, n, true));
+    if (!spawn_ctr) G2048_CUDA(cudaMemsetAsync(d_c, 0, (size_t)n * sizeof(uint32_t), a->stream));
+    if (reward) d_r = arena_take<double>(a, n);
+    if (score_delta) d_sd = arena_take<int32_t>(a, n);
+    if (valid) d_v = arena_take<uint8_t>(a, n);
+    if (legal) d_l = arena_take<uint8_t>(a, n);
+    if (done) d_d = arena_take<uint8_t>(a, n);
+    G2048_TRY(g2048_env_step(d_b, d_a, d_inj, d_s, d_h, d_c, d_r, nullptr, d_sd, d_v, d_l, d_d, n, seed, game0, a->stream));
+    G2048_TRY(to_host(a, boards, d_b, n));
+    G2048_TRY(to_host(a, score, d_s, n));
+    G2048_TRY(to_host(a, highest_exp, d_h, n));
+    G2048_TRY(to_host(a, spawn_ctr, d_c, n));
+    G2048_TRY(to_host(a, reward, d_r, n));
+    G2048_TRY(to_host(a, score_delta, d_sd, n));
+    G2048_TRY(to_host(a, valid, d_v, n));
+    G2048_TRY(to_host(a, legal, d_l, n));
+    G2048_TRY(to_host(a, done, d_d, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                           double *reward_sum, int32_t *episodes,
+                           int64_t n, int32_t steps, uint32_t t0, uint64_t seed, uint32_t game0)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards || !score || !highest_exp || !spawn_ctr)
+        return set_error(G2048_EINVAL, "g2048_host_env_rollout: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<int32_t>(n) + arena_bytes<uint8_t>(n) +
+                                  arena_bytes<uint32_t>(n) + arena_bytes<double>(n)));
+    uint64_t *d_b; int32_t *d_s; uint8_t *d_h; uint32_t *d_c; double *d_r; int32_t *d_e;
+    G2048_TRY(to_device(a, &d_b, (const uint64_t *)boards, n, true));
+    G2048_TRY(to_device(a, &d_s, (const int32_t *)score, n, true));
+    G2048_TRY(to_device(a, &d_h, (const uint8_t *)highest_exp, n, true));
+    G2048_TRY(to_device(a, &d_c, (const uint32_t *)spawn_ctr, n, true));
+    G2048_TRY(to_device(a, &d_r, (const double *)reward_sum, n, true));
+    if (!reward_sum) G2048_CUDA(cudaMemsetAsync(d_r, 0, (size_t)n * sizeof(double), a->stream));
+    G2048_TRY(to_device(a, &d_e, (const int32_t *)episodes, n, true));
+    if (!episodes) G2048_CUDA(cudaMemsetAsync(d_e, 0, (size_t)n * sizeof(int32_t), a->stream));
+    G2048_TRY(g2048_env_rollout(d_b, d_s, d_h, d_c, d_r, d_e, n, steps, t0, seed, game0, a->stream));
+    G2048_TRY(to_host(a, boards, d_b, n));
+    G2048_TRY(to_host(a, score, d_s, n));
+    G2048_TRY(to_host(a, highest_exp, d_h, n));
+    G2048_TRY(to_host(a, spawn_ctr, d_c, n));
+    G2048_TRY(to_host(a, reward_sum, d_r, n));
+    G2048_TRY(to_host(a, episodes, d_e, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_legal_masks: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<uint8_t>(n)));
+    uint64_t *d_b; uint8_t *d_e = nullptr, *d_g = nullptr;
+    G2048_TRY(to_device(a, &d_b, boards, n, true));
+    if (env_legal) d_e = arena_take<uint8_t>(a, n);
+    if (agent_legal) d_g = arena_take<uint8_t>(a, n);
+    G2048_TRY(g2048_legal_masks(d_b, d_e, d_g, n, a->stream));
+    G2048_TRY(to_host(a, env_legal, d_e, n));
+    G2048_TRY(to_host(a, agent_legal, d_g, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t n)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_evaluate: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<int32_t>(n) + arena_bytes<double>(3 * n)));
+    uint64_t *d_b; int32_t *d_f = nullptr; double *d_u = nullptr;
+    G2048_TRY(to_device(a, &d_b, boards, n, true));
+    if (fast) d_f = arena_take<int32_t>(a, n);
+    if (full) d_u = arena_take<double>(a, 3 * n);
+    G2048_TRY(g2048_evaluate(d_b, d_f, d_u, n, a->stream));
+    G2048_TRY(to_host(a, fast, d_f, n));
+    G2048_TRY(to_host(a, full, d_u, 3 * n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_t *call, uint32_t call0,
+                           uint8_t *action, float *prob, double *best_score, int32_t *nodes,
+                           int64_t n, int32_t beam_width, int32_t search_depth,
+                           int32_t early_thr, int32_t mid_thr, uint64_t seed, uint32_t game0)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !roots || !action) return set_error(G2048_EINVAL, "g2048_host_beam_search: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<uint8_t>(n) + arena_bytes<uint32_t>(n) +
+                                  arena_bytes<float>(n) + arena_bytes<double>(n) + arena_bytes<int32_t>(n)));
+    uint64_t *d_b; uint8_t *d_l = nullptr; uint32_t *d_c = nullptr; uint8_t *d_a; float *d_p; double *d_s; int32_t *d_n;
+    G2048_TRY(to_device(a, &d_b, roots, n, true));
+    if (legal) G2048_TRY(to_device(a, &d_l, legal, n, true));
+    if (call) G2048_TRY(to_device(a, &d_c, call, n, true));
+    d_a = arena_take<uint8_t>(a, n);
+    d_p = arena_take<float>(a, n);
+    d_s = arena_take<double>(a, n);
+    d_n = arena_take<int32_t>(a, n);
+    G2048_TRY(g2048_beam_search(d_b, d_l, d_c, call0, d_a, d_p, d_s, d_n, n, beam_width, search_depth, early_thr, mid_thr,
+                                seed, game0, a->stream));
+    G2048_TRY(to_host(a, action, d_a, n));
+    G2048_TRY(to_host(a, prob, d_p, n));
+    G2048_TRY(to_host(a, best_score, d_s, n));
+    G2048_TRY(to_host(a, nodes, d_n, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
+                          int32_t early_thr, int32_t mid_thr, int32_t max_moves, uint64_t seed, uint32_t game0,
+                          int32_t *score, uint8_t *highest_exp, int32_t *moves, int32_t *valid, int32_t *invalid,
+                          int32_t *milestone, int64_t *nodes, uint64_t *final_board, int64_t *stats)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0) return set_error(G2048_EINVAL, "g2048_host_play_games: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, 4 * arena_bytes<int32_t>(n) + arena_bytes<uint8_t>(n) + arena_bytes<int32_t>(8 * n) +
+                                  arena_bytes<int64_t>(n) + arena_bytes<uint64_t>(n) + arena_bytes<int64_t>(G2048_STATS_LEN)));
+    int32_t *d_s = arena_take<int32_t>(a, n);
+    uint8_t *d_h = arena_take<uint8_t>(a, n);
+    int32_t *d_m = arena_take<int32_t>(a, n);
+    int32_t *d_v = arena_take<int32_t>(a, n);
+    int32_t *d_i = arena_take<int32_t>(a, n);
+    int32_t *d_ms = arena_take<int32_t>(a, 8 * n);
+    int64_t *d_n = arena_take<int64_t>(a, n);
+    uint64_t *d_f = arena_take<uint64_t>(a, n);
+    int64_t *d_st = arena_take<int64_t>(a, G2048_STATS_LEN);
+    G2048_TRY(g2048_play_games(n, beam_width, search_depth, early_thr, mid_thr, max_moves, seed, game0,
+                               d_s, d_h, d_m, d_v, d_i, d_ms, d_n, d_f, a->stream));
+    if (stats) {
+        G2048_CUDA(cudaMemsetAsync(d_st, 0, sizeof(int64_t) * G2048_STATS_LEN, a->stream));
+        G2048_TRY(g2048_stats_reduce(d_s, d_h, d_m, d_v, d_i, d_ms, d_n, n, d_st, a->stream));
+    }
+    G2048_TRY(to_host(a, score, d_s, n));
+    G2048_TRY(to_host(a, highest_exp, d_h, n));
+    G2048_TRY(to_host(a, moves, d_m, n));
+    G2048_TRY(to_host(a, valid, d_v, n));
+    G2048_TRY(to_host(a, invalid, d_i, n));
+    G2048_TRY(to_host(a, milestone, d_ms, 8 * n));
+    G2048_TRY(to_host(a, nodes, d_n, n));
+    G2048_TRY(to_host(a, final_board, d_f, n));
+    G2048_TRY(to_host(a, stats, d_st, G2048_STATS_LEN));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+/*
+ * g2048.h -- C ABI of libg2048 (B200 / sm_100a batched 2048 engine).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (vivek-tiwari-vt/2048-Using-Reinforcement-Learning) is pure Python and has no
+ * FFI of its own; each entry point below names the reference method(s) it
+ * replaces (env = environment/game_2048.py, agent = agents/beam_search_agent.py)
+ * and INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  `g2048_*` take DEVICE pointers and a CUDA
+ *    stream handle (`void*` = cudaStream_t, NULL = default stream); they enqueue
+ *    and return without synchronising.  `g2048_host_*` take HOST pointers, do
+ *    their own H2D/D2H copies and return after the results are in host memory.
+ *  - The caller owns every buffer.  The library allocates only its lookup
+ *    tables (g2048_init) and, for g2048_host_*, internal staging buffers.
+ *  - Return value: 0 on success, a negative G2048_E* code otherwise;
+ *    g2048_last_error() gives a message.  Nothing throws across the boundary.
+ *  - Board: uint64, cell (r,c) = nibble 4r+c = log2(tile), 0 = empty
+ *    (row r = bits [16r,16r+16), LEFT moves towards nibble 0 of a row).
+ *  - Actions 0 LEFT, 1 UP, 2 RIGHT, 3 DOWN (env:11-16); any other value is a
+ *    no-op / invalid move, as in env:97-114.
+ *  - Random spawns come from Philox4x32-10, counter = (block, call, game, domain),
+ *    key = seed; env i of a batch is game `game0 + i` (DESIGN.md "Random streams").
+ *  - Optional outputs may be NULL.
+ */
+#ifndef G2048_H
+#define G2048_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2048_ABI_VERSION 1
+
+enum {
+    G2048_OK        = 0,
+    G2048_EINVAL    = -1,   /* bad argument (NULL required pointer, n < 0, width out of range ...) */
+    G2048_ENOTINIT  = -2,   /* g2048_init not called for the current device */
+    G2048_ECUDA     = -3,   /* a CUDA runtime call failed, see g2048_last_error() */
+    G2048_ENODEVICE = -4    /* no CUDA device: there is no CPU fallback */
+};
+
+#define G2048_MAX_BEAM_WIDTH 32
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int         g2048_abi_version(void);
+/* Builds the row tables and uploads them to `device`.  Idempotent per device. */
+int         g2048_init(int device);
+/* Makes `device` (already initialised) the one the calling thread's next calls run on. */
+int         g2048_set_device(int device);
+const char *g2048_last_error(void);
+/* Sticky count of merges that would have produced a 65536 tile (nibble saturation;
+ * the reference's int32 board has no ceiling, env:149).  Synchronises `stream`. */
+int         g2048_overflow_count(uint64_t *count, void *stream);
+
+/* ---- board format ------------------------------------------------------- */
+/* int32[n][16] tile values (env.get_state(), env:50-57)  <->  packed boards */
+int g2048_pack(const int32_t *values, uint64_t *boards, int64_t n, void *stream);
+int g2048_unpack(const uint64_t *boards, int32_t *values, int64_t n, void *stream);
+/* float32[n][16] observation log2(tile)/15, 0 for empty (agents/ppo_agent.py:184-195) */
+int g2048_observe(const uint64_t *boards, float *obs, int64_t n, void *stream);
+/* Synthetic mid-game boards: cell empty w.p. ~0.3 else 2^U{1..11} (bench workloads). */
+int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t game0, void *stream);
+
+/* ---- environment (environment/game_2048.py) ------------------------------ */
+/* Game2048Env.reset (env:29-48): zero board, score 0, two spawns continuing the env
+ * stream at spawn_ctr[i], highest = max exponent.  spawn_ctr is in/out. */
+int g2048_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                    int64_t n, uint64_t seed, uint32_t game0, void *stream);
+
+/* Game2048Env.step (env:170-210) for n independent envs.
+ *   in/out : boards, score (cumulative merge score), highest_exp (log2 highest_tile), spawn_ctr
+ *   in     : actions[n]; spawn_inject NULL or uint32[n][2] raw (position word, value word)
+ *            used instead of the env stream (spawn_ctr is then left untouched)
+ *   out    : reward (float64, bit-exact env:212-277), reward32, score_delta,
+ *            valid (info["valid_move"]), legal (get_valid_moves of the NEW board, bit a),
+ *            done (is_game_over, env:279-288).  All optional. */
+int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
+                   int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                   double *reward, float *reward32, int32_t *score_delta,
+                   uint8_t *valid, uint8_t *legal, uint8_t *done,
+                   int64_t n, uint64_t seed, uint32_t game0, void *stream);
+
+/* Game2048Env.get_valid_moves (env:69-95) -> env_legal; BeamSearchAgent._check_valid_moves
+ * (agent:183-192, DOWN quirk included) -> agent_legal.  Bit a = action a.  Either may be NULL. */
+int g2048_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal,
+                      int64_t n, void *stream);
+
+/* Fused rollout: `steps` consecutive env.step calls per env with boards held in registers.
+ * Action of env i at step t0+s comes from the Philox action stream (uniform in 0..3);
+ * when an env reports done it is reset (env.reset, same env stream) and episodes[i] += 1.
+ * reward_sum[i] += the float64 rewards in step order.  All state arrays are in/out. */
+int g2048_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                      double *reward_sum, int32_t *episodes,
+                      int64_t n, int32_t steps, uint32_t t0, uint64_t seed, uint32_t game0, void *stream);
+
+/* ---- beam search (agents/beam_search_agent.py) --------------------------- */
+/* _fast_evaluate (agent:280-314) -> fast[n] (exact integer);
+ * _evaluate_state (agent:316-403) -> full[n][3] float64 for phases early/mid/late, bit-exact. */
+int g2048_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t n, void *stream);
+
+/* BeamSearchAgent.get_action (agent:71-181) for n independent root boards, one warp per root.
+ *   legal    : NULL (valid_moves=None -> the agent's own legality) or uint8[n] bit masks
+ *              (valid_moves passed by the caller, e.g. env.get_valid_moves())
+ *   call     : NULL or uint32[n] per-root call index for the beam stream; else `call0` for all
+ *   out      : action[n], prob[n] (0.5 / 1.0 as the reference returns), best_score[n]
+ *              (score of candidates[0] at the last level), nodes[n] (evaluated children)
+ *   beam_width 1..G2048_MAX_BEAM_WIDTH, search_depth >= 1,
+ *   early_thr / mid_thr = agent.early_game_threshold / mid_game_threshold (512 / 1024). */
+int g2048_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_t *call, uint32_t call0,
+                      uint8_t *action, float *prob, double *best_score, int32_t *nodes,
+                      int64_t n, int32_t beam_width, int32_t search_depth,
+                      int32_t early_thr, int32_t mid_thr,
+                      uint64_t seed, uint32_t game0, void *stream);
+
+/* Whole games, evaluate_beam_search.run_game (evaluate_beam_search.py:16-98): Game2048Env(),
+ * reset(), then get_action(state) / env.step(action) until done or max_moves.
+ * Per-game outputs (all optional): score, highest_exp, moves, valid, invalid,
+ * milestone[n][8] = first move count at which highest_tile >= 64,128,...,8192 (-1 never),
+ * nodes (evaluated children), final_board. */
+int g2048_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
+                     int32_t early_thr, int32_t mid_thr, int32_t max_moves,
+                     uint64_t seed, uint32_t game0,
+                     int32_t *score, uint8_t *highest_exp, int32_t *moves, int32_t *valid, int32_t *invalid,
+                     int32_t *milestone, int64_t *nodes, uint64_t *final_board, void *stream);
+
+/* Statistics of a batch of finished games (evaluate_beam_search.py:127-135,201-213):
+ * stats[0..17]  histogram of highest_exp 0..17, [18] sum score, [19] sum moves, [20] sum valid,
+ * [21] sum invalid, [22] games, [23] max score, [24..31] games that reached 64..8192,
+ * [32] sum nodes.  int64[G2048_STATS_LEN], ADDED to (max'ed into [23]) the existing
+ * contents so that per-rank vectors can be all-reduced (sum; [23] with max). */
+#define G2048_STATS_LEN 40
+#define G2048_STATS_MAXSCORE 23
+int g2048_stats_reduce(const int32_t *score, const uint8_t *highest_exp, const int32_t *moves,
+                       const int32_t *valid, const int32_t *invalid, const int32_t *milestone,
+                       const int64_t *nodes, int64_t n, int64_t *stats, void *stream);
+
+/* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
+/* What a reference-side binding calls with numpy buffers; see INTEGRATION.md. */
+int g2048_host_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
+                        int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                        double *reward, int32_t *score_delta, uint8_t *valid, uint8_t *legal, uint8_t *done,
+                        int64_t n, uint64_t seed, uint32_t game0);
+int g2048_host_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                         int64_t n, uint64_t seed, uint32_t game0);
+int g2048_host_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                           double *reward_sum, int32_t *episodes,
+                           int64_t n, int32_t steps, uint32_t t0, uint64_t seed, uint32_t game0);
+int g2048_host_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n);
+int g2048_host_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t n);
+int g2048_host_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_t *call, uint32_t call0,
+                           uint8_t *action, float *prob, double *best_score, int32_t *nodes,
+                           int64_t n, int32_t beam_width, int32_t search_depth,
+                           int32_t early_thr, int32_t mid_thr, uint64_t seed, uint32_t game0);
+int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
+                          int32_t early_thr, int32_t mid_thr, int32_t max_moves,
+                          uint64_t seed, uint32_t game0,
+                          int32_t *score, uint8_t *highest_exp, int32_t *moves, int32_t *valid, int32_t *invalid,
+                          int32_t *milestone, int64_t *nodes, uint64_t *final_board, int64_t *stats);
+
+/* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
+uint64_t g2048_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2048_H */

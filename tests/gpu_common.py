@@ -1,0 +1,74 @@
+"""Helpers shared by the `-m gpu` parity tests: numpy wrappers over the host-buffer C ABI."""
+import ctypes as C
+
+import numpy as np
+
+import g2048_b200 as G
+from g2048_b200 import _lib
+
+P = _lib.np_ptr
+
+
+def lib():
+    return _lib.use_device(0)
+
+
+def host_reset(n, seed, game0=0, spawn_ctr=None):
+    b = np.zeros(n, np.uint64); s = np.zeros(n, np.int32); h = np.zeros(n, np.uint8)
+    c = np.zeros(n, np.uint32) if spawn_ctr is None else spawn_ctr
+    _lib.check(lib().g2048_host_env_reset(P(b), P(s), P(h), P(c), n, seed, game0))
+    return b, s, h, c
+
+
+def host_step(b, a, s, h, c, seed, game0=0, inject=None):
+    n = b.shape[0]
+    r = np.zeros(n, np.float64); sd = np.zeros(n, np.int32)
+    v = np.zeros(n, np.uint8); l = np.zeros(n, np.uint8); d = np.zeros(n, np.uint8)
+    _lib.check(lib().g2048_host_env_step(P(b), P(a), P(inject), P(s), P(h), P(c), P(r), P(sd), P(v), P(l), P(d),
+                                         n, seed, game0))
+    return r, sd, v, l, d
+
+
+def host_rollout(b, s, h, c, rs, ep, steps, t0, seed, game0=0):
+    _lib.check(lib().g2048_host_env_rollout(P(b), P(s), P(h), P(c), P(rs), P(ep), b.shape[0], steps, t0, seed, game0))
+
+
+def host_legal(b):
+    e = np.zeros(b.shape[0], np.uint8); a = np.zeros(b.shape[0], np.uint8)
+    _lib.check(lib().g2048_host_legal_masks(P(b), P(e), P(a), b.shape[0]))
+    return e, a
+
+
+def host_evaluate(b):
+    f = np.zeros(b.shape[0], np.int32); u = np.zeros((b.shape[0], 3), np.float64)
+    _lib.check(lib().g2048_host_evaluate(P(b), P(f), P(u), b.shape[0]))
+    return f, u
+
+
+def host_beam(b, W, D, seed, game0=0, call0=0, legal=None, call=None, early=512, mid=1024):
+    n = b.shape[0]
+    a = np.zeros(n, np.uint8); p = np.zeros(n, np.float32); s = np.zeros(n, np.float64); k = np.zeros(n, np.int32)
+    _lib.check(lib().g2048_host_beam_search(P(b), P(legal), P(call), call0, P(a), P(p), P(s), P(k), n, W, D, early, mid,
+                                            seed, game0))
+    return a, p, s, k
+
+
+def host_play(n, W, D, seed, game0=0, max_moves=10000, early=512, mid=1024):
+    out = dict(score=np.zeros(n, np.int32), highest=np.zeros(n, np.uint8), moves=np.zeros(n, np.int32),
+               valid=np.zeros(n, np.int32), invalid=np.zeros(n, np.int32), milestone=np.zeros((n, 8), np.int32),
+               nodes=np.zeros(n, np.int64), final=np.zeros(n, np.uint64), stats=np.zeros(_lib.STATS_LEN, np.int64))
+    _lib.check(lib().g2048_host_play_games(n, W, D, early, mid, max_moves, seed, game0, P(out["score"]), P(out["highest"]),
+                                           P(out["moves"]), P(out["valid"]), P(out["invalid"]), P(out["milestone"]),
+                                           P(out["nodes"]), P(out["final"]), P(out["stats"])))
+    return out
+
+
+def synthetic(orc, n, seed, game0=0):
+    """(values int32[n,16], packed uint64[n]) from the oracle's generator."""
+    vals = np.stack([orc.synthetic_board(seed, game0 + g) for g in range(n)])
+    return vals, G.pack_boards(vals)
+
+
+def exps(values):
+    v = np.asarray(values, dtype=np.int64)
+    return np.where(v > 0, np.log2(np.maximum(v, 1)).astype(np.int64), 0)

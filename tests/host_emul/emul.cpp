@@ -1,0 +1,131 @@
+// Host emulation of the packed-board device primitives (csrc/board.cuh, csrc/env.cuh).
+// TEST INFRASTRUCTURE ONLY: lets the CPU test-suite check the SWAR arithmetic of the CUDA
+// kernels against the oracle without a GPU.  It is never loaded by the product.
+#include <stdint.h>
+#include <algorithm>
+#include <cmath>
+
+#define G2048_HOST_EMUL 1
+#define __device__
+#define __host__
+#define __forceinline__ inline
+
+using std::max;
+using std::min;
+
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u));
+}
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint64_t v = (((uint64_t)b) << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t sel = (s >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(v >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b)
+{
+    uint32_t lo = std::max(a & 0xFFFFu, b & 0xFFFFu), hi = std::max(a >> 16, b >> 16);
+    return lo | (hi << 16);
+}
+static inline uint32_t __vsadu4(uint32_t a, uint32_t b)
+{
+    uint32_t s = 0;
+    for (int i = 0; i < 4; ++i) {
+        int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF;
+        s += (uint32_t)(x > y ? x - y : y - x);
+    }
+    return s;
+}
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+
+#include "../../2048-using-reinforcement-learning_b200/csrc/env.cuh"
+#include "../../2048-using-reinforcement-learning_b200/csrc/row_tables.h"
+
+using namespace g2048;
+
+// the product's own table builder (csrc/row_tables.h), so the tables are under test too
+static uint16_t g_row[65536];
+static uint8_t g_code[65536];
+static unsigned long long g_overflow;
+
+extern "C" {
+
+void emul_init(void) { build_row_tables(g_row, g_code); }
+uint32_t emul_row(uint32_t r) { return g_row[r & 0xFFFF]; }
+uint32_t emul_code(uint32_t r) { return g_code[r & 0xFFFF]; }
+uint64_t emul_transpose(uint64_t b) { return transpose(Board(b)).u64(); }
+uint64_t emul_flip_rows(uint64_t b) { return flip_rows(Board(b)).u64(); }
+uint64_t emul_flip_row_order(uint64_t b) { return flip_row_order(Board(b)).u64(); }
+uint64_t emul_rot180(uint64_t b) { return rot180(Board(b)).u64(); }
+uint64_t emul_env_move(uint64_t b, uint32_t action) { return env_move<false>(Board(b), action, g_row).u64(); }
+uint32_t emul_move_score(uint64_t b, uint32_t action)
+{
+    uint32_t sat;
+    return action < 4 ? decode_score(merge_codes<false>(to_line(Board(b), action), g_code), &sat) : 0;
+}
+uint32_t emul_env_legal(uint64_t b) { return env_legal_mask(Board(b)); }
+uint32_t emul_agent_legal(uint64_t b)
+{
+    Board x(b);
+    uint32_t m = env_legal_mask(x);
+    return (m & 7u) | ((rot180(env_move<false>(x, 3u, g_row)) != x) ? 8u : 0u);
+}
+uint64_t emul_agent_child(uint64_t b, uint32_t action)
+{
+    Board x(b);
+    if (action == 3) {
+        Board t = transpose(x);
+        return transpose(flip_row_order(move_left<false>(flip_rows(t), g_row))).u64();
+    }
+    return env_move<false>(x, action, g_row).u64();
+}
+int emul_count_empty(uint64_t b) { return count_empty(Board(b)); }
+uint32_t emul_max_exponent(uint64_t b) { return max_exponent(Board(b)); }
+uint64_t emul_place_tile(uint64_t b, uint32_t pw, uint32_t vw) { Board x(b); place_tile(x, pw, vw); return x.u64(); }
+int emul_fast_eval(uint64_t b) { Board x(b); return fast_eval(x, count_empty(x), max_exponent(x)); }
+double emul_full_eval(uint64_t b, int phase) { Board x(b); return full_eval(x, count_empty(x), max_exponent(x), phase); }
+void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)
+{
+    Philox4 p = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out[i] = p.w[i];
+}
+uint32_t emul_random_action(uint64_t seed, uint32_t game, uint32_t t)
+{
+    return random_action((uint32_t)seed, (uint32_t)(seed >> 32), game, t);
+}
+
+struct EmulEnv { uint64_t board; int32_t score; uint32_t highest; uint32_t spawn_ctr; };
+struct EmulStep { double reward; uint32_t score_delta; int32_t valid; int32_t done; };
+
+void emul_env_reset(EmulEnv *e, uint64_t seed, uint32_t game)
+{
+    EnvState s; s.spawn_ctr = e->spawn_ctr;
+    env_reset(s, (uint32_t)seed, (uint32_t)(seed >> 32), game);
+    e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
+}
+void emul_env_step(EmulEnv *e, uint32_t action, const uint32_t *inject, uint64_t seed, uint32_t game, EmulStep *o)
+{
+    EnvState s; s.board = Board(e->board); s.score = e->score; s.highest = e->highest; s.spawn_ctr = e->spawn_ctr;
+    StepResult r = env_step<false, false, true>(s, action, g_row, g_code, (uint32_t)seed, (uint32_t)(seed >> 32), game,
+                                                inject, &g_overflow);
+    e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
+    o->reward = r.reward; o->score_delta = r.score_delta; o->valid = r.valid; o->done = r.done;
+}
+unsigned long long emul_overflow(void) { return g_overflow; }
+
+}  // extern "C"

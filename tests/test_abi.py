@@ -1,0 +1,64 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/g2048.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import g2048_b200 as G
+    if not os.path.exists(G.LIB_PATH):
+        G.build_library()
+    return G
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "g2048.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(g2048_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(built):
+    lib = C.CDLL(built.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/g2048.h but not exported"
+    assert set(names) == set(built.EXPORTS)          # the ctypes binding covers the whole header
+
+
+def test_abi_version_and_error_path_without_gpu(built):
+    import torch
+    from g2048_b200 import _lib
+    lib = _lib.load()
+    assert lib.g2048_abi_version() == 1
+    if not torch.cuda.is_available():
+        # no CPU fallback: everything fails loudly
+        assert lib.g2048_init(0) == -4
+        assert b"no CUDA device" in lib.g2048_last_error()
+        with pytest.raises(built.G2048Error):
+            built.Game2048Env()
+        with pytest.raises(built.G2048Error):
+            built.BatchedGame2048Env(4, "cpu")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "2048-using-reinforcement-learning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_shard_range_covers_everything():
+    import g2048_b200 as G
+    for total in (1, 7, 100, 10000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [G.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))

@@ -1,0 +1,132 @@
+"""GPU parity, beam-search side: warp-per-game search kernel vs the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import g2048_b200 as G          # noqa: E402
+from tests import gpu_common as X   # noqa: E402
+
+SEED = 0x0B200B200B200
+
+
+def test_golden_get_action(golden):
+    seed = golden["seed"]
+    for c in golden["beam"]:
+        b = np.array([G.pack_board(c["board"])], np.uint64)
+        legal = None
+        if c["valid_moves"] is not None:
+            legal = np.array([sum(int(v) << k for k, v in enumerate(c["valid_moves"]))], np.uint8)
+        a, p, s, k = X.host_beam(b, c["W"], c["D"], seed, game0=c["game"], call0=c["call"], legal=legal)
+        assert (int(a[0]), float(p[0])) == (c["action"], c["prob"]), c
+
+
+@pytest.mark.parametrize("W,D,n", [(15, 20, 1500), (20, 40, 1200), (10, 15, 600), (32, 12, 400), (1, 30, 300),
+                                   (7, 3, 300), (20, 1, 200)])
+def test_batched_get_action_vs_oracle(orc, W, D, n):
+    vals, packed = X.synthetic(orc, n, SEED, 1000 * W)
+    a, p, s, k = X.host_beam(packed, W, D, SEED, game0=1000 * W, call0=5)
+    oa, op, on, ob = orc.beam_batch(vals, W, D, SEED, 1000 * W, 5)
+    assert (a == oa).all(), np.flatnonzero(a != oa)[:10]
+    assert (p == op).all() and (k == on).all()
+    assert (s == ob).all()                     # float64 best score, bit-exact (fast: integer; full: fp64 order)
+
+
+def test_caller_supplied_valid_moves_and_per_root_calls(orc):
+    vals, packed = X.synthetic(orc, 600, SEED, 31)
+    legal = np.array([orc.env_legal_mask(v) for v in vals], np.uint8)       # env.get_valid_moves(), as train.py passes
+    call = (np.arange(600) % 7).astype(np.uint32)
+    a, p, s, k = X.host_beam(packed, 15, 20, SEED, game0=31, legal=legal, call=call)
+    for i in range(600):
+        o = orc.beam_get_action(vals[i], int(legal[i]), 15, 20, SEED, 31 + i, int(call[i]))
+        assert (a[i], p[i], k[i]) == (o.action, o.prob, o.nodes), i
+    # a mask the agent disagrees with everywhere -> agent:126-128 random.choice fallback, prob 0.5
+    dead = np.array([G.pack_board([[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 8]])], np.uint64)
+    a, p, s, k = X.host_beam(dead, 10, 15, SEED, legal=np.array([0b0101], np.uint8))
+    o = orc.beam_get_action(G.unpack_board(int(dead[0])), 0b0101, 10, 15, SEED, 0, 0)
+    assert (a[0], p[0]) == (o.action, o.prob) and p[0] == 0.5
+
+
+def test_early_boards_from_play(orc):
+    """>= 10 empties -> min(d-5, 10) levels; few candidates per level (ragged beams)."""
+    n = 400
+    b, s, h, c = X.host_reset(n, SEED, 500)
+    rs = np.zeros(n); ep = np.zeros(n, np.int32)
+    X.host_rollout(b, s, h, c, rs, ep, 6, 0, SEED, 500)
+    vals = G.unpack_boards(b)
+    for W, D in ((15, 20), (20, 40), (3, 8)):
+        a, p, sc, k = X.host_beam(b, W, D, SEED, game0=500)
+        oa, op, on, ob = orc.beam_batch(vals, W, D, SEED, 500, 0)
+        assert (a == oa).all() and (p == op).all() and (k == on).all() and (sc == ob).all()
+
+
+def test_thresholds_change_phase(orc):
+    vals, packed = X.synthetic(orc, 300, SEED, 9000)
+    a, p, s, k = X.host_beam(packed, 12, 9, SEED, game0=9000, early=64, mid=256)
+    for i in range(300):
+        o = orc.beam_get_action(vals[i], None, 12, 9, SEED, 9000 + i, 0, early_thr=64, mid_thr=256)
+        assert (a[i], k[i], s[i]) == (o.action, o.nodes, o.best_score)
+
+
+def test_golden_full_games(golden):
+    for g in golden["games"]:
+        out = X.host_play(1, g["W"], g["D"], golden["seed"], game0=g["game"], max_moves=g["max_moves"])
+        assert (out["score"][0], 1 << int(out["highest"][0]), out["moves"][0], out["valid"][0], out["invalid"][0]) == \
+            (g["score"], g["highest_tile"], g["moves"], g["valid"], g["invalid"])
+        assert out["final"][0] == G.pack_board(g["final"])
+
+
+@pytest.mark.parametrize("W,D,n,cap", [(4, 6, 96, 10000), (10, 12, 40, 400), (15, 20, 24, 120)])
+def test_play_games_vs_oracle(orc, W, D, n, cap):
+    out = X.host_play(n, W, D, SEED, game0=70, max_moves=cap)
+    ref = orc.play_games(SEED, 70, n, W, D, max_moves=cap)
+    for i in range(n):
+        r = ref[i]
+        assert (out["score"][i], 1 << int(out["highest"][i]), out["moves"][i], out["valid"][i], out["invalid"][i],
+                out["nodes"][i]) == (r.score, r.highest_tile, r.moves, r.valid_moves, r.invalid_moves, r.nodes), i
+        assert list(out["milestone"][i]) == list(r.milestone_move)
+    st = out["stats"]
+    assert st[22] == n and st[18] == out["score"].astype(np.int64).sum() and st[23] == out["score"].max()
+    assert st[19] == out["moves"].sum() and st[32] == out["nodes"].sum()
+    hist = np.bincount(out["highest"], minlength=18)
+    assert (st[:18] == hist[:18]).all()
+    assert [st[24 + m] for m in range(8)] == [(out["milestone"][:, m] >= 0).sum() for m in range(8)]
+
+
+def test_sharding_invariance(orc):
+    """Per-game results do not depend on how games are split over launches / ranks."""
+    whole = X.host_play(48, 6, 8, SEED, game0=0, max_moves=300)
+    parts = [X.host_play(hi - lo, 6, 8, SEED, game0=lo, max_moves=300)
+             for lo, hi in (G.shard_range(48, r, 4) for r in range(4))]
+    for key in ("score", "highest", "moves", "valid", "invalid", "nodes", "final"):
+        assert (np.concatenate([p[key] for p in parts]) == whole[key]).all()
+    total = sum(p["stats"] for p in parts)
+    total[23] = max(p["stats"][23] for p in parts)
+    assert (total == whole["stats"]).all()
+
+
+def test_facade_agent_and_protocol(orc, tmp_path):
+    agent = G.BeamSearchAgent(beam_width=15, search_depth=20, seed=SEED)
+    env = G.Game2048Env(seed=SEED, game_id=11)
+    state = env.reset()
+    game = agent._game
+    for t in range(25):                      # train.py:55-107 call pattern
+        vm = env.get_valid_moves()
+        before = state.copy()
+        a, prob = agent.get_action(state, vm)
+        assert (state == before).all()       # input is not mutated
+        mask = sum(int(v) << k for k, v in enumerate(vm))
+        o = orc.beam_get_action(state, mask, 15, 20, SEED, game, t)
+        assert (a, prob) == (o.action, o.prob)
+        state, r, done, info = env.step(a)
+        agent.remember(before, a, prob, r, state, done); agent.update()
+        if done:
+            break
+    a2, _ = agent.get_action(state.reshape(4, 4).astype(np.int64))      # 2-D input, other dtype, no valid_moves
+    o = orc.beam_get_action(state, None, 15, 20, SEED, game, agent._calls - 1)
+    assert a2 == o.action
+    path = tmp_path / "ckpt" / "beam.pth"
+    agent.save(str(path))
+    loaded = G.BeamSearchAgent.load(str(path))
+    assert (loaded.beam_width, loaded.search_depth, loaded.early_game_threshold) == (15, 20, 512)
+    assert (tmp_path / "ckpt" / "beam_search_config_readme_15_20.txt").exists()

@@ -1,0 +1,215 @@
+"""GPU parity, environment side: CUDA kernels through the C ABI vs the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import g2048_b200 as G          # noqa: E402
+from tests import gpu_common as X   # noqa: E402
+
+SEED = 0x0B200B200B200
+
+
+def test_step_kats_from_reference(golden):
+    for k in golden["step_kats"]:
+        b = np.array([G.pack_board(k["board"])], np.uint64)
+        a = np.array([k["action"]], np.uint8); s = np.zeros(1, np.int32)
+        h = np.array([int(k["highest_tile"]).bit_length() - 1], np.uint8); c = np.zeros(1, np.uint32)
+        inj = np.array([k["inject"]], np.uint32)
+        r, sd, v, l, d = X.host_step(b, a, s, h, c, golden["seed"], inject=inj)
+        assert b[0] == G.pack_board(k["out"])
+        assert r[0] == float.fromhex(k["reward"])
+        assert bool(d[0]) == k["done"] and bool(v[0]) == k["valid"] and s[0] == k["score"]
+        assert (1 << int(h[0])) == k["highest_after"] and c[0] == 0
+
+
+def test_golden_trajectories_batched(golden):
+    seed = golden["seed"]
+    trajs = golden["trajectories"]
+    n = len(trajs)
+    assert [t["game"] for t in trajs] == list(range(n))
+    b, s, h, c = X.host_reset(n, seed)                  # constructor reset
+    b, s, h, c = X.host_reset(n, seed, spawn_ctr=c)     # explicit reset
+    for i, t in enumerate(trajs):
+        assert b[i] == G.pack_board(t["start"])
+    for step in range(len(trajs[0]["steps"])):
+        a = np.array([t["steps"][step]["a"] for t in trajs], np.uint8)
+        r, sd, v, l, d = X.host_step(b, a, s, h, c, seed)
+        for i, t in enumerate(trajs):
+            st = t["steps"][step]
+            assert b[i] == G.pack_board(st["board"]), (i, step)
+            assert r[i] == float.fromhex(st["reward"]), (i, step)
+            assert bool(d[i]) == st["done"] and bool(v[i]) == st["valid"] and s[i] == st["score"]
+            assert (1 << int(h[i])) == st["highest"]
+            assert [bool(l[i] >> k & 1) for k in range(4)] == st["legal"]
+            if st["done"]:          # harness-side reset of that env only
+                bi, si, hi, ci = X.host_reset(1, seed, game0=i, spawn_ctr=c[i:i + 1].copy())
+                b[i], s[i], h[i], c[i] = bi[0], si[0], hi[0], ci[0]
+                assert b[i] == G.pack_board(st["reset_to"])
+    for i, t in enumerate(trajs):
+        assert c[i] == t["spawns"]
+
+
+def _oracle_state(orc, n, seed, game0):
+    boards = np.zeros((n, 16), np.int32); score = np.zeros(n, np.int64); hi = np.zeros(n, np.int32)
+    ctr = np.zeros(n, np.uint32)
+    for i in range(n):
+        e = orc.Env(seed, game0 + i)       # ctor reset
+        e.reset()
+        boards[i] = e.board; hi[i] = e.s.highest_tile; ctr[i] = e.s.spawn_ctr
+    return boards, score, hi, ctr
+
+
+@pytest.mark.parametrize("n,steps,game0", [(4096, 300, 0), (777, 1000, 123456), (1, 50, 9), (33, 1, 5)])
+def test_rollout_vs_oracle(orc, n, steps, game0):
+    ob, osc, ohi, octr = _oracle_state(orc, n, SEED, game0)
+    ors = np.zeros(n, np.float64); oep = np.zeros(n, np.int32)
+    b, s, h, c = X.host_reset(n, SEED, game0)
+    b, s, h, c = X.host_reset(n, SEED, game0, spawn_ctr=c)
+    assert (b == G.pack_boards(ob)).all()
+    rs = np.zeros(n, np.float64); ep = np.zeros(n, np.int32)
+    # two chunks: exercises t0 and the in/out state contract
+    first = steps // 3
+    for (t0, k) in ((0, first), (first, steps - first)):
+        X.host_rollout(b, s, h, c, rs, ep, k, t0, SEED, game0)
+        orc.rollout(ob, osc, ohi, octr, ors, oep, k, t0, SEED, game0)
+    assert (b == G.pack_boards(ob)).all()
+    assert (s == osc).all() and ((1 << h.astype(np.int64)) == ohi).all() and (c == octr).all()
+    assert (rs == ors).all()            # float64 sums of bit-exact rewards, same order
+    assert (ep == oep).all()
+    if n >= 777:
+        assert ep.sum() > 0             # resets were exercised
+
+
+def test_per_step_api_vs_oracle_all_outputs(orc):
+    n, steps = 1500, 120
+    envs = [orc.Env(SEED, 40 + i) for i in range(n)]
+    for e in envs:
+        e.reset()
+    b, s, h, c = X.host_reset(n, SEED, 40)
+    b, s, h, c = X.host_reset(n, SEED, 40, spawn_ctr=c)
+    rng = np.random.default_rng(1)
+    for t in range(steps):
+        a = rng.integers(0, 5, n).astype(np.uint8)          # includes the out-of-range action 4
+        r, sd, v, l, d = X.host_step(b, a, s, h, c, SEED, 40)
+        for i in (0, 1, 2, 3, 500, 999, 1499):
+            ob, orw, od, oi = envs[i].step(int(a[i]))
+            assert b[i] == G.pack_board(ob) and r[i] == orw and bool(d[i]) == od
+            assert bool(v[i]) == oi["valid_move"] and s[i] == oi["score"] and sd[i] == oi["score_delta"]
+            assert l[i] == orc.env_legal_mask(ob)
+
+
+def test_legal_masks_and_evaluate_vs_oracle(orc, golden):
+    vals, packed = X.synthetic(orc, 5000, SEED, 77)
+    extra = np.array([rec["board"] for rec in golden["boards"] if max(rec["board"]) <= 32768], np.int32)
+    vals = np.concatenate([vals, extra]); packed = np.concatenate([packed, G.pack_boards(extra)])
+    e, a = X.host_legal(packed)
+    f, u = X.host_evaluate(packed)
+    for i in range(0, vals.shape[0], 1):
+        assert e[i] == orc.env_legal_mask(vals[i]) and a[i] == orc.agent_legal_mask(vals[i]), vals[i]
+        if vals[i].max() > 0:
+            assert float(f[i]) == orc.fast_eval(vals[i])
+            assert tuple(u[i]) == tuple(orc.full_eval(vals[i], ph) for ph in range(3))
+    for rec in golden["boards"]:
+        if max(rec["board"]) > 32768 or "fast_eval" not in rec:
+            continue
+        p = np.array([G.pack_board(rec["board"])], np.uint64)
+        e1, a1 = X.host_legal(p); f1, u1 = X.host_evaluate(p)
+        assert [bool(e1[0] >> k & 1) for k in range(4)] == rec["env_legal"]
+        assert [bool(a1[0] >> k & 1) for k in range(4)] == rec["agent_legal"]
+        assert float(f1[0]) == float.fromhex(rec["fast_eval"])
+        assert [float(x) for x in u1[0]] == [float.fromhex(x) for x in rec["full_eval"]]
+
+
+def test_full_size_rollout_properties_and_sampled_parity(orc):
+    """BASELINE config 2: 65,536 boards x 2,000 random-policy steps on one GPU."""
+    n, steps = 65536, 2000
+    b, s, h, c = X.host_reset(n, SEED)
+    rs = np.zeros(n, np.float64); ep = np.zeros(n, np.int32)
+    X.host_rollout(b, s, h, c, rs, ep, steps, 0, SEED)
+    vals = G.unpack_boards(b)
+    # size-independent properties
+    assert (G.pack_boards(vals) == b).all()
+    assert ((vals > 0).sum(axis=1) >= 2).all()                      # a live board has >= 2 tiles
+    assert (X.exps(vals).max(axis=1) == h).all()                    # highest tile == board max
+    assert (c >= 2 * (ep + 1)).all() and np.isfinite(rs).all()
+    e, _ = X.host_legal(b)
+    assert (e != 0).all()                                           # finished games were reset
+    # sampled bit-exact parity: envs are independent and keyed by game id
+    lo, m = 30000, 768
+    ob = np.zeros((m, 16), np.int32); osc = np.zeros(m, np.int64); ohi = np.zeros(m, np.int32)
+    octr = np.zeros(m, np.uint32); ors = np.zeros(m, np.float64); oep = np.zeros(m, np.int32)
+    for i in range(m):
+        env = orc.Env(SEED, lo + i, ctor_reset=False)
+        env.reset()
+        ob[i] = env.board; ohi[i] = env.s.highest_tile; octr[i] = env.s.spawn_ctr
+    orc.rollout(ob, osc, ohi, octr, ors, oep, steps, 0, SEED, lo)
+    sl = slice(lo, lo + m)
+    assert (b[sl] == G.pack_boards(ob)).all() and (s[sl] == osc).all() and (c[sl] == octr).all()
+    assert (rs[sl] == ors).all() and (ep[sl] == oep).all()
+    assert G.overflow_count() == 0
+
+
+def test_device_pointer_api_matches_host_api():
+    import torch
+    n = 10000
+    env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=3)
+    env.reset()
+    b, s, h, c = X.host_reset(n, SEED, 3)
+    assert (env.boards_u64() == b).all()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(20):
+        a = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+        boards, reward, done, info = env.step(a)
+        r, sd, v, l, d = X.host_step(b, a.cpu().numpy(), s, h, c, SEED, 3)
+        assert (env.boards_u64() == b).all() and (reward.cpu().numpy() == r).all()
+        assert (done.cpu().numpy() == d).all() and (info["legal_mask"].cpu().numpy() == l).all()
+        assert (info["reward32"].cpu().numpy() == r.astype(np.float32)).all()
+    obs = env.observe().cpu().numpy()
+    assert np.allclose(obs, X.exps(G.unpack_boards(b)) / 15.0)
+    assert (env.values().cpu().numpy() == G.unpack_boards(b)).all()
+    env.rollout(64)
+    rs = np.zeros(n, np.float64); ep = np.zeros(n, np.int32)
+    X.host_rollout(b, s, h, c, rs, ep, 64, 20, SEED, 3)
+    assert (env.boards_u64() == b).all() and (env.reward_sum.cpu().numpy() == rs).all()
+
+
+def test_large_batch_uses_shared_table_kernel_and_agrees():
+    """n above the staging threshold takes the shared-memory-table kernel; same results."""
+    import torch
+    n = 148 * 4096 + 1234
+    big = G.BatchedGame2048Env(n, "cuda:0", seed=SEED)
+    big.reset()
+    small = G.BatchedGame2048Env(5000, "cuda:0", seed=SEED)
+    small.reset()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for t in range(12):
+        a = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+        big.step(a); small.step(a[:5000])
+        assert torch.equal(big.boards[:5000], small.boards)
+        assert torch.equal(big.reward[:5000], small.reward) and torch.equal(big.done[:5000], small.done)
+
+
+def test_facade_env_matches_oracle(orc):
+    env = G.Game2048Env(seed=SEED, game_id=321)
+    o = orc.Env(SEED, 321)
+    assert (env.reset() == o.reset()).all()
+    assert env.board.shape == (4, 4) and env.board.dtype == np.int32
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        a = int(rng.integers(0, 4))
+        vm = env.get_valid_moves()
+        assert vm == [bool(orc.env_legal_mask(o.board) >> k & 1) for k in range(4)]
+        s, r, d, info = env.step(a)
+        ob, orw, od, oi = o.step(a)
+        assert (s == ob).all() and float(r) == orw and d == od and isinstance(d, bool)
+        assert int(info["score"]) == oi["score"] and info["valid_move"] == oi["valid_move"]
+        assert int(info["highest_tile"]) == oi["highest_tile"]
+        assert env.is_game_over() == od
+        if d:
+            assert (env.reset() == o.reset()).all()
+    # callers may poke the board between calls (hybrid.py and tests do)
+    env.board = np.array([[2, 0, 0, 0], [4, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]], dtype=np.int32)
+    env.score = 0
+    s, r, d, info = env.step(0)
+    assert not info["valid_move"] and r == -0.5666666666666668

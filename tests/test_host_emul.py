@@ -1,0 +1,206 @@
+"""SWAR device primitives (csrc/board.cuh, csrc/env.cuh) compiled for the host with intrinsic
+stand-ins (tests/host_emul/emul.cpp) and checked against the C oracle -- no GPU needed.
+
+This is test infrastructure: it proves the packed-board arithmetic the kernels are made of.
+The kernels themselves are checked on the GPU by the `-m gpu` tests.
+"""
+import ctypes as C
+import importlib.util
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location(
+    "_g2048_packing", os.path.join(ROOT, "2048-using-reinforcement-learning_b200", "packing.py"))
+packing = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(packing)
+
+SEED = 0xA5A5F00D1234
+
+
+class EmulEnv(C.Structure):
+    _fields_ = [("board", C.c_uint64), ("score", C.c_int32), ("highest", C.c_uint32), ("spawn_ctr", C.c_uint32)]
+
+
+class EmulStep(C.Structure):
+    _fields_ = [("reward", C.c_double), ("score_delta", C.c_uint32), ("valid", C.c_int32), ("done", C.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
+    so = os.path.join(ROOT, "tests", "host_emul", "_emul.so")
+    deps = [src] + [os.path.join(ROOT, "2048-using-reinforcement-learning_b200", "csrc", f)
+                    for f in ("board.cuh", "env.cuh", "row_tables.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                        "-Wno-unknown-pragmas", "-o", so, src], check=True)
+    L = C.CDLL(so)
+    u64, u32 = C.c_uint64, C.c_uint32
+    for name in ("emul_transpose", "emul_flip_rows", "emul_flip_row_order", "emul_rot180"):
+        getattr(L, name).argtypes = [u64]; getattr(L, name).restype = u64
+    L.emul_env_move.argtypes = [u64, u32]; L.emul_env_move.restype = u64
+    L.emul_move_score.argtypes = [u64, u32]; L.emul_move_score.restype = u32
+    L.emul_env_legal.argtypes = [u64]; L.emul_env_legal.restype = u32
+    L.emul_agent_legal.argtypes = [u64]; L.emul_agent_legal.restype = u32
+    L.emul_agent_child.argtypes = [u64, u32]; L.emul_agent_child.restype = u64
+    L.emul_count_empty.argtypes = [u64]; L.emul_count_empty.restype = C.c_int
+    L.emul_max_exponent.argtypes = [u64]; L.emul_max_exponent.restype = u32
+    L.emul_place_tile.argtypes = [u64, u32, u32]; L.emul_place_tile.restype = u64
+    L.emul_fast_eval.argtypes = [u64]; L.emul_fast_eval.restype = C.c_int
+    L.emul_full_eval.argtypes = [u64, C.c_int]; L.emul_full_eval.restype = C.c_double
+    L.emul_philox.argtypes = [u32] * 6 + [C.POINTER(u32)]
+    L.emul_random_action.argtypes = [u64, u32, u32]; L.emul_random_action.restype = u32
+    L.emul_env_reset.argtypes = [C.POINTER(EmulEnv), u64, u32]
+    L.emul_env_step.argtypes = [C.POINTER(EmulEnv), u32, C.POINTER(u32), u64, u32, C.POINTER(EmulStep)]
+    L.emul_row.argtypes = [u32]; L.emul_row.restype = u32
+    L.emul_code.argtypes = [u32]; L.emul_code.restype = u32
+    L.emul_overflow.restype = C.c_ulonglong
+    L.emul_init()
+    return L
+
+
+def boards_for_test(orc, n=600):
+    out = [orc.synthetic_board(SEED, g) for g in range(n)]
+    rng = np.random.default_rng(3)
+    for _ in range(n):                        # dense / sparse / high-tile mixes
+        p_empty = rng.choice([0.0, 0.1, 0.6, 0.9])
+        e = rng.integers(1, 16, 16)
+        e[rng.random(16) < p_empty] = 0
+        out.append(np.where(e > 0, 1 << e, 0).astype(np.int32))
+    out.append(np.zeros(16, np.int32))
+    out.append(np.full(16, 2, np.int32))
+    out.append(np.full(16, 32768, np.int32))
+    return out
+
+
+def test_pack_roundtrip(orc):
+    bs = np.stack(boards_for_test(orc, 50))
+    assert (packing.unpack_boards(packing.pack_boards(bs)) == bs).all()
+    assert packing.pack_board([[2, 2, 4, 8], [0, 2, 2, 0], [4, 0, 4, 16], [2, 2, 2, 2]]) == 0x1111420201103211
+    with pytest.raises(ValueError):
+        packing.pack_boards(np.full(16, 3))
+
+
+def test_row_tables_against_golden(emul, golden):
+    for r in golden["rows"]:
+        exps = [0 if v == 0 else int(v).bit_length() - 1 for v in r["row"]]
+        if max(exps) > 15:
+            continue
+        idx = sum(e << (4 * j) for j, e in enumerate(exps))
+        out = emul.emul_row(idx)
+        want = [0 if v == 0 else int(v).bit_length() - 1 for v in r["out"]]
+        if max(want) <= 15:
+            assert [(out >> (4 * j)) & 15 for j in range(4)] == want
+        code = emul.emul_code(idx)
+        assert sum((2 << ((code >> s) & 15)) & ~3 for s in (0, 4)) == r["score"]
+
+
+def test_geometry(emul, orc):
+    for b in boards_for_test(orc, 100):
+        p = packing.pack_board(b)
+        m = b.reshape(4, 4)
+        assert emul.emul_transpose(p) == packing.pack_board(m.T)
+        assert emul.emul_flip_rows(p) == packing.pack_board(np.fliplr(m))
+        assert emul.emul_flip_row_order(p) == packing.pack_board(np.flipud(m))
+        assert emul.emul_rot180(p) == packing.pack_board(np.rot90(m, 2))
+
+
+def test_moves_legality_counts(emul, orc):
+    for b in boards_for_test(orc):
+        p = packing.pack_board(b)
+        saturates = False
+        for a in range(4):
+            want, score = orc.env_move(b, a)
+            if want.max() > 32768:
+                saturates = True
+                continue
+            assert emul.emul_env_move(p, a) == packing.pack_board(want), (b, a)
+            assert emul.emul_move_score(p, a) == score
+            aw, _, _ = orc.agent_move(b, a)
+            assert emul.emul_agent_child(p, a) == packing.pack_board(aw), (b, a)
+        assert emul.emul_env_move(p, 7) == p                   # out-of-range action: no-op (env:97-114)
+        if not saturates:
+            assert emul.emul_env_legal(p) == orc.env_legal_mask(b), b
+            assert emul.emul_agent_legal(p) == orc.agent_legal_mask(b), b
+        assert emul.emul_count_empty(p) == int((b == 0).sum())
+        assert emul.emul_max_exponent(p) == (int(b.max()).bit_length() - 1 if b.max() else 0)
+
+
+def test_evals_bit_exact(emul, orc):
+    for b in boards_for_test(orc):
+        if b.max() == 0:
+            continue
+        p = packing.pack_board(b)
+        assert float(emul.emul_fast_eval(p)) == orc.fast_eval(b), b
+        for ph in range(3):
+            assert emul.emul_full_eval(p, ph) == orc.full_eval(b, ph), (b, ph)
+
+
+def test_place_tile_every_slot(emul, orc):
+    rng = np.random.default_rng(11)
+    for b in boards_for_test(orc, 80):
+        p = packing.pack_board(b)
+        n = int((b == 0).sum())
+        if n == 0:
+            assert emul.emul_place_tile(p, 12345, 678) == p
+            continue
+        empties = np.flatnonzero(b == 0)
+        for k in range(n):
+            # smallest word that maps to slot k: ceil(k * 2^32 / n)
+            w = (k * (1 << 32) + n - 1) // n
+            for vw, tile in ((0, 2), (3865470566, 2), (3865470567, 4), (0xFFFFFFFF, 4)):
+                want = b.copy(); want[empties[k]] = tile
+                assert emul.emul_place_tile(p, w, vw) == packing.pack_board(want), (b, k)
+        w = int(rng.integers(0, 1 << 32))
+        want = b.copy(); want[empties[(w * n) >> 32]] = 2
+        assert emul.emul_place_tile(p, w, 0) == packing.pack_board(want)
+
+
+def test_philox_and_action_stream(emul, orc):
+    out = (C.c_uint32 * 4)()
+    emul.emul_philox(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0, out)
+    assert list(out) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    for g in (0, 5, 99):
+        for t in range(0, 300, 3):
+            assert emul.emul_random_action(SEED, g, t) == orc.lib().orc_random_action(SEED, g, t)
+
+
+def test_env_trajectories_bit_exact_including_reward(emul, orc):
+    for g in range(40):
+        o = orc.Env(SEED, g)
+        o.reset()
+        e = EmulEnv(0, 0, 0, 0)
+        emul.emul_env_reset(C.byref(e), SEED, g)
+        emul.emul_env_reset(C.byref(e), SEED, g)
+        assert e.board == packing.pack_board(o.board)
+        for t in range(500):
+            a = orc.lib().orc_random_action(SEED, g, t)
+            ob, orw, od, oi = o.step(a)
+            st = EmulStep()
+            emul.emul_env_step(C.byref(e), a, None, SEED, g, C.byref(st))
+            assert e.board == packing.pack_board(ob), (g, t)
+            assert st.reward == orw, (g, t, st.reward, orw)
+            assert bool(st.done) == od and bool(st.valid) == oi["valid_move"]
+            assert e.score == oi["score"] and (1 << e.highest) == oi["highest_tile"]
+            assert e.spawn_ctr == o.s.spawn_ctr
+            if od:
+                o.reset()
+                emul.emul_env_reset(C.byref(e), SEED, g)
+                assert e.board == packing.pack_board(o.board)
+    assert emul.emul_overflow() == 0
+
+
+def test_step_kats_from_reference(emul, golden):
+    for k in golden["step_kats"]:
+        e = EmulEnv(packing.pack_board(k["board"]), 0, int(k["highest_tile"]).bit_length() - 1, 0)
+        inj = (C.c_uint32 * 2)(*k["inject"])
+        st = EmulStep()
+        emul.emul_env_step(C.byref(e), k["action"], inj, golden["seed"], 0, C.byref(st))
+        assert e.board == packing.pack_board(k["out"])
+        assert st.reward == float.fromhex(k["reward"]), k
+        assert bool(st.done) == k["done"] and bool(st.valid) == k["valid"] and e.score == k["score"]
+        assert (1 << e.highest) == k["highest_after"]
