@@ -109,7 +109,8 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
     const int root_max = tile_value(max_exponent(root));
     const int phase = root_max < P.early_thr ? 0 : root_max < P.mid_thr ? 1 : 2;
     const int n0 = count_empty(root);
-    const int depth = n0 <= 4 ? min(P.depth + 5, 25) : n0 >= 10 ? min(P.depth - 5, 10) : P.depth;
+    // the root expansion (agent:112-132) always runs; `for depth in range(1, actual_depth)` adds levels
+    const int depth = max(1, n0 <= 4 ? min(P.depth + 5, 25) : n0 >= 10 ? min(P.depth - 5, 10) : P.depth);
 
     Board mine(0u, 0u);          // beam entry of rank `lane`
     uint32_t my_first = 0u;

@@ -211,5 +211,6 @@ def test_facade_env_matches_oracle(orc):
     # callers may poke the board between calls (hybrid.py and tests do)
     env.board = np.array([[2, 0, 0, 0], [4, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]], dtype=np.int32)
     env.score = 0
+    env.highest_tile = 4          # the reference needs this too, else env:229 pays the (otherwise dead) new-tile bonus
     s, r, d, info = env.step(0)
     assert not info["valid_move"] and r == -0.5666666666666668
