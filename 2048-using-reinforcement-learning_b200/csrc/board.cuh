@@ -123,6 +123,34 @@ __device__ __forceinline__ uint32_t decode_score(uint32_t codes, uint32_t *sat)
     return total;
 }
 
+// 2^c for a 4-bit field c >= 1 and 0 for c == 0, summed over selected nibbles on the FMA pipe:
+// the field is shifted into the float exponent (c << 23 is the normal number 2^(c-127)) and
+// scaled by 2^127.  All terms and partial sums are small powers of two / integers < 2^24, so
+// the float arithmetic is exact.  `cells` has bit 4i set for every nibble i to include.
+__device__ __forceinline__ float pow2_field(uint32_t x, int i)
+{
+    const uint32_t field = 15u << 23;
+    uint32_t bits = (4 * i <= 23 ? (x << (23 - 4 * i)) : (x >> (4 * i - 23))) & field;
+    return __uint_as_float(bits);
+}
+__device__ __forceinline__ float pow2_sum(uint32_t x, uint32_t cells, float acc)
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if ((cells >> (4 * i)) & 1u) acc = fmaf(pow2_field(x, i), 0x1p127f, acc);
+    return acc;
+}
+// decode_score() on the FMA pipe: each code nibble c scores 2 << c (0 for c == 0).
+__device__ __forceinline__ uint32_t decode_score_fma(uint32_t codes)
+{
+    return 2u * (uint32_t)pow2_sum(codes, LSB4, 0.0f);
+}
+// some code nibble is 15  <=>  a merge produced 2^16 (nibble saturation)
+__device__ __forceinline__ bool codes_saturated(uint32_t codes)
+{
+    return ((((codes & 0x77777777u) + LSB4) & codes) & MSB4) != 0u;
+}
+
 // Direction wrappers.  `to_line` brings the rows the tiles travel along into LEFT-move
 // position, `from_line` undoes it.  Lane-varying actions use selects, not branches.
 __device__ __forceinline__ Board select(bool p, Board a, Board b) { return Board(p ? a.lo : b.lo, p ? a.hi : b.hi); }
@@ -260,6 +288,27 @@ __device__ __forceinline__ int place_tile(Board &b, uint32_t pos_word, uint32_t 
     return n;
 }
 
+// Same, with the zero flags of the board already known (zl/zh = zero_flags of lo/hi, n > 0
+// empties in total).  Returns the bit the new tile set in its half and whether that is `hi`.
+struct Spawned { uint32_t tile; bool in_hi; uint32_t exponent; };
+__device__ __forceinline__ Spawned place_tile_flags(Board &b, uint32_t zl, uint32_t zh, int n, uint32_t pos_word,
+                                                    uint32_t val_word)
+{
+    int cl = __popc(zl);
+    uint32_t k = __umulhi(pos_word, (uint32_t)n);
+    Spawned sp;
+    sp.in_hi = k >= (uint32_t)cl;
+    uint32_t kk = sp.in_hi ? k - (uint32_t)cl : k;
+    uint32_t z = sp.in_hi ? zh : zl;
+    uint32_t s = z * LSB4 + (7u - kk) * LSB4;         // bit 3 of nibble j set <=> #empty(0..j) > kk
+    uint32_t bit = __ffs((int)(s & MSB4)) - 1;        // 4j+3 of the first such nibble
+    sp.exponent = val_word < 3865470567u ? 1u : 2u;
+    sp.tile = sp.exponent << ((bit - 3u) & 31u);
+    b.lo |= sp.in_hi ? 0u : sp.tile;
+    b.hi |= sp.in_hi ? sp.tile : 0u;
+    return sp;
+}
+
 // ---- heuristics -----------------------------------------------------------------------
 // Sum over a set of cells of 2^e (0 for an empty cell); `cells` has bit 4i set for cell i.
 __device__ __forceinline__ uint32_t tile_sum_half(uint32_t x, uint32_t cells)
@@ -355,6 +404,52 @@ __device__ __forceinline__ void ordered_pairs(Board b, int line[4])
     line[1] = __popc(hl & 0xFFFF0000u) + __popc(v & 0x00800180u);
     line[2] = __popc(hh & 0x0000FFFFu) + __popc(v & 0x08001800u);
     line[3] = __popc(hh & 0xFFFF0000u) + __popc(v & 0x80018000u);
+}
+
+// ordered_pairs() with the occupancy flags (bit 0 of every non-empty nibble) already known
+__device__ __forceinline__ void ordered_pairs_flags(Board b, uint32_t nzl, uint32_t nzh, int line[4])
+{
+    const uint32_t nl = nzl << 3, nh = nzh << 3;
+    uint32_t hl = ge_flags(b.lo >> 4, b.lo) & nl & (nl >> 4) & 0x08880888u;
+    uint32_t hh = ge_flags(b.hi >> 4, b.hi) & nh & (nh >> 4) & 0x08880888u;
+    uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16), nbl = __funnelshift_r(nl, nh, 16);
+    uint32_t vl = ge_flags(below_lo, b.lo) & nl & nbl;
+    uint32_t vh = ge_flags(b.hi >> 16, b.hi) & nh & (nh >> 16) & 0x00008888u;
+    uint32_t v = vl | (vh << 1);
+    line[0] = __popc(hl & 0x0000FFFFu) + __popc(v & 0x00080018u);
+    line[1] = __popc(hl & 0xFFFF0000u) + __popc(v & 0x00800180u);
+    line[2] = __popc(hh & 0x0000FFFFu) + __popc(v & 0x08001800u);
+    line[3] = __popc(hh & 0xFFFF0000u) + __popc(v & 0x80018000u);
+}
+
+// shaped_reward() for callers that track the tile total (moves conserve it, a spawn adds its
+// value) and the occupancy flags; identical float64 operation sequence.
+__device__ __forceinline__ double shaped_reward_tracked(bool valid, int empty_before, Board cur, int empty_after,
+                                                        uint32_t nzl, uint32_t nzh, uint32_t score_delta,
+                                                        uint32_t highest_exp_before, uint32_t prev_max_exp,
+                                                        uint32_t total)
+{
+    double reward = __dmul_rn((double)score_delta, 0.25);
+    if (highest_exp_before > prev_max_exp) {                               // env:229-241
+        reward = __dadd_rn(reward, __dmul_rn(2.0, (double)highest_exp_before));
+        if (highest_exp_before >= 8)  reward = __dadd_rn(reward, 50.0);
+        if (highest_exp_before >= 9)  reward = __dadd_rn(reward, 100.0);
+        if (highest_exp_before >= 10) reward = __dadd_rn(reward, 200.0);
+        if (highest_exp_before >= 11) reward = __dadd_rn(reward, 500.0);
+    }
+    if (!valid) reward = __dadd_rn(reward, -2.0);
+    reward = __dadd_rn(reward, __dmul_rn((double)(empty_after - empty_before), 0.5));
+    // edge_sum = total - inner 2x2 + corners (corners are counted by a row and by a column)
+    float inner = pow2_sum(cur.hi, 0x00000110u, pow2_sum(cur.lo, 0x01100000u, 0.0f));
+    float corners = pow2_sum(cur.hi, 0x10010000u, pow2_sum(cur.lo, 0x00001001u, 0.0f));
+    uint32_t edge = total - (uint32_t)inner + (uint32_t)corners;
+    reward = __dadd_rn(reward, __dmul_rn(__ddiv_rn((double)edge, (double)total), 1.0));
+    if (empty_after <= 2) reward = __dadd_rn(reward, -2.0);
+    int line[4];
+    ordered_pairs_flags(cur, nzl, nzh, line);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reward = __dadd_rn(reward, __dmul_rn((double)line[i], 0.1));
+    return reward;
 }
 
 __device__ __forceinline__ double shaped_reward(bool valid, int empty_before, Board cur, int empty_after,

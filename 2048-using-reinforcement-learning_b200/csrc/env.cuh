@@ -72,4 +72,68 @@ __device__ __forceinline__ StepResult env_step(EnvState &s, uint32_t action, con
     return r;
 }
 
+// ---- fused-rollout fast path ----------------------------------------------------------------
+// Same transition as env_step(), for callers that keep an env in registers across steps and
+// therefore can carry what a step already knows into the next one: the empty count, the sum
+// of the tile values (a move conserves it, a spawn adds 2 or 4) and the board's max exponent
+// (it grows by one exactly when two max tiles merge).  Bit-exact with env_step(); the tests
+// compare both with the oracle.
+struct TrackedEnv {
+    EnvState s;
+    int n_empty;          // empty cells of s.board
+    uint32_t total;       // sum of the tile values of s.board
+    uint32_t bmax;        // largest exponent on s.board
+};
+
+__device__ __forceinline__ void track(TrackedEnv &t)
+{
+    t.n_empty = count_empty(t.s.board);
+    t.total = (uint32_t)pow2_sum(t.s.board.hi, LSB4, pow2_sum(t.s.board.lo, LSB4, 0.0f));
+    t.bmax = max_exponent(t.s.board);
+}
+
+template <bool kReward>
+__device__ __forceinline__ StepResult env_step_tracked(TrackedEnv &t, uint32_t action, const uint16_t *row,
+                                                       const uint8_t *code, uint32_t k0, uint32_t k1, uint32_t game,
+                                                       unsigned long long *overflow)
+{
+    StepResult r;
+    EnvState &s = t.s;
+    const Board prev = s.board;
+    const Board line = to_line(prev, action);
+    Board next = from_line(move_left<true>(line, row), action);
+    const uint32_t codes = merge_codes<true>(line, code);                   // action is always 0..3 here
+    r.score_delta = decode_score_fma(codes);
+    if (codes_saturated(codes)) atomicAdd(overflow, 1ull);
+    s.score += (int32_t)r.score_delta;
+    r.valid = next != prev;
+    uint32_t zl = zero_flags(next.lo), zh = zero_flags(next.hi);
+    int empty_after = __popc(zl) + __popc(zh);
+    uint32_t spawn_value = 0u, spawn_exp = 0u;
+    if (r.valid) {
+        SpawnWords w = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr);
+        s.spawn_ctr += 1u;
+        Spawned sp = place_tile_flags(next, zl, zh, empty_after, w.pos, w.val);
+        uint32_t flag = sp.tile >> (sp.exponent - 1u);                      // bit 0 of the new tile's nibble
+        zl &= sp.in_hi ? ~0u : ~flag;
+        zh &= sp.in_hi ? ~flag : ~0u;
+        empty_after -= 1;
+        spawn_exp = sp.exponent;
+        spawn_value = 1u << sp.exponent;
+    }
+    const uint32_t total = t.total + spawn_value;
+    r.reward = 0.0;
+    if (kReward)
+        r.reward = shaped_reward_tracked(r.valid, t.n_empty, next, empty_after, zl ^ LSB4, zh ^ LSB4, r.score_delta,
+                                         s.highest, t.bmax, total);
+    // two tiles of the current maximum merged <=> some merge code equals bmax
+    uint32_t bmax = t.bmax + (zero_flags(codes ^ (t.bmax * LSB4)) != 0u ? 1u : 0u);
+    bmax = max(bmax, spawn_exp);
+    r.done = (empty_after == 0) && env_game_over(next);
+    s.highest = max(s.highest, bmax);
+    s.board = next;
+    t.n_empty = empty_after; t.total = total; t.bmax = bmax;
+    return r;
+}
+
 }  // namespace g2048

@@ -150,11 +150,12 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(Rollout
     const uint8_t *code = smem + kRowTableBytes;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t game = a.game0 + (uint32_t)i;
-        EnvState s;
-        s.board = Board(a.boards[i]);
-        s.score = a.score[i];
-        s.highest = a.highest[i];
-        s.spawn_ctr = a.spawn_ctr[i];
+        TrackedEnv e;
+        e.s.board = Board(a.boards[i]);
+        e.s.score = a.score[i];
+        e.s.highest = a.highest[i];
+        e.s.spawn_ctr = a.spawn_ctr[i];
+        track(e);
         double rsum = a.reward_sum ? a.reward_sum[i] : 0.0;
         int32_t episodes = a.episodes ? a.episodes[i] : 0;
         Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
@@ -164,14 +165,14 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(Rollout
             const uint32_t sel = (t >> 4) & 3u;
             const uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
             const uint32_t action = (word >> (2u * (t & 15u))) & 3u;
-            StepResult r = env_step<true, true, true>(s, action, row, code, a.k0, a.k1, game, nullptr, a.overflow);
+            StepResult r = env_step_tracked<true>(e, action, row, code, a.k0, a.k1, game, a.overflow);
             rsum = __dadd_rn(rsum, r.reward);
-            if (r.done) { ++episodes; env_reset(s, a.k0, a.k1, game); }
+            if (r.done) { ++episodes; env_reset(e.s, a.k0, a.k1, game); track(e); }
         }
-        a.boards[i] = s.board.u64();
-        a.score[i] = s.score;
-        a.highest[i] = (uint8_t)s.highest;
-        a.spawn_ctr[i] = s.spawn_ctr;
+        a.boards[i] = e.s.board.u64();
+        a.score[i] = e.s.score;
+        a.highest[i] = (uint8_t)e.s.highest;
+        a.spawn_ctr[i] = e.s.spawn_ctr;
         if (a.reward_sum) a.reward_sum[i] = rsum;
         if (a.episodes) a.episodes[i] = episodes;
     }
@@ -464,8 +465,11 @@ int g2048_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_exp, ui
     G2048_ENTER(boards && score && highest_exp && spawn_ctr && steps >= 0);
     RolloutArgs a{boards, score, highest_exp, spawn_ctr, reward_sum, episodes, n, steps, t0,
                   (uint32_t)seed, (uint32_t)(seed >> 32), game0, st->row, st->code, st->overflow};
-    int grid = grid_for(n, kRolloutThreads, st->sm_count, 1);
-    env_rollout_kernel<<<grid, kRolloutThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
+    // one 192 KiB block per SM; spread the envs over ALL SMs (65,536 envs -> 148 blocks x 448 threads)
+    int grid = (int)(n < st->sm_count ? n : st->sm_count);
+    int64_t per_block = (n + grid - 1) / grid;
+    int threads = (int)(per_block >= kRolloutThreads ? kRolloutThreads : ((per_block + 31) / 32) * 32);
+    env_rollout_kernel<<<grid, threads, kRowTableBytes + kCodeTableBytes, s>>>(a);
     G2048_LAUNCHED();
 }
 

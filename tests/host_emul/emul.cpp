@@ -47,6 +47,7 @@ static inline uint32_t __vsadu4(uint32_t a, uint32_t b)
     }
     return s;
 }
+static inline float __uint_as_float(uint32_t u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
@@ -125,6 +126,19 @@ void emul_env_step(EmulEnv *e, uint32_t action, const uint32_t *inject, uint64_t
                                                 inject, &g_overflow);
     e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
     o->reward = r.reward; o->score_delta = r.score_delta; o->valid = r.valid; o->done = r.done;
+}
+// `steps` tracked steps with the random-policy action stream and auto-reset, like env_rollout_kernel
+void emul_rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uint32_t game, double *reward_sum, int *episodes)
+{
+    TrackedEnv t; t.s.board = Board(e->board); t.s.score = e->score; t.s.highest = e->highest; t.s.spawn_ctr = e->spawn_ctr;
+    track(t);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int i = 0; i < steps; ++i) {
+        StepResult r = env_step_tracked<true>(t, random_action(k0, k1, game, t0 + i), g_row, g_code, k0, k1, game, &g_overflow);
+        *reward_sum += r.reward;
+        if (r.done) { ++*episodes; env_reset(t.s, k0, k1, game); track(t); }
+    }
+    e->board = t.s.board.u64(); e->score = t.s.score; e->highest = t.s.highest; e->spawn_ctr = t.s.spawn_ctr;
 }
 unsigned long long emul_overflow(void) { return g_overflow; }
 

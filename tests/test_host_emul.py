@@ -56,6 +56,7 @@ def emul():
     L.emul_random_action.argtypes = [u64, u32, u32]; L.emul_random_action.restype = u32
     L.emul_env_reset.argtypes = [C.POINTER(EmulEnv), u64, u32]
     L.emul_env_step.argtypes = [C.POINTER(EmulEnv), u32, C.POINTER(u32), u64, u32, C.POINTER(EmulStep)]
+    L.emul_rollout_tracked.argtypes = [C.POINTER(EmulEnv), C.c_int, u32, u64, u32, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.emul_row.argtypes = [u32]; L.emul_row.restype = u32
     L.emul_code.argtypes = [u32]; L.emul_code.restype = u32
     L.emul_overflow.restype = C.c_ulonglong
@@ -204,3 +205,24 @@ def test_step_kats_from_reference(emul, golden):
         assert st.reward == float.fromhex(k["reward"]), k
         assert bool(st.done) == k["done"] and bool(st.valid) == k["valid"] and e.score == k["score"]
         assert (1 << e.highest) == k["highest_after"]
+
+
+def test_tracked_rollout_step_matches_oracle(emul, orc):
+    """env_step_tracked (the fused-rollout fast path: carried empties / tile total / max exponent,
+    FMA-pipe score decode) against the oracle, reward sums included."""
+    n, steps = 64, 1500
+    ob = np.zeros((n, 16), np.int32); osc = np.zeros(n, np.int64); ohi = np.zeros(n, np.int32)
+    octr = np.zeros(n, np.uint32); ors = np.zeros(n, np.float64); oep = np.zeros(n, np.int32)
+    for i in range(n):
+        env = orc.Env(SEED, 700 + i, ctor_reset=False)
+        env.reset()
+        ob[i] = env.board; ohi[i] = env.s.highest_tile; octr[i] = env.s.spawn_ctr
+    start = ob.copy()
+    orc.rollout(ob, osc, ohi, octr, ors, oep, steps, 3, SEED, 700)
+    for i in range(n):
+        e = EmulEnv(packing.pack_board(start[i]), 0, int(start[i].max()).bit_length() - 1, 2)
+        rs = C.c_double(0.0); ep = C.c_int(0)
+        emul.emul_rollout_tracked(C.byref(e), steps, 3, SEED, 700 + i, C.byref(rs), C.byref(ep))
+        assert e.board == packing.pack_board(ob[i]) and e.score == osc[i] and e.spawn_ctr == octr[i]
+        assert rs.value == ors[i] and ep.value == oep[i] and (1 << e.highest) == ohi[i]
+    assert oep.sum() > 0
