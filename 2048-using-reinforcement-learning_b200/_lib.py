@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libg2048.so")
+LIB_PATH = os.environ.get("G2048_LIB_PATH") or os.path.join(_HERE, "libg2048.so")   # override: kernel experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 STATS_LEN = 40

@@ -14,9 +14,13 @@
 #include "common.cuh"
 #include "env.cuh"
 
+#ifndef G2048_BEAM_WARPS
+#define G2048_BEAM_WARPS 24
+#endif
+
 namespace g2048 {
 
-constexpr int kBeamWarps = 16;                              // roots in flight per block
+constexpr int kBeamWarps = G2048_BEAM_WARPS;                             // roots in flight per block
 constexpr int kBeamThreads = kBeamWarps * 32;
 constexpr int kMaxCand = 4 * G2048_MAX_BEAM_WIDTH;          // 128 children per level at most
 constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -41,21 +45,22 @@ struct BeamResult {
 };
 
 // ---- warp-wide sorting network on unique uint32 keys, descending (lane 0 = largest) --------
-__device__ __forceinline__ uint32_t exchange(uint32_t v, int j, bool keep_max)
+// Bitonic sort in its "flip" form: every compare-exchange keeps the larger key in the lower
+// lane, so the direction of a stage is one lane-id bit test (five loop-invariant predicates)
+// instead of a per-stage direction computation.
+__device__ __forceinline__ uint32_t exchange(uint32_t v, int xor_mask, bool lower)
 {
-    uint32_t o = __shfl_xor_sync(FULL, v, j);
-    return keep_max ? max(v, o) : min(v, o);
+    uint32_t o = __shfl_xor_sync(FULL, v, xor_mask);
+    uint32_t hi = max(v, o), lo = min(v, o);
+    return lower ? hi : lo;
 }
 __device__ __forceinline__ uint32_t sort_desc32(uint32_t v, uint32_t lane)
 {
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
+        v = exchange(v, k - 1, (lane & (k >> 1)) == 0);       // mirror inside the block of k
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            bool lower = (lane & j) == 0;
-            bool desc = (lane & k) == 0;             // k == 32: every lane
-            v = exchange(v, j, lower == desc);
-        }
+        for (int j = k >> 2; j > 0; j >>= 1) v = exchange(v, j, (lane & j) == 0);
     }
     return v;
 }
@@ -254,7 +259,7 @@ __device__ __forceinline__ void stage_row_table(uint8_t *smem, const uint16_t *r
 struct BeamArgs {
     const uint64_t *roots; const uint8_t *legal; const uint32_t *call; uint32_t call0;
     uint8_t *action; float *prob; double *best; int32_t *nodes;
-    int64_t n; BeamParams P; uint32_t game0; const uint16_t *row;
+    int64_t n; BeamParams P; uint32_t game0; const uint16_t *row; unsigned int *work;
 };
 
 __global__ void __launch_bounds__(kBeamThreads, 1) beam_search_kernel(BeamArgs a)
@@ -265,7 +270,13 @@ __global__ void __launch_bounds__(kBeamThreads, 1) beam_search_kernel(BeamArgs a
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
     const uint32_t lane = threadIdx.x & 31u;
-    for (int64_t i = (int64_t)blockIdx.x * kBeamWarps + warp; i < a.n; i += (int64_t)gridDim.x * kBeamWarps) {
+    // roots differ a lot in cost (fast exits, adaptive depth 10 / d / 25): warps pull the next
+    // root from a global queue instead of striding over a fixed share
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(a.work, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if ((int64_t)i >= a.n) break;
         Board root(a.roots[i]);
         int legal = a.legal ? (int)a.legal[i] : -1;
         uint32_t call = a.call ? a.call[i] : a.call0;
@@ -342,6 +353,13 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
 
 static int g_attr_done[kMaxDevices];
 
+// Each launch gets its own queue head so launches on different streams never share one.
+static unsigned int *next_work_counter(DeviceState *st)
+{
+    unsigned int slot = __atomic_fetch_add(&st->next_counter, 1u, __ATOMIC_RELAXED) % kWorkCounters;
+    return st->work_counter + slot;
+}
+
 static int ensure_attrs()
 {
     int dev = 0;
@@ -363,7 +381,8 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
     if (rc != G2048_OK) return rc;
     BeamArgs a{roots, legal, call, call0, action, prob, best_score, nodes, n,
                BeamParams{beam_width, search_depth, early_thr, mid_thr, (uint32_t)seed, (uint32_t)(seed >> 32)},
-               game0, st->row};
+               game0, st->row, next_work_counter(st)};
+    G2048_CUDA(cudaMemsetAsync(a.work, 0, sizeof(unsigned int), stream));
     int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
     int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
     beam_search_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
@@ -378,10 +397,11 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
 {
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
-    G2048_CUDA(cudaMemsetAsync(st->work_counter, 0, sizeof(unsigned int), stream));
+    unsigned int *work = next_work_counter(st);
+    G2048_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned int), stream));
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, (uint32_t)seed, (uint32_t)(seed >> 32)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
-                st->row, st->code, st->overflow, st->work_counter};
+                st->row, st->code, st->overflow, work};
     int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
     int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
     play_games_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);

@@ -35,18 +35,21 @@ __device__ __forceinline__ uint32_t nz_flags(uint32_t x)
 // bit 4i set  <=>  nibble i of x is zero
 __device__ __forceinline__ uint32_t zero_flags(uint32_t x) { return ~nz_flags(x) & LSB4; }
 
+// (a & mask) | (b & ~mask): one LOP3
+__device__ __forceinline__ uint32_t bitselect(uint32_t mask, uint32_t a, uint32_t b) { return (a & mask) | (b & ~mask); }
+
 // ---- geometry -------------------------------------------------------------
 // 4x4 nibble transpose: swap inside 2x2 blocks (per half), then swap the two
 // off-diagonal 2x2 blocks (a byte permutation across the halves).
 __device__ __forceinline__ Board transpose(Board b)
 {
-    uint32_t l = (b.lo & 0xF0F00F0Fu) | ((b.lo << 12) & 0x0F0F0000u) | ((b.lo >> 12) & 0x0000F0F0u);
-    uint32_t h = (b.hi & 0xF0F00F0Fu) | ((b.hi << 12) & 0x0F0F0000u) | ((b.hi >> 12) & 0x0000F0F0u);
+    uint32_t l = bitselect(0x0000F0F0u, b.lo >> 12, bitselect(0x0F0F0000u, b.lo << 12, b.lo));
+    uint32_t h = bitselect(0x0000F0F0u, b.hi >> 12, bitselect(0x0F0F0000u, b.hi << 12, b.hi));
     return Board(__byte_perm(l, h, 0x6240), __byte_perm(l, h, 0x7351));
 }
 __device__ __forceinline__ uint32_t swap_nibbles_in_bytes(uint32_t x)
 {
-    return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+    return bitselect(0xF0F0F0F0u, x << 4, x >> 4);
 }
 // np.fliplr: reverse the 4 nibbles of every row
 __device__ __forceinline__ Board flip_rows(Board b)
@@ -205,6 +208,9 @@ __device__ __forceinline__ uint32_t env_legal_mask(Board b)
 }
 // is_game_over (env:279-288): no empty cell and no equal neighbours
 __device__ __forceinline__ bool env_game_over(Board b) { return env_legal_mask(b) == 0u; }
+// Out-of-line copy for hot loops: a full board is rare, and a call cannot be if-converted
+// into the per-step instruction stream the way the inline test is.
+static __device__ __noinline__ bool env_game_over_rare(uint32_t lo, uint32_t hi) { return env_legal_mask(Board(lo, hi)) == 0u; }
 
 // ---- counting ----------------------------------------------------------------
 __device__ __forceinline__ int count_empty(Board b) { return __popc(zero_flags(b.lo)) + __popc(zero_flags(b.hi)); }

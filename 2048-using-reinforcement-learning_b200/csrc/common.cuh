@@ -9,6 +9,7 @@ namespace g2048 {
 
 constexpr int kMaxDevices = 32;
 constexpr int kRowEntries = 65536;
+constexpr int kWorkCounters = 256;          // work-queue heads handed out round-robin to launches
 constexpr size_t kRowTableBytes = kRowEntries * sizeof(uint16_t);    // 128 KiB
 constexpr size_t kCodeTableBytes = kRowEntries * sizeof(uint8_t);    //  64 KiB
 
@@ -17,7 +18,8 @@ struct DeviceState {
     uint16_t *row = nullptr;                 // LEFT-move result per 16-bit row
     uint8_t *code = nullptr;                 // merge codes per 16-bit row
     unsigned long long *overflow = nullptr;  // sticky nibble-saturation counter
-    unsigned int *work_counter = nullptr;    // game queue head of play_games
+    unsigned int *work_counter = nullptr;    // ring of kWorkCounters queue heads (one per launch in flight)
+    unsigned int next_counter = 0;
     int sm_count = 0;
 };
 

@@ -92,48 +92,91 @@ __device__ __forceinline__ void track(TrackedEnv &t)
     t.bmax = max_exponent(t.s.board);
 }
 
-template <bool kReward>
-__device__ __forceinline__ StepResult env_step_tracked(TrackedEnv &t, uint32_t action, const uint16_t *row,
-                                                       const uint8_t *code, uint32_t k0, uint32_t k1, uint32_t game,
-                                                       unsigned long long *overflow)
+// The step is split in two so that a caller can software-pipeline it: `step_move` produces
+// the next board (move, spawn, game-over test) and everything the reward needs; `step_reward`
+// turns that into the float64 reward.  The reward of step t does not feed step t+1, so a loop
+// that issues step_move(t+1) and step_reward(t) back to back gives the scheduler two
+// independent dependency chains (the kernel has only ~3.5 warps per scheduler to hide latency).
+//
+// kTrackMax = false: the caller guarantees highest == board max on entry, which the transition
+// preserves (highest only ever follows the board's max), so the dead "new highest tile" branch
+//  cannot fire and neither value is maintained per step; the caller sets
+// highest = max_exponent(board) when it is done.
+struct PendingReward {
+    Board cur;                 // board after move + spawn
+    uint32_t nzl, nzh;         // its occupancy flags
+    uint32_t score_delta, total, highest_before, prev_max;
+    int empty_before, empty_after;
+    bool valid;
+};
+
+template <bool kTrackMax>
+__device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t action, const uint16_t *row,
+                                                   const uint8_t *code, uint32_t k0, uint32_t k1, uint32_t game,
+                                                   uint32_t &saturated, bool &full)
 {
-    StepResult r;
+    PendingReward p;
     EnvState &s = t.s;
     const Board prev = s.board;
+    // the spawn words depend only on the counter: issue the Philox block first so that it
+    // overlaps the table lookups (it runs on the FMA pipe, the move on the ALU pipe)
+    const SpawnWords w = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr);
     const Board line = to_line(prev, action);
     Board next = from_line(move_left<true>(line, row), action);
     const uint32_t codes = merge_codes<true>(line, code);                   // action is always 0..3 here
-    r.score_delta = decode_score_fma(codes);
-    if (codes_saturated(codes)) atomicAdd(overflow, 1ull);
-    s.score += (int32_t)r.score_delta;
-    r.valid = next != prev;
+    p.score_delta = decode_score_fma(codes);
+    saturated |= codes_saturated(codes) ? 1u : 0u;
+    s.score += (int32_t)p.score_delta;
+    p.valid = next != prev;
     uint32_t zl = zero_flags(next.lo), zh = zero_flags(next.hi);
     int empty_after = __popc(zl) + __popc(zh);
+    // spawn computed unconditionally and masked by `valid` (env:191-192); a valid move always
+    // leaves an empty cell
+    Board spawned = next;
+    Spawned sp = place_tile_flags(spawned, zl, zh, max(empty_after, 1), w.pos, w.val);
+    uint32_t flag = sp.tile >> (sp.exponent - 1u);                          // bit 0 of the new tile's nibble
     uint32_t spawn_value = 0u, spawn_exp = 0u;
-    if (r.valid) {
-        SpawnWords w = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr);
+    if (p.valid) {
+        next = spawned;
         s.spawn_ctr += 1u;
-        Spawned sp = place_tile_flags(next, zl, zh, empty_after, w.pos, w.val);
-        uint32_t flag = sp.tile >> (sp.exponent - 1u);                      // bit 0 of the new tile's nibble
         zl &= sp.in_hi ? ~0u : ~flag;
         zh &= sp.in_hi ? ~flag : ~0u;
         empty_after -= 1;
         spawn_exp = sp.exponent;
         spawn_value = 1u << sp.exponent;
     }
-    const uint32_t total = t.total + spawn_value;
-    r.reward = 0.0;
-    if (kReward)
-        r.reward = shaped_reward_tracked(r.valid, t.n_empty, next, empty_after, zl ^ LSB4, zh ^ LSB4, r.score_delta,
-                                         s.highest, t.bmax, total);
-    // two tiles of the current maximum merged <=> some merge code equals bmax
-    uint32_t bmax = t.bmax + (zero_flags(codes ^ (t.bmax * LSB4)) != 0u ? 1u : 0u);
-    bmax = max(bmax, spawn_exp);
-    r.done = (empty_after == 0) && env_game_over(next);
-    s.highest = max(s.highest, bmax);
+    p.total = t.total + spawn_value;
+    p.cur = next; p.nzl = zl ^ LSB4; p.nzh = zh ^ LSB4;
+    p.empty_before = t.n_empty; p.empty_after = empty_after;
+    p.highest_before = kTrackMax ? s.highest : 0u;
+    p.prev_max = kTrackMax ? t.bmax : 0u;
+    if (kTrackMax) {
+        // two tiles of the current maximum merged <=> some merge code equals bmax
+        uint32_t bmax = t.bmax + (zero_flags(codes ^ (t.bmax * LSB4)) != 0u ? 1u : 0u);
+        bmax = max(bmax, spawn_exp);
+        s.highest = max(s.highest, bmax);
+        t.bmax = bmax;
+    }
+    full = empty_after == 0;              // only a full board can be game over (env:279-288)
     s.board = next;
-    t.n_empty = empty_after; t.total = total; t.bmax = bmax;
-    return r;
+    t.n_empty = empty_after; t.total = p.total;
+    return p;
+}
+
+__device__ __forceinline__ double step_reward(const PendingReward &p)
+{
+    return shaped_reward_tracked(p.valid, p.empty_before, p.cur, p.empty_after, p.nzl, p.nzh, p.score_delta,
+                                 p.highest_before, p.prev_max, p.total);
+}
+
+// A full board is over when no two neighbours are equal.  (x ^ shifted) | guard has a zero
+// nibble exactly where a real pair is equal; "any zero nibble" via the borrow trick is exact.
+__device__ __forceinline__ bool full_board_game_over(Board b)
+{
+    auto any_zero = [](uint32_t v) { return ((v - LSB4) & ~v & MSB4) != 0u; };
+    bool h = any_zero((b.lo ^ (b.lo >> 4)) | 0xF000F000u) || any_zero((b.hi ^ (b.hi >> 4)) | 0xF000F000u);
+    bool v = any_zero(b.lo ^ __funnelshift_r(b.lo, b.hi, 16)) || any_zero((b.hi ^ (b.hi >> 16)) | 0xFFFF0000u);
+    return !(h || v);
 }
 
 }  // namespace g2048

@@ -142,6 +142,45 @@ struct RolloutArgs {
 // `steps` env.step calls per env with the board in registers; random-policy actions from the
 // Philox action stream (one block = 64 actions), auto-reset on game over.
 constexpr int kRolloutThreads = 512;
+#ifndef G2048_ROLLOUT_UNROLL
+#define G2048_ROLLOUT_UNROLL 1
+#endif
+constexpr int kRolloutUnroll = G2048_ROLLOUT_UNROLL;   // steps per loop trip (ILP across steps)
+
+// Uniform random action of step t from the cached Philox action block (64 actions per block).
+__device__ __forceinline__ uint32_t cached_action(Philox4 &act, uint32_t t, bool first, uint32_t game,
+                                                  uint32_t k0, uint32_t k1)
+{
+    if ((t & 63u) == 0u && !first) act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, k0, k1);
+    const uint32_t sel = (t >> 4) & 3u;
+    const uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
+    return (word >> (2u * (t & 15u))) & 3u;
+}
+
+// Software-pipelined step loop: step_move(t) and step_reward(t-1) share a basic block.
+template <bool kTrackMax>
+__device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &a, uint32_t game, const uint16_t *row,
+                                              const uint8_t *code, double &rsum, int32_t &episodes)
+{
+    if (a.steps <= 0) return;
+    Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
+    uint32_t saturated = 0u;
+    bool full;
+    PendingReward pend = step_move<kTrackMax>(e, cached_action(act, a.t0, true, game, a.k0, a.k1), row, code,
+                                              a.k0, a.k1, game, saturated, full);
+    if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.k0, a.k1, game); track(e); }
+    for (int32_t step = 1; step < a.steps; ++step) {
+        const uint32_t action = cached_action(act, a.t0 + (uint32_t)step, false, game, a.k0, a.k1);
+        PendingReward cur = step_move<kTrackMax>(e, action, row, code, a.k0, a.k1, game, saturated, full);
+        rsum = __dadd_rn(rsum, step_reward(pend));          // float64 sum stays in step order
+        pend = cur;
+        if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.k0, a.k1, game); track(e); }
+    }
+    rsum = __dadd_rn(rsum, step_reward(pend));
+    if (saturated) atomicAdd(a.overflow, 1ull);
+    if (!kTrackMax) e.s.highest = max_exponent(e.s.board);
+}
+
 __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(RolloutArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -158,17 +197,11 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(Rollout
         track(e);
         double rsum = a.reward_sum ? a.reward_sum[i] : 0.0;
         int32_t episodes = a.episodes ? a.episodes[i] : 0;
-        Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
-        for (int32_t step = 0; step < a.steps; ++step) {
-            const uint32_t t = a.t0 + (uint32_t)step;
-            if ((t & 63u) == 0u && step != 0) act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
-            const uint32_t sel = (t >> 4) & 3u;
-            const uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
-            const uint32_t action = (word >> (2u * (t & 15u))) & 3u;
-            StepResult r = env_step_tracked<true>(e, action, row, code, a.k0, a.k1, game, a.overflow);
-            rsum = __dadd_rn(rsum, r.reward);
-            if (r.done) { ++episodes; env_reset(e.s, a.k0, a.k1, game); track(e); }
-        }
+        // highest > board max only if the caller poked it (env:229): such warps take the
+        // variant that maintains both per step; everybody else skips that bookkeeping.
+        const bool poked = __any_sync(__activemask(), e.s.highest > e.bmax);
+        if (poked) rollout_steps<true>(e, a, game, row, code, rsum, episodes);
+        else       rollout_steps<false>(e, a, game, row, code, rsum, episodes);
         a.boards[i] = e.s.board.u64();
         a.score[i] = e.s.score;
         a.highest[i] = (uint8_t)e.s.highest;
@@ -353,11 +386,11 @@ int g2048_init(int device)
     G2048_CUDA(cudaMalloc(&st.row, kRowTableBytes));
     G2048_CUDA(cudaMalloc(&st.code, kCodeTableBytes));
     G2048_CUDA(cudaMalloc(&st.overflow, sizeof(unsigned long long)));
-    G2048_CUDA(cudaMalloc(&st.work_counter, sizeof(unsigned int)));
+    G2048_CUDA(cudaMalloc(&st.work_counter, sizeof(unsigned int) * kWorkCounters));
     G2048_CUDA(cudaMemcpy(st.row, row.data(), kRowTableBytes, cudaMemcpyHostToDevice));
     G2048_CUDA(cudaMemcpy(st.code, code.data(), kCodeTableBytes, cudaMemcpyHostToDevice));
     G2048_CUDA(cudaMemset(st.overflow, 0, sizeof(unsigned long long)));
-    G2048_CUDA(cudaMemset(st.work_counter, 0, sizeof(unsigned int)));
+    G2048_CUDA(cudaMemset(st.work_counter, 0, sizeof(unsigned int) * kWorkCounters));
     G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
     const int smem = (int)(kRowTableBytes + kCodeTableBytes);
     G2048_CUDA(cudaFuncSetAttribute(env_step_kernel<true, kEnvSharedThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -9,6 +9,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 
 using std::max;
 using std::min;
@@ -128,17 +129,31 @@ void emul_env_step(EmulEnv *e, uint32_t action, const uint32_t *inject, uint64_t
     o->reward = r.reward; o->score_delta = r.score_delta; o->valid = r.valid; o->done = r.done;
 }
 // `steps` tracked steps with the random-policy action stream and auto-reset, like env_rollout_kernel
-void emul_rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uint32_t game, double *reward_sum, int *episodes)
+}  // extern "C"
+template <bool kTrackMax>
+static void rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uint32_t game, double *reward_sum, int *episodes)
 {
     TrackedEnv t; t.s.board = Board(e->board); t.s.score = e->score; t.s.highest = e->highest; t.s.spawn_ctr = e->spawn_ctr;
     track(t);
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t saturated = 0;
     for (int i = 0; i < steps; ++i) {
-        StepResult r = env_step_tracked<true>(t, random_action(k0, k1, game, t0 + i), g_row, g_code, k0, k1, game, &g_overflow);
-        *reward_sum += r.reward;
-        if (r.done) { ++*episodes; env_reset(t.s, k0, k1, game); track(t); }
+        bool full;
+        PendingReward p = step_move<kTrackMax>(t, random_action(k0, k1, game, t0 + i), g_row, g_code, k0, k1, game, saturated, full);
+        *reward_sum += step_reward(p);
+        bool done = full && full_board_game_over(t.s.board);
+        if (full && done != env_game_over(t.s.board)) __builtin_trap();   // the two game-over tests must agree
+        if (done) { ++*episodes; env_reset(t.s, k0, k1, game); track(t); }
     }
+    g_overflow += saturated;
+    if (!kTrackMax) t.s.highest = max_exponent(t.s.board);
     e->board = t.s.board.u64(); e->score = t.s.score; e->highest = t.s.highest; e->spawn_ctr = t.s.spawn_ctr;
+}
+extern "C" {
+void emul_rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uint32_t game, double *reward_sum, int *episodes, int track_max)
+{
+    if (track_max) rollout_tracked<true>(e, steps, t0, seed, game, reward_sum, episodes);
+    else rollout_tracked<false>(e, steps, t0, seed, game, reward_sum, episodes);
 }
 unsigned long long emul_overflow(void) { return g_overflow; }
 

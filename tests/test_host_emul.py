@@ -56,7 +56,7 @@ def emul():
     L.emul_random_action.argtypes = [u64, u32, u32]; L.emul_random_action.restype = u32
     L.emul_env_reset.argtypes = [C.POINTER(EmulEnv), u64, u32]
     L.emul_env_step.argtypes = [C.POINTER(EmulEnv), u32, C.POINTER(u32), u64, u32, C.POINTER(EmulStep)]
-    L.emul_rollout_tracked.argtypes = [C.POINTER(EmulEnv), C.c_int, u32, u64, u32, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.emul_rollout_tracked.argtypes = [C.POINTER(EmulEnv), C.c_int, u32, u64, u32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     L.emul_row.argtypes = [u32]; L.emul_row.restype = u32
     L.emul_code.argtypes = [u32]; L.emul_code.restype = u32
     L.emul_overflow.restype = C.c_ulonglong
@@ -222,7 +222,7 @@ def test_tracked_rollout_step_matches_oracle(emul, orc):
     for i in range(n):
         e = EmulEnv(packing.pack_board(start[i]), 0, int(start[i].max()).bit_length() - 1, 2)
         rs = C.c_double(0.0); ep = C.c_int(0)
-        emul.emul_rollout_tracked(C.byref(e), steps, 3, SEED, 700 + i, C.byref(rs), C.byref(ep))
+        emul.emul_rollout_tracked(C.byref(e), steps, 3, SEED, 700 + i, C.byref(rs), C.byref(ep), i & 1)
         assert e.board == packing.pack_board(ob[i]) and e.score == osc[i] and e.spawn_ctr == octr[i]
         assert rs.value == ors[i] and ep.value == oep[i] and (1 << e.highest) == ohi[i]
     assert oep.sum() > 0
