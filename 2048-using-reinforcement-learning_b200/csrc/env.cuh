@@ -76,8 +76,8 @@ __device__ __forceinline__ StepResult env_step(EnvState &s, uint32_t action, con
 // Same transition as env_step(), for callers that keep an env in registers across steps and
 // therefore can carry what a step already knows into the next one: the empty count, the sum
 // of the tile values (a move conserves it, a spawn adds 2 or 4) and the board's max exponent
-// (it grows by one exactly when two max tiles merge).  Bit-exact with env_step(); the tests
-// compare both with the oracle.
+// (it grows by one exactly when two max tiles merge).  Bit-exact with env_step(); the GPU
+// tests hold both to the same reference results.
 struct TrackedEnv {
     EnvState s;
     int n_empty;          // empty cells of s.board
