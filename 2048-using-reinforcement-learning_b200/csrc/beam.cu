@@ -35,7 +35,7 @@ constexpr size_t kBeamSmemBytes = kRowTableBytes + kBeamWarps * sizeof(WarpScrat
 struct BeamParams {
     int width, depth;
     int early_thr, mid_thr;
-    uint32_t k0, k1;
+    PhiloxKey K;
 };
 struct BeamResult {
     uint32_t action;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void agent_children(Board b, const uint16_t *row, Boa
 __device__ __forceinline__ int tile_value(uint32_t e) { return e ? (1 << e) : 0; }
 
 // All 32 lanes call this with the same root / parameters.
-__device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamParams &P, uint32_t game,
+__device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_given, const BeamParams &P, uint32_t game,
                                        uint32_t call, const uint16_t *row, WarpScratch &ws)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -118,7 +118,9 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
     const int depth = max(1, n0 <= 4 ? min(P.depth + 5, 25) : n0 >= 10 ? min(P.depth - 5, 10) : P.depth);
 
     Board mine(0u, 0u);          // beam entry of rank `lane`
-    uint32_t my_first = 0u;
+    uint32_t my_first = 0u;      // first action of its path
+    uint32_t my_emax = 0u;       // its largest exponent (a child's is the parent's or one more)
+    const uint32_t root_emax = max_exponent(root);
     int nb = 0;                  // beam entries alive
     uint32_t spawn_base = 0u;    // spawns drawn so far in this call
 
@@ -131,7 +133,7 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
             if (is_cand) {
                 int pos = __popc(bal & lt_mask);
                 ws.cand[pos] = root_child.u64();
-                ws.first[pos] = (uint8_t)lane;
+                ws.first[pos] = (uint8_t)(lane | (root_emax << 2));
             }
             n_valid = __popc(bal);
         } else {                                                        // agent:142-167
@@ -154,7 +156,7 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
             for (int a = 0; a < 4; ++a) {
                 if ((v >> a) & 1u) {
                     ws.cand[pos] = c[a].u64();
-                    ws.first[pos] = (uint8_t)my_first;
+                    ws.first[pos] = (uint8_t)(my_first | (my_emax << 2));
                     ++pos;
                 }
             }
@@ -163,7 +165,7 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
         if (n_valid == 0) {
             if (d > 0) break;                                           // agent:170-171 keeps the old beam
             // agent:126-128: random.choice among the caller's valid moves, one draw
-            Philox4 p = philox4x32_10(0u, call, game, DOM_BEAM, P.k0, P.k1);
+            Philox4 p = philox4x32_10(0u, call, game, DOM_BEAM, P.K);
             int pick = (int)__umulhi(p.w[0], (uint32_t)__popc(vm));
             uint32_t m = vm;
             for (int i = 0; i < pick; ++i) m &= m - 1u;
@@ -182,24 +184,31 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
                 const int c = r * 32 + (int)lane;
                 const bool active = c < n_valid;
                 Board b = active ? Board(ws.cand[c]) : Board(0u, 0u);
-                int n_empty = count_empty(b);
+                uint32_t zl = zero_flags(b.lo), zh = zero_flags(b.hi);
+                int n_empty = __popc(zl) + __popc(zh);
                 const bool draws = active && n_empty > 0;               // agent:262-263: no draw on a full board
                 uint32_t bal = __ballot_sync(FULL, draws);
                 if (draws) {
-                    SpawnWords w = spawn_words(P.k0, P.k1, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lt_mask));
-                    place_tile(b, w.pos, w.val);
+                    SpawnWords w = spawn_words(P.K, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lt_mask));
+                    Spawned sp = place_tile_flags(b, zl, zh, n_empty, w.pos, w.val);
+                    uint32_t flag = sp.tile >> (sp.exponent - 1u);
+                    zl &= sp.in_hi ? ~0u : ~flag;
+                    zh &= sp.in_hi ? ~flag : ~0u;
                     n_empty -= 1;
                 }
                 spawn_base += (uint32_t)__popc(bal);
                 if (active) {
-                    const uint32_t emax = max_exponent(b);
-                    const uint32_t tail = ((uint32_t)(127 - c) << 2) | ws.first[c];
+                    const uint32_t fe = ws.first[c];
+                    const uint32_t pmax = fe >> 2;                      // parent's largest exponent
+                    const uint32_t emax = pmax + ((pmax < 15u && has_exponent(b, pmax + 1u)) ? 1u : 0u);
+                    const uint32_t tail = ((uint32_t)(127 - c) << 2) | (fe & 3u);
                     ws.cand[c] = b.u64();
+                    ws.first[c] = (uint8_t)((fe & 3u) | (emax << 2));
                     if (full_level) {
-                        ws.score[c] = full_eval(b, n_empty, emax, phase);
+                        ws.score[c] = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase);
                         key[r] = tail;                                  // rank field filled in below
                     } else {
-                        key[r] = ((uint32_t)fast_eval(b, n_empty, emax) << 9) | tail;
+                        key[r] = ((uint32_t)fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax) << 9) | tail;
                     }
                 }
             }
@@ -237,6 +246,7 @@ __device__ BeamResult beam_search_warp(Board root, int legal_given, const BeamPa
         if ((int)lane < nb) {
             mine = Board(ws.cand[pick]);
             my_first = top & 3u;
+            my_emax = ws.first[pick] >> 2;
         }
         const int pick0 = __shfl_sync(FULL, pick, 0);
         const uint32_t top0 = __shfl_sync(FULL, top, 0);
@@ -316,8 +326,8 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         const uint32_t game = a.game0 + g;
         EnvState s;
         s.spawn_ctr = 0u;
-        env_reset(s, a.P.k0, a.P.k1, game);      // Game2048Env() -> __init__ calls reset (env:27)
-        env_reset(s, a.P.k0, a.P.k1, game);      // state = env.reset() (evaluate_beam_search.py:30)
+        env_reset(s, a.P.K, game);      // Game2048Env() -> __init__ calls reset (env:27)
+        env_reset(s, a.P.K, game);      // state = env.reset() (evaluate_beam_search.py:30)
         int moves = 0, n_valid = 0, n_invalid = 0;
         long long nodes = 0;
         int ms[8];
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         while (!done && moves < a.max_moves) {
             BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)moves, row, ws);
             nodes += r.nodes;
-            StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.k0, a.P.k1, game, nullptr, a.overflow);
+            StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
             done = st.done;
             ++moves;
             if (st.valid) ++n_valid; else ++n_invalid;
@@ -380,7 +390,7 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
     BeamArgs a{roots, legal, call, call0, action, prob, best_score, nodes, n,
-               BeamParams{beam_width, search_depth, early_thr, mid_thr, (uint32_t)seed, (uint32_t)(seed >> 32)},
+               BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                game0, st->row, next_work_counter(st)};
     G2048_CUDA(cudaMemsetAsync(a.work, 0, sizeof(unsigned int), stream));
     int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
@@ -399,7 +409,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     if (rc != G2048_OK) return rc;
     unsigned int *work = next_work_counter(st);
     G2048_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned int), stream));
-    GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, (uint32_t)seed, (uint32_t)(seed >> 32)},
+    GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
                 st->row, st->code, st->overflow, work};
     int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;

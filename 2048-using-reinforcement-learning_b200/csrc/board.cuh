@@ -25,11 +25,19 @@ __device__ __forceinline__ bool operator!=(const Board &a, const Board &b) { ret
 constexpr uint32_t LSB4 = 0x11111111u;   // bit 0 of every nibble
 constexpr uint32_t MSB4 = 0x88888888u;   // bit 3 of every nibble
 
+// x >> k on the FMA pipe (IMAD.HI by 2^(32-k)): the kernels are bound by the ALU pipe, which
+// executes LOP3/SHF/PRMT; moving some constant right shifts over balances the two pipes.
+#ifdef G2048_SHR_ON_FMA
+template <int k> __device__ __forceinline__ uint32_t shr(uint32_t x) { return __umulhi(x, 1u << (32 - k)); }
+#else
+template <int k> __device__ __forceinline__ uint32_t shr(uint32_t x) { return x >> k; }
+#endif
+
 // bit 4i set  <=>  nibble i of x is non-zero
 __device__ __forceinline__ uint32_t nz_flags(uint32_t x)
 {
-    uint32_t t = x | (x >> 1);
-    t |= t >> 2;
+    uint32_t t = x | shr<1>(x);
+    t |= shr<2>(t);
     return t & LSB4;
 }
 // bit 4i set  <=>  nibble i of x is zero
@@ -43,13 +51,13 @@ __device__ __forceinline__ uint32_t bitselect(uint32_t mask, uint32_t a, uint32_
 // off-diagonal 2x2 blocks (a byte permutation across the halves).
 __device__ __forceinline__ Board transpose(Board b)
 {
-    uint32_t l = bitselect(0x0000F0F0u, b.lo >> 12, bitselect(0x0F0F0000u, b.lo << 12, b.lo));
-    uint32_t h = bitselect(0x0000F0F0u, b.hi >> 12, bitselect(0x0F0F0000u, b.hi << 12, b.hi));
+    uint32_t l = bitselect(0x0000F0F0u, shr<12>(b.lo), bitselect(0x0F0F0000u, b.lo << 12, b.lo));
+    uint32_t h = bitselect(0x0000F0F0u, shr<12>(b.hi), bitselect(0x0F0F0000u, b.hi << 12, b.hi));
     return Board(__byte_perm(l, h, 0x6240), __byte_perm(l, h, 0x7351));
 }
 __device__ __forceinline__ uint32_t swap_nibbles_in_bytes(uint32_t x)
 {
-    return bitselect(0xF0F0F0F0u, x << 4, x >> 4);
+    return bitselect(0xF0F0F0F0u, x << 4, shr<4>(x));
 }
 // np.fliplr: reverse the 4 nibbles of every row
 __device__ __forceinline__ Board flip_rows(Board b)
@@ -229,24 +237,38 @@ __device__ __forceinline__ uint32_t max_exponent(Board b)
 // does any nibble of the board equal v (1..15)?
 __device__ __forceinline__ bool has_exponent(Board b, uint32_t v)
 {
-    uint32_t rep = v * LSB4;
-    return (zero_flags(b.lo ^ rep) | zero_flags(b.hi ^ rep)) != 0u;
+    uint32_t rep = v * LSB4, x = b.lo ^ rep, y = b.hi ^ rep;
+    // "some nibble is zero" by the borrow trick (exact as an any-test)
+    return ((((x - LSB4) & ~x) | ((y - LSB4) & ~y)) & MSB4) != 0u;
 }
 
 // ---- Philox4x32-10 ---------------------------------------------------------------
 struct Philox4 { uint32_t w[4]; };
 
+// The ten round keys of a seed (key schedule k + r * Weyl constant).  Built once on the host and
+// passed by value in the kernel arguments, so every round reads its keys as constant-bank
+// operands instead of spending two integer adds per round per thread.
+struct PhiloxKey {
+    uint32_t k0[10], k1[10];
+};
+inline PhiloxKey make_philox_key(uint64_t seed)
+{
+    PhiloxKey K;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.k0[r] = a; K.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return K;
+}
+
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1)
+                                                 const PhiloxKey &K)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r];
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
     return o;
@@ -256,18 +278,18 @@ enum : uint32_t { DOM_ENV = 0, DOM_BEAM = 1, DOM_ACTION = 2, DOM_BOARD = 3 };
 
 struct SpawnWords { uint32_t pos, val; };
 // spawn i of stream (seed, game, call, domain): words 2(i&1), 2(i&1)+1 of block i>>1
-__device__ __forceinline__ SpawnWords spawn_words(uint32_t k0, uint32_t k1, uint32_t game, uint32_t call,
+__device__ __forceinline__ SpawnWords spawn_words(const PhiloxKey &K, uint32_t game, uint32_t call,
                                                   uint32_t domain, uint32_t i)
 {
-    Philox4 p = philox4x32_10(i >> 1, call, game, domain, k0, k1);
+    Philox4 p = philox4x32_10(i >> 1, call, game, domain, K);
     SpawnWords s;
     s.pos = (i & 1u) ? p.w[2] : p.w[0];
     s.val = (i & 1u) ? p.w[3] : p.w[1];
     return s;
 }
-__device__ __forceinline__ uint32_t random_action(uint32_t k0, uint32_t k1, uint32_t game, uint32_t t)
+__device__ __forceinline__ uint32_t random_action(const PhiloxKey &K, uint32_t game, uint32_t t)
 {
-    Philox4 p = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, k0, k1);
+    Philox4 p = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, K);
     uint32_t s = (t >> 4) & 3u;
     uint32_t w = s == 0 ? p.w[0] : s == 1 ? p.w[1] : s == 2 ? p.w[2] : p.w[3];
     return (w >> (2u * (t & 15u))) & 3u;
@@ -327,9 +349,14 @@ __device__ __forceinline__ uint32_t tile_sum_half(uint32_t x, uint32_t cells)
 }
 
 // #equal non-empty neighbour pairs (agent:302-312) and the sum of their exponents (agent:387-403)
+__device__ __forceinline__ void merge_pairs_flags(Board b, uint32_t nl, uint32_t nh, int *pairs, int *exponent_sum);
 __device__ __forceinline__ void merge_pairs(Board b, int *pairs, int *exponent_sum)
 {
-    const uint32_t nl = nz_flags(b.lo), nh = nz_flags(b.hi);
+    merge_pairs_flags(b, nz_flags(b.lo), nz_flags(b.hi), pairs, exponent_sum);
+}
+// nl / nh: occupancy flags (bit 0 of every non-empty nibble) of b.lo / b.hi
+__device__ __forceinline__ void merge_pairs_flags(Board b, uint32_t nl, uint32_t nh, int *pairs, int *exponent_sum)
+{
     uint32_t hl = eq_flags(b.lo, b.lo >> 4) & nl & 0x01110111u;
     uint32_t hh = eq_flags(b.hi, b.hi >> 4) & nh & 0x01110111u;
     uint32_t vl = eq_flags(b.lo, __funnelshift_r(b.lo, b.hi, 16)) & nl;
@@ -346,18 +373,27 @@ __device__ __forceinline__ void merge_pairs(Board b, int *pairs, int *exponent_s
 }
 
 // BeamSearchAgent._fast_evaluate (agent:280-314): always an exact integer.
-__device__ __forceinline__ int fast_eval(Board b, int n_empty, uint32_t emax)
+__device__ __forceinline__ int fast_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax)
 {
     uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
     int corner_score = corner ? (int)(2u << corner) : 0;          // 2 * tile value of the best corner
     int pairs;
-    merge_pairs(b, &pairs, nullptr);
+    merge_pairs_flags(b, nl, nh, &pairs, nullptr);
     return n_empty * 10 + (int)emax * 2 + corner_score + pairs * 2;
+}
+__device__ __forceinline__ int fast_eval(Board b, int n_empty, uint32_t emax)
+{
+    return fast_eval_flags(b, nz_flags(b.lo), nz_flags(b.hi), n_empty, emax);
 }
 
 // BeamSearchAgent._evaluate_state (agent:316-373) in float64 with the reference's operation
 // order and no FMA contraction: bit-exact.  phase 0 early, 1 mid, 2 late.
+__device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax, int phase);
 __device__ __forceinline__ double full_eval(Board b, int n_empty, uint32_t emax, int phase)
+{
+    return full_eval_flags(b, nz_flags(b.lo), nz_flags(b.hi), n_empty, emax, phase);
+}
+__device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax, int phase)
 {
     const double w_empty  = phase == 0 ? 15.0 : phase == 1 ? 10.0 : 8.0;
     const double w_max    = phase == 0 ? 1.0  : phase == 1 ? 1.5  : 2.0;
@@ -372,7 +408,7 @@ __device__ __forceinline__ double full_eval(Board b, int n_empty, uint32_t emax,
     uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
     double corner_bonus = __dmul_rn(__dmul_rn((double)corner, 2.0), w_corner);
     int pairs, esum;
-    merge_pairs(b, &pairs, &esum);
+    merge_pairs_flags(b, nl, nh, &pairs, &esum);
     double merge_potential = __dmul_rn((double)esum, w_merge);
     // snake weights 15 14 13 12 / 8 9 10 11 / 7 6 5 4 / 0 1 2 3 (agent:37-42), exact in int
     int snake = 0;

@@ -19,13 +19,13 @@ struct StepResult {
 };
 
 // Game2048Env.reset (env:29-48): two spawns on an empty board.
-__device__ __forceinline__ void env_reset(EnvState &s, uint32_t k0, uint32_t k1, uint32_t game)
+__device__ __forceinline__ void env_reset(EnvState &s, const PhiloxKey &K, uint32_t game)
 {
     s.board = Board(0u, 0u);
     s.score = 0;
-    SpawnWords a = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr);
+    SpawnWords a = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr);
     place_tile(s.board, a.pos, a.val);
-    SpawnWords b = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr + 1u);
+    SpawnWords b = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr + 1u);
     place_tile(s.board, b.pos, b.val);
     s.spawn_ctr += 2u;
     s.highest = max_exponent(s.board);
@@ -35,7 +35,7 @@ __device__ __forceinline__ void env_reset(EnvState &s, uint32_t k0, uint32_t k1,
 // inject: nullptr or the two raw words to use instead of the env stream.
 template <bool kRowShared, bool kCodeShared, bool kReward>
 __device__ __forceinline__ StepResult env_step(EnvState &s, uint32_t action, const uint16_t *row,
-                                               const uint8_t *code, uint32_t k0, uint32_t k1, uint32_t game,
+                                               const uint8_t *code, const PhiloxKey &K, uint32_t game,
                                                const uint32_t *inject, unsigned long long *overflow)
 {
     StepResult r;
@@ -56,7 +56,7 @@ __device__ __forceinline__ StepResult env_step(EnvState &s, uint32_t action, con
     if (r.valid) {                                                          // env:191-192, always >= 1 empty here
         SpawnWords w;
         if (inject) { w.pos = inject[0]; w.val = inject[1]; }
-        else { w = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr); s.spawn_ctr += 1u; }
+        else { w = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr); s.spawn_ctr += 1u; }
         place_tile(next, w.pos, w.val);
         empty_after -= 1;
     }
@@ -112,7 +112,7 @@ struct PendingReward {
 
 template <bool kTrackMax>
 __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t action, const uint16_t *row,
-                                                   const uint8_t *code, uint32_t k0, uint32_t k1, uint32_t game,
+                                                   const uint8_t *code, const PhiloxKey &K, uint32_t game,
                                                    uint32_t &saturated, bool &full)
 {
     PendingReward p;
@@ -120,7 +120,7 @@ __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t actio
     const Board prev = s.board;
     // the spawn words depend only on the counter: issue the Philox block first so that it
     // overlaps the table lookups (it runs on the FMA pipe, the move on the ALU pipe)
-    const SpawnWords w = spawn_words(k0, k1, game, 0u, DOM_ENV, s.spawn_ctr);
+    const SpawnWords w = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr);
     const Board line = to_line(prev, action);
     Board next = from_line(move_left<true>(line, row), action);
     const uint32_t codes = merge_codes<true>(line, code);                   // action is always 0..3 here

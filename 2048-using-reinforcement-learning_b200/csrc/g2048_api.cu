@@ -75,7 +75,7 @@ struct StepArgs {
     uint64_t *boards; const uint8_t *actions; const uint32_t *inject;
     int32_t *score; uint8_t *highest; uint32_t *spawn_ctr;
     double *reward; float *reward32; int32_t *score_delta; uint8_t *valid; uint8_t *legal; uint8_t *done;
-    int64_t n; uint32_t k0, k1, game0;
+    int64_t n; PhiloxKey K; uint32_t game0;
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
 };
 
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(kThreads) env_step_kernel(StepArgs a)
         uint32_t inj[2];
         if (a.inject) { inj[0] = a.inject[2 * i]; inj[1] = a.inject[2 * i + 1]; }
         StepResult r = want_reward
-            ? env_step<kShared, kShared, true>(s, action, row, code, a.k0, a.k1, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow)
-            : env_step<kShared, kShared, false>(s, action, row, code, a.k0, a.k1, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow);
+            ? env_step<kShared, kShared, true>(s, action, row, code, a.K, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow)
+            : env_step<kShared, kShared, false>(s, action, row, code, a.K, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow);
         a.boards[i] = s.board.u64();
         if (a.score) a.score[i] = s.score;
         if (a.highest) a.highest[i] = (uint8_t)s.highest;
@@ -118,13 +118,13 @@ __global__ void __launch_bounds__(kThreads) env_step_kernel(StepArgs a)
 }
 
 __global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(uint64_t *boards, int32_t *score, uint8_t *highest,
-                                                                 uint32_t *spawn_ctr, int64_t n, uint32_t k0,
-                                                                 uint32_t k1, uint32_t game0)
+                                                                 uint32_t *spawn_ctr, int64_t n, PhiloxKey K,
+                                                                 uint32_t game0)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         EnvState s;
         s.spawn_ctr = spawn_ctr ? spawn_ctr[i] : 0u;
-        env_reset(s, k0, k1, game0 + (uint32_t)i);
+        env_reset(s, K, game0 + (uint32_t)i);
         boards[i] = s.board.u64();
         if (score) score[i] = 0;
         if (highest) highest[i] = (uint8_t)s.highest;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(uint64_t *boards
 struct RolloutArgs {
     uint64_t *boards; int32_t *score; uint8_t *highest; uint32_t *spawn_ctr;
     double *reward_sum; int32_t *episodes;
-    int64_t n; int32_t steps; uint32_t t0; uint32_t k0, k1, game0;
+    int64_t n; int32_t steps; uint32_t t0; PhiloxKey K; uint32_t game0;
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
 };
 
@@ -149,9 +149,9 @@ constexpr int kRolloutUnroll = G2048_ROLLOUT_UNROLL;   // steps per loop trip (I
 
 // Uniform random action of step t from the cached Philox action block (64 actions per block).
 __device__ __forceinline__ uint32_t cached_action(Philox4 &act, uint32_t t, bool first, uint32_t game,
-                                                  uint32_t k0, uint32_t k1)
+                                                  const PhiloxKey &K)
 {
-    if ((t & 63u) == 0u && !first) act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, k0, k1);
+    if ((t & 63u) == 0u && !first) act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, K);
     const uint32_t sel = (t >> 4) & 3u;
     const uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
     return (word >> (2u * (t & 15u))) & 3u;
@@ -163,18 +163,18 @@ __device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &
                                               const uint8_t *code, double &rsum, int32_t &episodes)
 {
     if (a.steps <= 0) return;
-    Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.k0, a.k1);
+    Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.K);
     uint32_t saturated = 0u;
     bool full;
-    PendingReward pend = step_move<kTrackMax>(e, cached_action(act, a.t0, true, game, a.k0, a.k1), row, code,
-                                              a.k0, a.k1, game, saturated, full);
-    if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.k0, a.k1, game); track(e); }
+    PendingReward pend = step_move<kTrackMax>(e, cached_action(act, a.t0, true, game, a.K), row, code,
+                                              a.K, game, saturated, full);
+    if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
     for (int32_t step = 1; step < a.steps; ++step) {
-        const uint32_t action = cached_action(act, a.t0 + (uint32_t)step, false, game, a.k0, a.k1);
-        PendingReward cur = step_move<kTrackMax>(e, action, row, code, a.k0, a.k1, game, saturated, full);
+        const uint32_t action = cached_action(act, a.t0 + (uint32_t)step, false, game, a.K);
+        PendingReward cur = step_move<kTrackMax>(e, action, row, code, a.K, game, saturated, full);
         rsum = __dadd_rn(rsum, step_reward(pend));          // float64 sum stays in step order
         pend = cur;
-        if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.k0, a.k1, game); track(e); }
+        if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
     }
     rsum = __dadd_rn(rsum, step_reward(pend));
     if (saturated) atomicAdd(a.overflow, 1ull);
@@ -280,13 +280,13 @@ __global__ void observe_kernel(const uint64_t *boards, float *obs, int64_t n)
     }
 }
 
-__global__ void synthetic_kernel(uint64_t *boards, int64_t n, uint32_t k0, uint32_t k1, uint32_t game0)
+__global__ void synthetic_kernel(uint64_t *boards, int64_t n, PhiloxKey K, uint32_t game0)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         uint64_t b = 0;
 #pragma unroll
         for (uint32_t blk = 0; blk < 4; ++blk) {
-            Philox4 p = philox4x32_10(blk, 0u, game0 + (uint32_t)i, DOM_BOARD, k0, k1);
+            Philox4 p = philox4x32_10(blk, 0u, game0 + (uint32_t)i, DOM_BOARD, K);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint32_t x = p.w[j];
@@ -454,7 +454,7 @@ int g2048_observe(const uint64_t *boards, float *obs, int64_t n, void *stream)
 int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t game0, void *stream)
 {
     G2048_ENTER(boards);
-    synthetic_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(boards, n, (uint32_t)seed, (uint32_t)(seed >> 32), game0);
+    synthetic_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(boards, n, make_philox_key(seed), game0);
     G2048_LAUNCHED();
 }
 
@@ -463,7 +463,7 @@ int g2048_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint
 {
     G2048_ENTER(boards);
     env_reset_kernel<<<grid_for(n, kEnvThreads, st->sm_count, 8), kEnvThreads, 0, s>>>(
-        boards, score, highest_exp, spawn_ctr, n, (uint32_t)seed, (uint32_t)(seed >> 32), game0);
+        boards, score, highest_exp, spawn_ctr, n, make_philox_key(seed), game0);
     G2048_LAUNCHED();
 }
 
@@ -475,7 +475,7 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
 {
     G2048_ENTER(boards && actions);
     StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, (uint32_t)seed, (uint32_t)(seed >> 32), game0, st->row, st->code, st->overflow};
+               valid, legal, done, n, make_philox_key(seed), game0, st->row, st->code, st->overflow};
     if (use_shared_tables(n, st->sm_count)) {
         env_step_kernel<true, kEnvSharedThreads><<<st->sm_count, kEnvSharedThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
     } else {
@@ -497,7 +497,7 @@ int g2048_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_exp, ui
 {
     G2048_ENTER(boards && score && highest_exp && spawn_ctr && steps >= 0);
     RolloutArgs a{boards, score, highest_exp, spawn_ctr, reward_sum, episodes, n, steps, t0,
-                  (uint32_t)seed, (uint32_t)(seed >> 32), game0, st->row, st->code, st->overflow};
+                  make_philox_key(seed), game0, st->row, st->code, st->overflow};
     // one 192 KiB block per SM; spread the envs over ALL SMs (65,536 envs -> 148 blocks x 448 threads)
     int grid = (int)(n < st->sm_count ? n : st->sm_count);
     int64_t per_block = (n + grid - 1) / grid;

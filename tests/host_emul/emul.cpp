@@ -103,12 +103,13 @@ int emul_fast_eval(uint64_t b) { Board x(b); return fast_eval(x, count_empty(x),
 double emul_full_eval(uint64_t b, int phase) { Board x(b); return full_eval(x, count_empty(x), max_exponent(x), phase); }
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)
 {
-    Philox4 p = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    PhiloxKey K; { uint32_t a = k0, b = k1; for (int r = 0; r < 10; ++r) { K.k0[r] = a; K.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; } }
+    Philox4 p = philox4x32_10(c0, c1, c2, c3, K);
     for (int i = 0; i < 4; ++i) out[i] = p.w[i];
 }
 uint32_t emul_random_action(uint64_t seed, uint32_t game, uint32_t t)
 {
-    return random_action((uint32_t)seed, (uint32_t)(seed >> 32), game, t);
+    return random_action(make_philox_key(seed), game, t);
 }
 
 struct EmulEnv { uint64_t board; int32_t score; uint32_t highest; uint32_t spawn_ctr; };
@@ -117,13 +118,13 @@ struct EmulStep { double reward; uint32_t score_delta; int32_t valid; int32_t do
 void emul_env_reset(EmulEnv *e, uint64_t seed, uint32_t game)
 {
     EnvState s; s.spawn_ctr = e->spawn_ctr;
-    env_reset(s, (uint32_t)seed, (uint32_t)(seed >> 32), game);
+    env_reset(s, make_philox_key(seed), game);
     e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
 }
 void emul_env_step(EmulEnv *e, uint32_t action, const uint32_t *inject, uint64_t seed, uint32_t game, EmulStep *o)
 {
     EnvState s; s.board = Board(e->board); s.score = e->score; s.highest = e->highest; s.spawn_ctr = e->spawn_ctr;
-    StepResult r = env_step<false, false, true>(s, action, g_row, g_code, (uint32_t)seed, (uint32_t)(seed >> 32), game,
+    StepResult r = env_step<false, false, true>(s, action, g_row, g_code, make_philox_key(seed), game,
                                                 inject, &g_overflow);
     e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
     o->reward = r.reward; o->score_delta = r.score_delta; o->valid = r.valid; o->done = r.done;
@@ -135,15 +136,15 @@ static void rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, u
 {
     TrackedEnv t; t.s.board = Board(e->board); t.s.score = e->score; t.s.highest = e->highest; t.s.spawn_ctr = e->spawn_ctr;
     track(t);
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const PhiloxKey K = make_philox_key(seed);
     uint32_t saturated = 0;
     for (int i = 0; i < steps; ++i) {
         bool full;
-        PendingReward p = step_move<kTrackMax>(t, random_action(k0, k1, game, t0 + i), g_row, g_code, k0, k1, game, saturated, full);
+        PendingReward p = step_move<kTrackMax>(t, random_action(K, game, t0 + i), g_row, g_code, K, game, saturated, full);
         *reward_sum += step_reward(p);
         bool done = full && full_board_game_over(t.s.board);
         if (full && done != env_game_over(t.s.board)) __builtin_trap();   // the two game-over tests must agree
-        if (done) { ++*episodes; env_reset(t.s, k0, k1, game); track(t); }
+        if (done) { ++*episodes; env_reset(t.s, K, game); track(t); }
     }
     g_overflow += saturated;
     if (!kTrackMax) t.s.highest = max_exponent(t.s.board);
