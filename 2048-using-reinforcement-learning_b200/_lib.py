@@ -48,6 +48,11 @@ _SIGNATURES = {
     "g2048_pack": ([_vp, _vp, _i64, _vp], C.c_int),
     "g2048_unpack": ([_vp, _vp, _i64, _vp], C.c_int),
     "g2048_observe": ([_vp, _vp, _i64, _vp], C.c_int),
+    "g2048_simulate_move": ([_vp] * 7 + [_i64, _vp], C.c_int),
+    "g2048_evaluate_pattern": ([_vp, _vp, _i64, _vp], C.c_int),
+    "g2048_host_simulate_move": ([_vp] * 8 + [_i64], C.c_int),
+    "g2048_ppo_features": ([_vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
+    "g2048_host_ppo_features": ([_vp, _vp, _vp, _vp, _i64], C.c_int),
     "g2048_synthetic_boards": ([_vp, _i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_reset": ([_vp, _vp, _vp, _vp, _i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_step": ([_vp] * 12 + [_i64, _u64, _u32, _vp], C.c_int),

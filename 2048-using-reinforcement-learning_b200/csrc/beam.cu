@@ -339,11 +339,12 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
             nodes += r.nodes;
             StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
             done = st.done;
-            ++moves;
-            if (st.valid) ++n_valid; else ++n_invalid;
+            // evaluate_beam_search.py:59-64 records the move index BEFORE `moves += 1` (:86)
 #pragma unroll
             for (int m = 0; m < 8; ++m)
                 if (ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) ms[m] = moves;
+            if (st.valid) ++n_valid; else ++n_invalid;
+            ++moves;
         }
         if (lane == 0) {
             if (a.score) a.score[g] = s.score;

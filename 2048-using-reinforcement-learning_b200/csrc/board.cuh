@@ -522,4 +522,47 @@ __device__ __forceinline__ double shaped_reward(bool valid, int empty_before, Bo
     return reward;
 }
 
+// ---- PPO-side features (agents/ppo_agent.py), SURVEY 8f row 1 -----------------------------------
+// evaluate_heuristic (ppo_agent.py:271-333): 2 * best-direction monotonicity / 24
+// + 1 if the largest corner holds the largest tile - 0.1 * #(tiles >= 8); float64, same order.
+__device__ __forceinline__ double ppo_heuristic(Board b)
+{
+    const uint32_t nl = nz_flags(b.lo) << 3, nh = nz_flags(b.hi) << 3;       // occupancy on bit 3
+    const uint32_t HP = 0x08880888u;
+    // horizontal pairs (left, right), flag on the left cell
+    uint32_t hml = nl & (nl >> 4) & HP, hmh = nh & (nh >> 4) & HP;
+    int h_le = __popc(ge_flags(b.lo >> 4, b.lo) & hml) + __popc(ge_flags(b.hi >> 4, b.hi) & hmh);
+    int h_ge = __popc(ge_flags(b.lo, b.lo >> 4) & hml) + __popc(ge_flags(b.hi, b.hi >> 4) & hmh);
+    // vertical pairs (upper, lower), flag on the upper cell
+    uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16), below_hi = b.hi >> 16;
+    uint32_t vml = nl & __funnelshift_r(nl, nh, 16), vmh = nh & (nh >> 16) & 0x00008888u;
+    int v_le = __popc(ge_flags(below_lo, b.lo) & vml) + __popc(ge_flags(below_hi, b.hi) & vmh);
+    int v_ge = __popc(ge_flags(b.lo, below_lo) & vml) + __popc(ge_flags(b.hi, below_hi) & vmh);
+    int best = max(h_le, h_ge) + max(v_le, v_ge);         // max over the four (row_dir, col_dir) pairs
+    double score = __dmul_rn(2.0, __ddiv_rn((double)best, 24.0));
+    uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
+    if (corner == max_exponent(b)) score = __dadd_rn(score, 1.0);
+    // tiles >= 8  <=>  exponent >= 3
+    int high = __popc(ge_flags(b.lo, 0x33333333u)) + __popc(ge_flags(b.hi, 0x33333333u));
+    if (high > 0) score = __dadd_rn(score, __dmul_rn(-0.1, (double)high));
+    return score;
+}
+
+// 0.1 * sum(log2 of the four largest tiles) (ppo_agent.py:251-254): exponents are summed exactly
+__device__ __forceinline__ double ppo_top4_bonus(Board b)
+{
+    // counting sort over the 16 possible exponents: cnt[e] packed 5 bits each would overflow a
+    // word, so walk the exponents from the top and take what is still needed
+    int need = 4, sum = 0;
+#pragma unroll
+    for (int e = 15; e >= 1; --e) {
+        uint32_t rep = (uint32_t)e * LSB4;
+        int c = __popc(zero_flags(b.lo ^ rep)) + __popc(zero_flags(b.hi ^ rep));
+        int take = min(c, need);
+        sum += take * e;
+        need -= take;
+    }
+    return __dmul_rn(0.1, (double)sum);
+}
+
 }  // namespace g2048

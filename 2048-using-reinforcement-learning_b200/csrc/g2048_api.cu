@@ -280,6 +280,90 @@ __global__ void observe_kernel(const uint64_t *boards, float *obs, int64_t n)
     }
 }
 
+// Game2048Env.simulate_move (env:341-387): all (empty cell, tile in {2,4}) outcomes of a move, one
+// (board, action) per thread.  The reference's loop never restores self.board (env:378), so every
+// outcome starts from the PREVIOUS outcome and the reward (env:375) is computed on that previous
+// board; reproduced as is.  Outcome k of board i lands at index 32*i + k; count[i] <= 30.
+constexpr int kSimStride = 32;
+__global__ void simulate_move_kernel(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest,
+                                     uint64_t *out_boards, double *out_reward, uint8_t *out_done, int32_t *count,
+                                     int64_t n, const uint16_t *row, const uint8_t *code)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Board state(boards[i]);
+        const uint32_t action = actions[i];
+        const uint32_t hi_exp = highest ? highest[i] : 0u;
+        const Board line = to_line(state, action);
+        Board cur = from_line(move_left<false>(line, row), action);
+        uint32_t sat;
+        uint32_t gained = decode_score(merge_codes<false>(line, code), &sat);
+        if (action >= 4u) { cur = state; gained = 0u; }
+        int k = 0;
+        if (cur != state) {
+            const uint64_t moved = cur.u64();
+            const int empty_before = count_empty(state);
+            const uint32_t prev_max = max_exponent(state);
+            for (int cell = 0; cell < 16; ++cell) {
+                if ((moved >> (4 * cell)) & 15ull) continue;                 // env:367: empties of the moved board
+                for (uint32_t e = 1; e <= 2; ++e) {
+                    uint64_t ns = (cur.u64() & ~(15ull << (4 * cell))) | ((uint64_t)e << (4 * cell));
+                    double r = shaped_reward(true, empty_before, cur, count_empty(cur), gained, hi_exp, prev_max);
+                    cur = Board(ns);
+                    if (out_boards) out_boards[kSimStride * i + k] = ns;
+                    if (out_reward) out_reward[kSimStride * i + k] = r;
+                    if (out_done) out_done[kSimStride * i + k] = env_game_over(cur);
+                    ++k;
+                }
+            }
+        }
+        if (count) count[i] = k;
+    }
+}
+
+// Game2048Env._evaluate_pattern (env:313-339): max(snake-weighted, corner-weighted tile sum) / 100
+__global__ void pattern_kernel(const uint64_t *boards, double *out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = boards[i];
+        double snake = 0.0, corner = 0.0;          // exact: dyadic partial sums far below 2^53
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int r = c >> 2, q = c & 3;
+            const double ws = (r & 1) ? (double)(16 - 4 * r - 3 + q) : (double)(16 - 4 * r - q);   // 16 15 14 13 / 9 10 11 12 / 8 7 6 5 / 1 2 3 4
+            const double wc = 16.0 / (double)(1 << (r + q));                                         // 16 8 4 2 / 8 4 2 1 / ...
+            uint32_t e = (uint32_t)(b >> (4 * c)) & 15u;
+            double v = e ? (double)(1u << e) : 0.0;
+            snake = __dadd_rn(snake, __dmul_rn(v, ws));
+            corner = __dadd_rn(corner, __dmul_rn(v, wc));
+        }
+        snake = __ddiv_rn(snake, 100.0);
+        corner = __ddiv_rn(corner, 100.0);
+        out[i] = snake > corner ? snake : corner;
+    }
+}
+
+// normalize_state + the per-state shaping terms of PPOAgent.remember (ppo_agent.py:184-195,
+// 251-254, 271-333) in one pass over the boards; every output is optional.
+__global__ void ppo_features_kernel(const uint64_t *boards, float *obs, double *heuristic, double *top4, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t raw = boards[i];
+        Board b(raw);
+        if (obs) {
+            float4 *o = reinterpret_cast<float4 *>(obs + 16 * i);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = (float)((uint32_t)(raw >> (4 * (4 * q + j))) & 15u) / 15.0f;
+                o[q] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        if (heuristic) heuristic[i] = ppo_heuristic(b);
+        if (top4) top4[i] = ppo_top4_bonus(b);
+    }
+}
+
 __global__ void synthetic_kernel(uint64_t *boards, int64_t n, PhiloxKey K, uint32_t game0)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -448,6 +532,29 @@ int g2048_observe(const uint64_t *boards, float *obs, int64_t n, void *stream)
 {
     G2048_ENTER(boards && obs);
     observe_kernel<<<grid_for(n, 256, st->sm_count, 16), 256, 0, s>>>(boards, obs, n);
+    G2048_LAUNCHED();
+}
+
+int g2048_simulate_move(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest_exp,
+                        uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count, int64_t n, void *stream)
+{
+    G2048_ENTER(boards && actions);
+    simulate_move_kernel<<<grid_for(n, 128, st->sm_count, 16), 128, 0, s>>>(boards, actions, highest_exp, next_boards, reward,
+                                                                          done, count, n, st->row, st->code);
+    G2048_LAUNCHED();
+}
+
+int g2048_evaluate_pattern(const uint64_t *boards, double *pattern, int64_t n, void *stream)
+{
+    G2048_ENTER(boards && pattern);
+    pattern_kernel<<<grid_for(n, 256, st->sm_count, 8), 256, 0, s>>>(boards, pattern, n);
+    G2048_LAUNCHED();
+}
+
+int g2048_ppo_features(const uint64_t *boards, float *obs, double *heuristic, double *top4_bonus, int64_t n, void *stream)
+{
+    G2048_ENTER(boards);
+    ppo_features_kernel<<<grid_for(n, 256, st->sm_count, 8), 256, 0, s>>>(boards, obs, heuristic, top4_bonus, n);
     G2048_LAUNCHED();
 }
 
@@ -723,6 +830,58 @@ int g2048_host_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *
     G2048_TRY(g2048_legal_masks(d_b, d_e, d_g, n, a->stream));
     G2048_TRY(to_host(a, env_legal, d_e, n));
     G2048_TRY(to_host(a, agent_legal, d_g, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_ppo_features(const uint64_t *boards, float *obs, double *heuristic, double *top4_bonus, int64_t n)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_ppo_features: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<float>(16 * n) + 2 * arena_bytes<double>(n)));
+    uint64_t *d_b; float *d_o = nullptr; double *d_h = nullptr, *d_t = nullptr;
+    G2048_TRY(to_device(a, &d_b, boards, n, true));
+    if (obs) d_o = arena_take<float>(a, 16 * n);
+    if (heuristic) d_h = arena_take<double>(a, n);
+    if (top4_bonus) d_t = arena_take<double>(a, n);
+    G2048_TRY(g2048_ppo_features(d_b, d_o, d_h, d_t, n, a->stream));
+    G2048_TRY(to_host(a, obs, d_o, 16 * n));
+    G2048_TRY(to_host(a, heuristic, d_h, n));
+    G2048_TRY(to_host(a, top4_bonus, d_t, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_simulate_move(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest_exp,
+                             uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count, double *pattern, int64_t n)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards || !actions) return set_error(G2048_EINVAL, "g2048_host_simulate_move: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<uint8_t>(n) + arena_bytes<uint64_t>(32 * n) +
+                                  arena_bytes<double>(32 * n) + arena_bytes<uint8_t>(32 * n) + arena_bytes<int32_t>(n) +
+                                  arena_bytes<double>(n)));
+    uint64_t *d_b; uint8_t *d_a; uint8_t *d_h = nullptr;
+    G2048_TRY(to_device(a, &d_b, boards, n, true));
+    G2048_TRY(to_device(a, &d_a, actions, n, true));
+    if (highest_exp) G2048_TRY(to_device(a, &d_h, highest_exp, n, true));
+    uint64_t *d_nb = arena_take<uint64_t>(a, 32 * n);
+    double *d_r = arena_take<double>(a, 32 * n);
+    uint8_t *d_d = arena_take<uint8_t>(a, 32 * n);
+    int32_t *d_c = arena_take<int32_t>(a, n);
+    double *d_p = arena_take<double>(a, n);
+    G2048_TRY(g2048_simulate_move(d_b, d_a, d_h, d_nb, d_r, d_d, d_c, n, a->stream));
+    if (pattern) G2048_TRY(g2048_evaluate_pattern(d_b, d_p, n, a->stream));
+    G2048_TRY(to_host(a, next_boards, d_nb, 32 * n));
+    G2048_TRY(to_host(a, reward, d_r, 32 * n));
+    G2048_TRY(to_host(a, done, d_d, 32 * n));
+    G2048_TRY(to_host(a, count, d_c, n));
+    G2048_TRY(to_host(a, pattern, d_p, n));
     G2048_CUDA(cudaStreamSynchronize(a->stream));
     return G2048_OK;
 }

@@ -106,6 +106,28 @@ class Game2048Env:
         return self.get_state(), np.float64(r[0]), self.game_over, {
             "score": self.score, "valid_move": bool(v[0]), "highest_tile": self.highest_tile}
 
+    def simulate_move(self, state, action):
+        """env:341-387 -> list of (next_state int32[16], reward, done) for every empty cell x {2, 4}.
+        Keeps the reference's behaviour, including that outcomes build on one another (env:371,378).
+        Does not touch the environment's own board or score."""
+        lib = _lib.use_device(self._device)
+        b = np.array([pack_board(np.asarray(state).reshape(16))], dtype=np.uint64)
+        a = np.array([int(action) if 0 <= int(action) <= 255 else 255], np.uint8)
+        h = np.array([_exp_of(self.highest_tile)], np.uint8)
+        nb = np.zeros(32, np.uint64); r = np.zeros(32, np.float64); d = np.zeros(32, np.uint8); c = np.zeros(1, np.int32)
+        _lib.check(lib.g2048_host_simulate_move(_lib.np_ptr(b), _lib.np_ptr(a), _lib.np_ptr(h), _lib.np_ptr(nb),
+                                                _lib.np_ptr(r), _lib.np_ptr(d), _lib.np_ptr(c), None, 1))
+        states = unpack_boards(nb[:int(c[0])])
+        return [(states[k].copy(), np.float64(r[k]), bool(d[k])) for k in range(int(c[0]))]
+
+    def _evaluate_pattern(self):
+        """env:313-339"""
+        lib = _lib.use_device(self._device)
+        b = self._packed(); a = np.zeros(1, np.uint8); p = np.zeros(1, np.float64); c = np.zeros(1, np.int32)
+        _lib.check(lib.g2048_host_simulate_move(_lib.np_ptr(b), _lib.np_ptr(a), None, None, None, None, _lib.np_ptr(c),
+                                                _lib.np_ptr(p), 1))
+        return np.float64(p[0])
+
     def render(self, mode="human"):
         """env:290-311"""
         if mode != "human":
@@ -222,6 +244,22 @@ class BatchedGame2048Env:
         obs = self.torch.empty(self.n, 16, dtype=self.torch.float32, device=self.device)
         _lib.check(self._use().g2048_observe(self.boards.data_ptr(), obs.data_ptr(), self.n, self._stream()))
         return obs
+
+    def ppo_features(self, obs=True, heuristic=True, top4_bonus=True):
+        """PPOAgent.normalize_state / evaluate_heuristic / top-4-tiles bonus (agents/ppo_agent.py:184-195,
+        271-333, 251-254) for every env in one launch -> dict of device tensors."""
+        t = self.torch
+        out = {}
+        if obs:
+            out["obs"] = t.empty(self.n, 16, dtype=t.float32, device=self.device)
+        if heuristic:
+            out["heuristic"] = t.empty(self.n, dtype=t.float64, device=self.device)
+        if top4_bonus:
+            out["top4_bonus"] = t.empty(self.n, dtype=t.float64, device=self.device)
+        ptr = lambda k: out[k].data_ptr() if k in out else 0      # noqa: E731
+        _lib.check(self._use().g2048_ppo_features(self.boards.data_ptr(), ptr("obs"), ptr("heuristic"), ptr("top4_bonus"),
+                                                  self.n, self._stream()))
+        return out
 
     def values(self):
         """int32[N,16] tile values (what Game2048Env.get_state returns)."""

@@ -62,6 +62,11 @@ int g2048_pack(const int32_t *values, uint64_t *boards, int64_t n, void *stream)
 int g2048_unpack(const uint64_t *boards, int32_t *values, int64_t n, void *stream);
 /* float32[n][16] observation log2(tile)/15, 0 for empty (agents/ppo_agent.py:184-195) */
 int g2048_observe(const uint64_t *boards, float *obs, int64_t n, void *stream);
+/* PPO-side features of agents/ppo_agent.py in one pass: obs = normalize_state
+ * (:184-195, float32[n][16]); heuristic = evaluate_heuristic (:271-333, float64, bit-exact);
+ * top4_bonus = 0.1 * sum(log2 of the four largest tiles) (:251-254).  Outputs optional. */
+int g2048_ppo_features(const uint64_t *boards, float *obs, double *heuristic, double *top4_bonus,
+                       int64_t n, void *stream);
 /* Synthetic mid-game boards: cell empty w.p. ~0.3 else 2^U{1..11} (bench workloads). */
 int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t game0, void *stream);
 
@@ -83,6 +88,17 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
                    double *reward, float *reward32, int32_t *score_delta,
                    uint8_t *valid, uint8_t *legal, uint8_t *done,
                    int64_t n, uint64_t seed, uint32_t game0, void *stream);
+
+/* Game2048Env.simulate_move (env:341-387): every (empty cell of the moved board, tile 2 then 4)
+ * outcome of `actions[i]` on `boards[i]`, in the reference's order and with its accumulating-board
+ * quirk (env:371,378: each outcome starts from the previous one; the reward of env:375 is taken on
+ * that previous board).  Outcome k of board i is at index 32*i + k, count[i] <= 30 (0 = invalid move).
+ * highest_exp: log2(env.highest_tile) per board or NULL (0). */
+int g2048_simulate_move(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest_exp,
+                        uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                        int64_t n, void *stream);
+/* Game2048Env._evaluate_pattern (env:313-339): max(snake, corner weighted tile sums) / 100. */
+int g2048_evaluate_pattern(const uint64_t *boards, double *pattern, int64_t n, void *stream);
 
 /* Game2048Env.get_valid_moves (env:69-95) -> env_legal; BeamSearchAgent._check_valid_moves
  * (agent:183-192, DOWN quirk included) -> agent_legal.  Bit a = action a.  Either may be NULL. */
@@ -119,7 +135,8 @@ int g2048_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_
 /* Whole games, evaluate_beam_search.run_game (evaluate_beam_search.py:16-98): Game2048Env(),
  * reset(), then get_action(state) / env.step(action) until done or max_moves.
  * Per-game outputs (all optional): score, highest_exp, moves, valid, invalid,
- * milestone[n][8] = first move count at which highest_tile >= 64,128,...,8192 (-1 never),
+ * milestone[n][8] = 0-based index of the first move after which max tile >= 64,128,...,8192
+ * (evaluate_beam_search.py:59-64; -1 = never),
  * nodes (evaluated children), final_board. */
 int g2048_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
                      int32_t early_thr, int32_t mid_thr, int32_t max_moves,
@@ -151,6 +168,9 @@ int g2048_host_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_ex
                            int64_t n, int32_t steps, uint32_t t0, uint64_t seed, uint32_t game0);
 int g2048_host_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n);
 int g2048_host_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t n);
+int g2048_host_simulate_move(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest_exp,
+                             uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count, double *pattern, int64_t n);
+int g2048_host_ppo_features(const uint64_t *boards, float *obs, double *heuristic, double *top4_bonus, int64_t n);
 int g2048_host_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_t *call, uint32_t call0,
                            uint8_t *action, float *prob, double *best_score, int32_t *nodes,
                            int64_t n, int32_t beam_width, int32_t search_depth,

@@ -175,13 +175,14 @@ def main():
 
     # ---- full games, evaluate_beam_search.run_game style (get_action(state) without valid_moves)
     games = []
-    for (W, D, g, cap) in [(4, 6, 0, 400), (6, 8, 1, 400), (3, 12, 2, 300)]:
+    for (W, D, g, cap) in [(4, 6, 0, 400), (6, 8, 1, 400), (3, 12, 2, 300), (8, 10, 3, 700)]:
         shim.select(P.DOM_ENV, g, 0, 0)
         env = game.Game2048Env()
         state = env.reset()
         env_draw = shim.draw
         ag2 = agent.BeamSearchAgent(W, D)
         actions, moves, done = [], 0, False
+        milestones = [-1] * 8
         valid = invalid = 0
         while not done and moves < cap:
             shim.select(P.DOM_BEAM, g, moves, 0)
@@ -189,12 +190,45 @@ def main():
             shim.select(P.DOM_ENV, g, 0, env_draw)
             state, r, done, info = env.step(a)
             env_draw = shim.draw
+            for mi, tile in enumerate((64, 128, 256, 512, 1024, 2048, 4096, 8192)):      # evaluate_beam_search.py:59-64
+                if state.max() >= tile and milestones[mi] < 0:
+                    milestones[mi] = moves
             actions.append(int(a)); moves += 1
             valid += bool(info["valid_move"]); invalid += not info["valid_move"]
         games.append({"W": W, "D": D, "game": g, "max_moves": cap, "actions": actions, "score": int(env.score),
                       "highest_tile": int(env.highest_tile), "moves": moves, "valid": valid, "invalid": invalid,
-                      "final": L(state), "done": bool(done)})
+                      "final": L(state), "done": bool(done), "milestones": milestones})
     G["games"] = games
+
+    # ---- Game2048Env.simulate_move (game_2048.py:341-387) and _evaluate_pattern (:313-339)
+    sims = []
+    for b in boards[:40]:
+        if b.max() == 0:
+            continue
+        for a in range(4):
+            env = game.Game2048Env.__new__(game.Game2048Env)
+            env.size = 4; env.board = np.zeros((4, 4), np.int32); env.score = 0; env.game_over = False
+            env.highest_tile = int(b.max())
+            outs = env.simulate_move(b.copy(), a)
+            sims.append({"board": L(b), "action": a, "highest_tile": int(b.max()),
+                         "outcomes": [{"state": L(s_), "reward": float(r_).hex(), "done": bool(d_)} for s_, r_, d_ in outs]})
+        env.board = b.reshape(4, 4).copy()
+        sims[-1]["pattern"] = float(env._evaluate_pattern()).hex()
+    G["simulate_move"] = sims
+
+    # ---- PPO-side features (agents/ppo_agent.py:184-195, 251-254, 271-333), SURVEY 8f row 1
+    PPO = R.load_ppo_agent_class()
+    ppo = object.__new__(PPO)
+    feats = []
+    for b in boards:
+        if b.max() == 0:
+            continue
+        top = np.sort(b.flatten())[-4:]
+        feats.append({"board": L(b),
+                      "obs": [float(v).hex() for v in ppo.normalize_state(b)],
+                      "heuristic": float(ppo.evaluate_heuristic(b)).hex(),
+                      "top4_bonus": float(0.1 * sum(np.log2(t) for t in top if t > 0)).hex()})
+    G["ppo"] = feats
 
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:

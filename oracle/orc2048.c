@@ -238,6 +238,49 @@ void orc_env_step(orc_env *env, int action, const uint32_t *inject, orc_step_out
     out->reward = reward; out->valid = valid; out->done = env->game_over; out->score_delta = gained;
 }
 
+/* env:341-387 simulate_move(state, action): every empty cell x {2, 4} after the move.
+ * Restated WITH the reference's quirk: the loop writes `self.board = new_state.copy()` (env:378)
+ * for the game-over test and never restores it inside the loop, so `new_state = self.board.copy()`
+ * (env:371) starts from the PREVIOUS outcome (tiles accumulate: earlier cells stay filled with
+ * their last value, 4) and the reward (env:375) is computed on that previous board.
+ * Returns the number of outcomes (<= 30). */
+int orc_env_simulate_move(const int32_t state[16], int action, int32_t highest_tile,
+                          int32_t out_boards[30][16], double out_reward[30], int32_t out_done[30])
+{
+    int32_t cur[16];
+    memcpy(cur, state, sizeof cur);
+    int64_t gained = orc_env_move(cur, action);                       /* env:362 (score stays bumped) */
+    if (memcmp(cur, state, sizeof cur) == 0) return 0;                /* env:363-366 */
+    int empties[16], n = 0;
+    for (int i = 0; i < 16; ++i) if (cur[i] == 0) empties[n++] = i;   /* env:367, taken once */
+    int k = 0;
+    for (int e = 0; e < n; ++e) {
+        for (int tile = 2; tile <= 4; tile += 2) {
+            int32_t ns[16];
+            memcpy(ns, cur, sizeof ns);                               /* env:371: self.board, not the moved board */
+            ns[empties[e]] = tile;
+            out_reward[k] = orc_env_reward(1, state, cur, gained, highest_tile);   /* env:375 */
+            memcpy(cur, ns, sizeof cur);                              /* env:378 */
+            out_done[k] = orc_env_legal_mask(cur) == 0;               /* env:379 */
+            memcpy(out_boards[k], ns, sizeof ns);
+            ++k;
+        }
+    }
+    return k;
+}
+
+/* env:313-339 _evaluate_pattern (never called by the reference): max of the snake-weighted and the
+ * corner-weighted sum of tile VALUES, each / 100. */
+double orc_env_pattern(const int32_t b[16])
+{
+    static const double SNAKE[16] = {16, 15, 14, 13, 9, 10, 11, 12, 8, 7, 6, 5, 1, 2, 3, 4};
+    static const double CORNER[16] = {16, 8, 4, 2, 8, 4, 2, 1, 4, 2, 1, 0.5, 2, 1, 0.5, 0.25};
+    double s = 0.0, c = 0.0;                 /* all partial sums are exact dyadic numbers */
+    for (int i = 0; i < 16; ++i) { s += (double)b[i] * SNAKE[i]; c += (double)b[i] * CORNER[i]; }
+    s /= 100.0; c /= 100.0;
+    return s > c ? s : c;
+}
+
 /* ------------------------------------------------------------------ */
 /* Beam-search agent                                                    */
 /* ------------------------------------------------------------------ */
@@ -321,6 +364,54 @@ double orc_full_eval(const int32_t b[16], int phase)      /* agent:316-373 (+375
     for (int i = 0; i < 16; ++i) if (b[i] > 0) snake += (double)ilog2(b[i]) * (double)SNAKE[i];
     snake /= 100.0;
     return (((empty_score + max_score) + corner_bonus) + merge_potential) + snake;   /* :373 */
+}
+
+/* ------------------------------------------------------------------ */
+/* PPO-side features: agents/ppo_agent.py            */
+/* ------------------------------------------------------------------ */
+/* ppo_agent.py:184-195 normalize_state: log2(tile)/15, 0 for empty (float32) */
+void orc_ppo_observe(const int32_t b[16], float obs[16])
+{
+    for (int i = 0; i < 16; ++i) obs[i] = b[i] > 0 ? (float)ilog2(b[i]) / 15.0f : 0.0f;
+}
+
+/* ppo_agent.py:271-333 evaluate_heuristic: 2 * best-direction monotonicity / 24
+ * + 1 if the largest corner is the largest tile - 0.1 * #(tiles >= 8) */
+double orc_ppo_heuristic(const int32_t b[16])
+{
+    int h_le = 0, h_ge = 0, v_le = 0, v_ge = 0;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 3; ++c) {
+        int32_t x = b[4 * r + c], y = b[4 * r + c + 1];
+        if (x > 0 && y > 0) { h_le += x <= y; h_ge += x >= y; }
+    }
+    for (int c = 0; c < 4; ++c) for (int r = 0; r < 3; ++r) {
+        int32_t x = b[4 * r + c], y = b[4 * r + 4 + c];
+        if (x > 0 && y > 0) { v_le += x <= y; v_ge += x >= y; }
+    }
+    /* max over the four (row_dir, col_dir) combinations of (rows + cols) / 24.0 */
+    int best = (h_le > h_ge ? h_le : h_ge) + (v_le > v_ge ? v_le : v_ge);
+    double score = 2.0 * ((double)best / 24.0);
+    int32_t cmax = b[0];
+    if (b[3] > cmax) cmax = b[3];
+    if (b[12] > cmax) cmax = b[12];
+    if (b[15] > cmax) cmax = b[15];
+    if (cmax == max_tile(b)) score += 1.0;
+    int high = 0;
+    for (int i = 0; i < 16; ++i) high += b[i] >= 8;
+    if (high > 0) score += -0.1 * (double)high;
+    return score;
+}
+
+/* ppo_agent.py:251-254: 0.1 * sum(log2 of the four largest tiles that are > 0) */
+double orc_ppo_top4_bonus(const int32_t b[16])
+{
+    int32_t t[16];
+    memcpy(t, b, sizeof t);
+    for (int i = 0; i < 4; ++i)                 /* partial selection sort, descending */
+        for (int j = i + 1; j < 16; ++j) if (t[j] > t[i]) { int32_t x = t[i]; t[i] = t[j]; t[j] = x; }
+    double sum = 0.0;
+    for (int i = 3; i >= 0; --i) if (t[i] > 0) sum += (double)ilog2(t[i]);     /* ascending, as np.sort()[-4:] */
+    return 0.1 * sum;
 }
 
 typedef struct { int32_t board[16]; int first; double score; } cand_t;
@@ -434,10 +525,10 @@ void orc_play_game(uint64_t seed, uint32_t game, int beam_width, int search_dept
         orc_step_out s;
         orc_env_step(&env, b.action, NULL, &s);
         done = s.done;
-        ++moves;
+        for (int m = 0; m < 8; ++m)           /* milestones 64..8192, evaluate_beam_search.py:42-43,61-64: */
+            if (out->milestone_move[m] < 0 && max_tile(env.board) >= (64 << m)) out->milestone_move[m] = moves;   /* index before moves += 1 (:86) */
         if (s.valid) out->valid_moves++; else out->invalid_moves++;
-        for (int m = 0; m < 8; ++m)           /* milestones 64..8192, evaluate_beam_search.py:42-43,61-64 */
-            if (out->milestone_move[m] < 0 && env.highest_tile >= (64 << m)) out->milestone_move[m] = moves;
+        ++moves;
     }
     out->score = env.score; out->highest_tile = env.highest_tile; out->moves = moves;
 }

@@ -65,6 +65,11 @@ void orc_env_step(orc_env *env, int action, const uint32_t *inject, orc_step_out
 double orc_env_reward(int valid, const int32_t prev_board[16], const int32_t new_board[16],
                       int64_t score_delta, int32_t highest_tile_before);
 
+/* game_2048.py:341-387 (with its accumulating-board quirk) and :313-339 */
+int orc_env_simulate_move(const int32_t state[16], int action, int32_t highest_tile,
+                          int32_t out_boards[30][16], double out_reward[30], int32_t out_done[30]);
+double orc_env_pattern(const int32_t board[16]);
+
 /* ---- beam-search agent (beam_search_agent.py) ---- */
 /* :194-258 incl. the DOWN quirk.  Returns valid flag. */
 int orc_agent_move(const int32_t board[16], int action, int32_t out[16], int64_t *merge_score);
@@ -73,6 +78,11 @@ double orc_fast_eval(const int32_t board[16]);               /* :280-314 */
 /* :316-403; phase 0 early, 1 mid, 2 late */
 double orc_full_eval(const int32_t board[16], int phase);
 int orc_phase(int32_t max_tile, int32_t early_thr, int32_t mid_thr);  /* :271-278 */
+
+/* ---- PPO-side features (agents/ppo_agent.py), SURVEY 8f row 1 ---- */
+void orc_ppo_observe(const int32_t board[16], float obs[16]);      /* :184-195 */
+double orc_ppo_heuristic(const int32_t board[16]);                 /* :271-333 */
+double orc_ppo_top4_bonus(const int32_t board[16]);                /* :251-254 */
 
 typedef struct {
     int32_t action;        /* chosen action                                */

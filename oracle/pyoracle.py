@@ -63,6 +63,10 @@ def lib():
         L.orc_env_step.argtypes = [C.POINTER(EnvState), C.c_int, C.POINTER(C.c_uint32), C.POINTER(StepOut)]
         L.orc_env_reward.argtypes = [C.c_int, i32p, i32p, C.c_int64, C.c_int32]
         L.orc_env_reward.restype = C.c_double
+        L.orc_env_simulate_move.argtypes = [i32p, C.c_int, C.c_int32, C.POINTER(C.c_int32 * 16), C.POINTER(C.c_double), i32p]
+        L.orc_env_simulate_move.restype = C.c_int
+        L.orc_env_pattern.argtypes = [i32p]
+        L.orc_env_pattern.restype = C.c_double
         L.orc_agent_move.argtypes = [i32p, C.c_int, i32p, C.POINTER(C.c_int64)]
         L.orc_agent_move.restype = C.c_int
         L.orc_agent_legal_mask.argtypes = [i32p]
@@ -71,6 +75,11 @@ def lib():
         L.orc_fast_eval.restype = C.c_double
         L.orc_full_eval.argtypes = [i32p, C.c_int]
         L.orc_full_eval.restype = C.c_double
+        L.orc_ppo_heuristic.argtypes = [i32p]
+        L.orc_ppo_heuristic.restype = C.c_double
+        L.orc_ppo_top4_bonus.argtypes = [i32p]
+        L.orc_ppo_top4_bonus.restype = C.c_double
+        L.orc_ppo_observe.argtypes = [i32p, C.POINTER(C.c_float)]
         L.orc_phase.argtypes = [C.c_int32] * 3
         L.orc_phase.restype = C.c_int
         L.orc_beam_get_action.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32,
@@ -121,6 +130,17 @@ def env_legal_mask(board):
     return lib().orc_env_legal_mask(_b(board))
 
 
+def env_simulate_move(board, action, highest_tile):
+    """-> list of (int32[16], reward, done), game_2048.py:341-387"""
+    ob = ((C.c_int32 * 16) * 30)(); rw = (C.c_double * 30)(); dn = (C.c_int32 * 30)()
+    k = lib().orc_env_simulate_move(_b(board), action, int(highest_tile), ob, rw, dn)
+    return [(np.array(ob[i], dtype=np.int32), rw[i], bool(dn[i])) for i in range(k)]
+
+
+def env_pattern(board):
+    return lib().orc_env_pattern(_b(board))
+
+
 def agent_move(board, action):
     o = (C.c_int32 * 16)(); s = C.c_int64()
     v = lib().orc_agent_move(_b(board), action, o, C.byref(s))
@@ -137,6 +157,20 @@ def fast_eval(board):
 
 def full_eval(board, phase):
     return lib().orc_full_eval(_b(board), phase)
+
+
+def ppo_heuristic(board):
+    return lib().orc_ppo_heuristic(_b(board))
+
+
+def ppo_top4_bonus(board):
+    return lib().orc_ppo_top4_bonus(_b(board))
+
+
+def ppo_observe(board):
+    o = (C.c_float * 16)()
+    lib().orc_ppo_observe(_b(board), o)
+    return np.array(o, dtype=np.float32)
 
 
 class Env:

@@ -38,3 +38,22 @@ def load(shim):
     game.random = shim       # game_2048.py:2   `import random`
     agent.random = shim      # beam_search_agent.py:3
     return game, agent
+
+
+def load_ppo_agent_class():
+    """agents/ppo_agent.PPOAgent of the unmodified reference (needs torch; no network is built here:
+    tests call its pure feature methods on `object.__new__(PPOAgent)`)."""
+    if not available():
+        raise RuntimeError("reference tree not present")
+    sys.dont_write_bytecode = True
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k in ("environment", "agents") or k.startswith(("environment.", "agents."))}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        mod = importlib.import_module("agents.ppo_agent")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k in ("environment", "agents") or k.startswith(("environment.", "agents."))]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
+    return mod.PPOAgent

@@ -101,6 +101,8 @@ uint32_t emul_max_exponent(uint64_t b) { return max_exponent(Board(b)); }
 uint64_t emul_place_tile(uint64_t b, uint32_t pw, uint32_t vw) { Board x(b); place_tile(x, pw, vw); return x.u64(); }
 int emul_fast_eval(uint64_t b) { Board x(b); return fast_eval(x, count_empty(x), max_exponent(x)); }
 double emul_full_eval(uint64_t b, int phase) { Board x(b); return full_eval(x, count_empty(x), max_exponent(x), phase); }
+double emul_ppo_heuristic(uint64_t b) { return ppo_heuristic(Board(b)); }
+double emul_ppo_top4(uint64_t b) { return ppo_top4_bonus(Board(b)); }
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)
 {
     PhiloxKey K; { uint32_t a = k0, b = k1; for (int r = 0; r < 10; ++r) { K.k0[r] = a; K.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; } }

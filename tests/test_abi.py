@@ -62,3 +62,31 @@ def test_shard_range_covers_everything():
             spans = [G.shard_range(total, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_results_writer_matches_reference_layout(tmp_path):
+    """overall_results.json as evaluate_beam_search.py:198-214 writes it."""
+    import json
+    import numpy as np
+    import g2048_b200 as G
+    score = np.array([500, 900, 900, 100, 1200, 50, 901], np.int32)
+    hexp = np.array([6, 7, 7, 5, 8, 4, 7], np.uint8)
+    moves = np.arange(7) + 100
+    ms = -np.ones((7, 8), np.int32); ms[:, 0] = [40, 41, 42, -1, 43, -1, 44]; ms[4, 1] = 90
+    res = G.compile_results(score, hexp, moves, moves - 3, np.full(7, 3), ms, 15, 20)
+    # evaluate_beam_search.py:145-151 kept literally
+    best = []
+    for i in range(7):
+        if len(best) < 5:
+            best.append(i); best.sort(key=lambda idx: int(score[idx]), reverse=True)
+        elif score[i] > score[best[-1]]:
+            best[-1] = i; best.sort(key=lambda idx: int(score[idx]), reverse=True)
+    assert res["best_games"] == best
+    assert res["highest_tiles"] == [64, 128, 128, 32, 256, 16, 128]
+    assert res["milestones"][64] == [40, 41, 42, 43, 44] and res["milestones"][128] == [90] and res["milestones"][8192] == []
+    path = G.write_overall_results(res, str(tmp_path / "results_x"))
+    doc = json.load(open(path))
+    assert list(doc) == ["scores", "highest_tiles", "moves", "valid_moves", "invalid_moves", "milestones", "best_games", "parameters"]
+    assert doc["parameters"] == {"beam_width": 15, "search_depth": 20, "num_games": 7}
+    assert list(doc["milestones"]) == ["64", "128", "256", "512", "1024", "2048", "4096", "8192"]
+    assert all(isinstance(v, int) for v in doc["scores"])

@@ -74,6 +74,7 @@ def test_golden_full_games(golden):
         assert (out["score"][0], 1 << int(out["highest"][0]), out["moves"][0], out["valid"][0], out["invalid"][0]) == \
             (g["score"], g["highest_tile"], g["moves"], g["valid"], g["invalid"])
         assert out["final"][0] == G.pack_board(g["final"])
+        assert list(out["milestone"][0]) == g["milestones"]
 
 
 @pytest.mark.parametrize("W,D,n,cap", [(4, 6, 96, 10000), (10, 12, 40, 400), (15, 20, 24, 120)])
@@ -130,3 +131,18 @@ def test_facade_agent_and_protocol(orc, tmp_path):
     loaded = G.BeamSearchAgent.load(str(path))
     assert (loaded.beam_width, loaded.search_depth, loaded.early_game_threshold) == (15, 20, 512)
     assert (tmp_path / "ckpt" / "beam_search_config_readme_15_20.txt").exists()
+
+
+def test_run_evaluation_writes_reference_results(orc, tmp_path):
+    """the evaluate_beam_search.run_evaluation drop-in over play_games."""
+    import json
+    res = G.run_evaluation(num_games=12, beam_width=4, search_depth=6, save_dir=str(tmp_path / "results"),
+                           max_moves=10000, seed=SEED, timestamp=False)
+    ref = orc.play_games(SEED, 0, 12, 4, 6, max_moves=10000)
+    assert res["scores"] == [r.score for r in ref] and res["highest_tiles"] == [r.highest_tile for r in ref]
+    assert res["moves"] == [r.moves for r in ref] and res["valid_moves"] == [r.valid_moves for r in ref]
+    for j, m in enumerate((64, 128, 256, 512, 1024, 2048, 4096, 8192)):
+        assert res["milestones"][m] == [r.milestone_move[j] for r in ref if r.milestone_move[j] >= 0]
+    doc = json.load(open(tmp_path / "results" / "overall_results.json"))
+    assert doc["scores"] == res["scores"] and doc["parameters"]["num_games"] == 12
+    assert res["summary"]["games"] == 12 and res["summary"]["max_score"] == max(res["scores"])

@@ -214,3 +214,64 @@ def test_facade_env_matches_oracle(orc):
     env.highest_tile = 4          # the reference needs this too, else env:229 pays the (otherwise dead) new-tile bonus
     s, r, d, info = env.step(0)
     assert not info["valid_move"] and r == -0.5666666666666668
+
+
+def test_ppo_features_vs_oracle_and_golden(orc, golden):
+    """normalize_state / evaluate_heuristic / top-4 bonus of agents/ppo_agent.py."""
+    import ctypes as C
+    from g2048_b200 import _lib
+    vals, packed = X.synthetic(orc, 3000, SEED, 4242)
+    extra = np.array([r["board"] for r in golden["ppo"] if max(r["board"]) <= 32768], np.int32)
+    vals = np.concatenate([vals, extra]); packed = np.concatenate([packed, G.pack_boards(extra)])
+    n = packed.shape[0]
+    obs = np.zeros((n, 16), np.float32); heur = np.zeros(n, np.float64); top4 = np.zeros(n, np.float64)
+    _lib.check(X.lib().g2048_host_ppo_features(X.P(packed), X.P(obs), X.P(heur), X.P(top4), n))
+    for i in range(n):
+        if vals[i].max() == 0:
+            continue
+        assert heur[i] == orc.ppo_heuristic(vals[i]) and top4[i] == orc.ppo_top4_bonus(vals[i]), vals[i]
+        assert (obs[i] == orc.ppo_observe(vals[i])).all()
+    by_board = {tuple(r["board"]): r for r in golden["ppo"]}
+    for i in range(n - len(extra), n):
+        r = by_board[tuple(int(v) for v in vals[i])]
+        assert heur[i] == float.fromhex(r["heuristic"]) and top4[i] == float.fromhex(r["top4_bonus"])
+        assert [float(v).hex() for v in obs[i]] == r["obs"]
+    env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED)
+    env.set_boards(packed)
+    f = env.ppo_features()
+    assert (f["heuristic"].cpu().numpy() == heur).all() and (f["obs"].cpu().numpy() == obs).all()
+
+
+def test_simulate_move_and_pattern(orc, golden):
+    """Game2048Env.simulate_move (with the reference's accumulating-board quirk)."""
+    from g2048_b200 import _lib
+    recs = [r for r in golden["simulate_move"] if max(r["board"]) <= 16384]
+    n = len(recs)
+    b = G.pack_boards(np.array([r["board"] for r in recs], np.int32))
+    a = np.array([r["action"] for r in recs], np.uint8)
+    h = np.array([int(r["highest_tile"]).bit_length() - 1 for r in recs], np.uint8)
+    nb = np.zeros((n, 32), np.uint64); rw = np.zeros((n, 32), np.float64); dn = np.zeros((n, 32), np.uint8)
+    cnt = np.zeros(n, np.int32); pat = np.zeros(n, np.float64)
+    _lib.check(X.lib().g2048_host_simulate_move(X.P(b), X.P(a), X.P(h), X.P(nb), X.P(rw), X.P(dn), X.P(cnt), X.P(pat), n))
+    for i, r in enumerate(recs):
+        assert cnt[i] == len(r["outcomes"]), r
+        for k, want in enumerate(r["outcomes"]):
+            assert nb[i, k] == G.pack_board(want["state"]) and rw[i, k] == float.fromhex(want["reward"])
+            assert bool(dn[i, k]) == want["done"]
+        if "pattern" in r:
+            assert pat[i] == float.fromhex(r["pattern"])
+    # oracle on more boards, and the facade
+    vals, packed = X.synthetic(orc, 400, SEED, 606)
+    env = G.Game2048Env(seed=SEED, game_id=1)
+    for i in range(0, 400, 7):
+        if vals[i].max() == 0:
+            continue
+        env.highest_tile = int(vals[i].max())
+        for act in range(4):
+            got = env.simulate_move(vals[i], act)
+            want = orc.env_simulate_move(vals[i], act, int(vals[i].max()))
+            assert len(got) == len(want)
+            for (s1, r1, d1), (s2, r2, d2) in zip(got, want):
+                assert (s1 == s2).all() and float(r1) == r2 and d1 == d2
+        env.board = vals[i].reshape(4, 4)
+        assert float(env._evaluate_pattern()) == orc.env_pattern(vals[i])

@@ -52,6 +52,8 @@ def emul():
     L.emul_place_tile.argtypes = [u64, u32, u32]; L.emul_place_tile.restype = u64
     L.emul_fast_eval.argtypes = [u64]; L.emul_fast_eval.restype = C.c_int
     L.emul_full_eval.argtypes = [u64, C.c_int]; L.emul_full_eval.restype = C.c_double
+    L.emul_ppo_heuristic.argtypes = [u64]; L.emul_ppo_heuristic.restype = C.c_double
+    L.emul_ppo_top4.argtypes = [u64]; L.emul_ppo_top4.restype = C.c_double
     L.emul_philox.argtypes = [u32] * 6 + [C.POINTER(u32)]
     L.emul_random_action.argtypes = [u64, u32, u32]; L.emul_random_action.restype = u32
     L.emul_env_reset.argtypes = [C.POINTER(EmulEnv), u64, u32]
@@ -226,3 +228,12 @@ def test_tracked_rollout_step_matches_oracle(emul, orc):
         assert e.board == packing.pack_board(ob[i]) and e.score == osc[i] and e.spawn_ctr == octr[i]
         assert rs.value == ors[i] and ep.value == oep[i] and (1 << e.highest) == ohi[i]
     assert oep.sum() > 0
+
+
+def test_ppo_features_bit_exact(emul, orc):
+    for b in boards_for_test(orc):
+        if b.max() == 0:
+            continue
+        p = packing.pack_board(b)
+        assert emul.emul_ppo_heuristic(p) == orc.ppo_heuristic(b), b
+        assert emul.emul_ppo_top4(p) == orc.ppo_top4_bonus(b), b

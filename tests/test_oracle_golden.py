@@ -84,3 +84,22 @@ def test_full_games(orc, golden):
         o = orc.play_game(seed, g["game"], g["W"], g["D"], max_moves=g["max_moves"])
         assert (o.score, o.highest_tile, o.moves, o.valid_moves, o.invalid_moves) == \
             (g["score"], g["highest_tile"], g["moves"], g["valid"], g["invalid"])
+        assert list(o.milestone_move) == g["milestones"]
+
+
+def test_ppo_features(orc, golden):
+    for rec in golden["ppo"]:
+        b = np.array(rec["board"], np.int32)
+        assert orc.ppo_heuristic(b) == float.fromhex(rec["heuristic"]), rec
+        assert orc.ppo_top4_bonus(b) == float.fromhex(rec["top4_bonus"]), rec
+        assert [float(v).hex() for v in orc.ppo_observe(b)] == rec["obs"]
+
+
+def test_simulate_move_and_pattern(orc, golden):
+    for rec in golden["simulate_move"]:
+        outs = orc.env_simulate_move(rec["board"], rec["action"], rec["highest_tile"])
+        assert len(outs) == len(rec["outcomes"])
+        for (s, r, d), want in zip(outs, rec["outcomes"]):
+            assert s.tolist() == want["state"] and r == float.fromhex(want["reward"]) and d == want["done"]
+        if "pattern" in rec:
+            assert orc.env_pattern(rec["board"]) == float.fromhex(rec["pattern"])

@@ -71,3 +71,21 @@ def test_get_action(orc, ref, W, D):
             o = orc.beam_get_action(b, mask, W, D, SEED, g, 11)
             assert (int(a), float(p)) == (o.action, o.prob)
             assert shim.draw == 2 * o.spawns
+
+
+def test_ppo_features_vs_reference(orc):
+    PPO = R.load_ppo_agent_class()
+    ppo = object.__new__(PPO)
+    rng = np.random.default_rng(5)
+    for g in range(500):
+        if g % 2:
+            b = orc.synthetic_board(SEED, 5000 + g)
+        else:
+            e = rng.integers(0, 13, 16); e[rng.random(16) < rng.choice([0.0, 0.3, 0.7])] = 0
+            b = np.where(e > 0, 1 << e, 0).astype(np.int32)
+        if b.max() == 0:
+            continue
+        assert float(ppo.evaluate_heuristic(b)) == orc.ppo_heuristic(b), b
+        top = np.sort(b.flatten())[-4:]
+        assert float(0.1 * sum(np.log2(t) for t in top if t > 0)) == orc.ppo_top4_bonus(b)
+        assert (ppo.normalize_state(b) == orc.ppo_observe(b)).all()
