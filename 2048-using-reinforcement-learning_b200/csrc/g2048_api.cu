@@ -132,6 +132,26 @@ __global__ void __launch_bounds__(kEnvThreads) env_reset_kernel(uint64_t *boards
     }
 }
 
+// env.reset() for the envs whose done flag is set (the harness-side "reset when done" of a rollout
+// loop, without a device->host round trip); the others are left untouched.
+__global__ void __launch_bounds__(kEnvThreads) env_reset_done_kernel(uint64_t *boards, int32_t *score, uint8_t *highest,
+                                                                      uint32_t *spawn_ctr, const uint8_t *done,
+                                                                      int32_t *episodes, int64_t n, PhiloxKey K,
+                                                                      uint32_t game0)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!done[i]) continue;
+        EnvState s;
+        s.spawn_ctr = spawn_ctr ? spawn_ctr[i] : 0u;
+        env_reset(s, K, game0 + (uint32_t)i);
+        boards[i] = s.board.u64();
+        if (score) score[i] = 0;
+        if (highest) highest[i] = (uint8_t)s.highest;
+        if (spawn_ctr) spawn_ctr[i] = s.spawn_ctr;
+        if (episodes) episodes[i] += 1;
+    }
+}
+
 struct RolloutArgs {
     uint64_t *boards; int32_t *score; uint8_t *highest; uint32_t *spawn_ctr;
     double *reward_sum; int32_t *episodes;
@@ -571,6 +591,15 @@ int g2048_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint
     G2048_ENTER(boards);
     env_reset_kernel<<<grid_for(n, kEnvThreads, st->sm_count, 8), kEnvThreads, 0, s>>>(
         boards, score, highest_exp, spawn_ctr, n, make_philox_key(seed), game0);
+    G2048_LAUNCHED();
+}
+
+int g2048_env_reset_done(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                         const uint8_t *done, int32_t *episodes, int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards && done);
+    env_reset_done_kernel<<<grid_for(n, kEnvThreads, st->sm_count, 8), kEnvThreads, 0, s>>>(
+        boards, score, highest_exp, spawn_ctr, done, episodes, n, make_philox_key(seed), game0);
     G2048_LAUNCHED();
 }
 

@@ -175,6 +175,11 @@ class BatchedGame2048Env:
         self.reward_sum = torch.zeros(self.n, dtype=torch.float64, **z)
         self.episodes = torch.zeros(self.n, dtype=torch.int32, **z)
         self.t = 0
+        names = ("boards", "score", "highest_exp", "spawn_ctr", "reward", "reward32", "score_delta", "valid", "legal",
+                 "done", "reward_sum", "episodes")
+        self._ptrs = {k: getattr(self, k).data_ptr() for k in names}        # state tensors never move
+        self._info = {"score": self.score, "valid_move": self.valid, "highest_exp": self.highest_exp,
+                      "legal_mask": self.legal, "score_delta": self.score_delta, "reward32": self.reward32}
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -207,22 +212,46 @@ class BatchedGame2048Env:
 
         Returns (boards, reward float64[N], done uint8[N], info) with info = dict(score, valid_move,
         highest_exp, legal_mask, score_delta, reward32); all are views of internal device tensors
-        that the next call overwrites.
+        that the next call overwrites.  Only kernel launches on the current stream: the call is
+        CUDA-graph capturable (see `graph`).
         """
         t = self.torch
         if actions.dtype != t.uint8:
             actions = actions.to(t.uint8)
-        actions = actions.contiguous()
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
         inj = 0 if inject is None else inject.contiguous().data_ptr()
-        _lib.check(self._use().g2048_env_step(
-            self.boards.data_ptr(), actions.data_ptr(), inj, self.score.data_ptr(), self.highest_exp.data_ptr(),
-            self.spawn_ctr.data_ptr(), self.reward.data_ptr() if want_reward else 0,
-            self.reward32.data_ptr() if want_reward else 0, self.score_delta.data_ptr(), self.valid.data_ptr(),
-            self.legal.data_ptr(), self.done.data_ptr(), self.n, self.seed, self.game0, self._stream()))
+        p = self._ptrs
+        rc = self._use().g2048_env_step(
+            p["boards"], actions.data_ptr(), inj, p["score"], p["highest_exp"], p["spawn_ctr"],
+            p["reward"] if want_reward else 0, p["reward32"] if want_reward else 0, p["score_delta"], p["valid"],
+            p["legal"], p["done"], self.n, self.seed, self.game0, self._stream())
+        if rc:
+            _lib.check(rc)
         self.t += 1
-        return self.boards, self.reward, self.done, {
-            "score": self.score, "valid_move": self.valid, "highest_exp": self.highest_exp,
-            "legal_mask": self.legal, "score_delta": self.score_delta, "reward32": self.reward32}
+        return self.boards, self.reward, self.done, self._info
+
+    def graph(self, fn):
+        """Capture `fn()` (any sequence of this env's calls and torch ops on static tensors) into a
+        CUDA graph and return it; `g.replay()` then re-issues the whole sequence with one launch."""
+        t = self.torch
+        s = t.cuda.Stream(device=self.device)
+        s.wait_stream(t.cuda.current_stream(self.device))
+        with t.cuda.stream(s):
+            fn()                                   # warm-up outside capture (lazy init, allocator)
+        t.cuda.current_stream(self.device).wait_stream(s)
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g):
+            fn()
+        return g
+
+    def reset_done(self):
+        """Reset exactly the envs whose last step reported done (train.py:49,107 `if done: reset`),
+        on the device; counts them in `episodes`."""
+        _lib.check(self._use().g2048_env_reset_done(
+            self.boards.data_ptr(), self.score.data_ptr(), self.highest_exp.data_ptr(), self.spawn_ctr.data_ptr(),
+            self.done.data_ptr(), self.episodes.data_ptr(), self.n, self.seed, self.game0, self._stream()))
+        return self.boards
 
     def rollout(self, steps):
         """`steps` random-policy steps per env in one launch (boards stay in registers)."""

@@ -229,6 +229,20 @@ def run_ours(args):
     barrier()
     per_step_api = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
     per_step_api_value = world * n * 64 / per_step_api
+    # the same 64 per-step launches replayed as one CUDA graph (what a PPO loop would do)
+    def sixty_four_steps():
+        for i in range(64):
+            env.step(acts[i])
+            env.reset_done()
+    graph = env.graph(sixty_four_steps)
+    graph.replay()
+    barrier()
+    e0.record()
+    for _ in range(4):
+        graph.replay()
+    e1.record()
+    barrier()
+    per_step_graph_value = world * n * 64 * 4 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H per call) ---------------------------
     P = _lib.np_ptr
@@ -335,7 +349,9 @@ def run_ours(args):
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{cpu_n} envs x {cpu_steps} steps, oracle/orc2048.c on {threads} threads"},
         "per_step_api": {"value": per_step_api_value, "unit": UNIT,
-                         "note": "g2048_env_step, one launch per env step, device-resident tensors"},
+                         "note": "g2048_env_step, one launch per env step, device-resident tensors",
+                         "cuda_graph": {"value": per_step_graph_value, "unit": UNIT,
+                                        "note": "64 x (g2048_env_step + g2048_env_reset_done) captured in one CUDA graph"}},
         "beam": {"metric": "beam-search nodes/sec (BeamSearchAgent.get_action, width 20 depth 40)", "value": beam_value,
                  "unit": "nodes/s", "roots_per_gpu": args.beam_roots, "nodes_per_step": nodes_total // max(1, args.steps),
                  "ms_per_step": beam_ms / args.steps, "e2e": {"value": beam_e2e, "unit": "nodes/s", "api": "g2048_host_beam_search"},

@@ -76,6 +76,13 @@ int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t 
 int g2048_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
                     int64_t n, uint64_t seed, uint32_t game0, void *stream);
 
+/* Game2048Env.reset for exactly the envs with done[i] != 0 (what a rollout harness does after a
+ * step, `if done: state = env.reset()` -- train.py:49,107), without leaving the device.
+ * episodes[i] += 1 for those envs (optional). */
+int g2048_env_reset_done(uint64_t *boards, int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                         const uint8_t *done, int32_t *episodes, int64_t n, uint64_t seed, uint32_t game0,
+                         void *stream);
+
 /* Game2048Env.step (env:170-210) for n independent envs.
  *   in/out : boards, score (cumulative merge score), highest_exp (log2 highest_tile), spawn_ctr
  *   in     : actions[n]; spawn_inject NULL or uint32[n][2] raw (position word, value word)

@@ -275,3 +275,29 @@ def test_simulate_move_and_pattern(orc, golden):
                 assert (s1 == s2).all() and float(r1) == r2 and d1 == d2
         env.board = vals[i].reshape(4, 4)
         assert float(env._evaluate_pattern()) == orc.env_pattern(vals[i])
+
+
+def test_reset_done_on_device(orc):
+    import torch
+    n = 4000
+    env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=17)
+    env.reset()
+    oracles = [orc.Env(SEED, 17 + i, ctor_reset=False) for i in range(0, n, 200)]
+    for o in oracles:
+        o.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    total_done = 0
+    for t in range(400):
+        a = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+        _, _, done, _ = env.step(a)
+        total_done += int(done.sum())
+        env.reset_done()
+        ah = a.cpu().numpy()
+        for j, o in enumerate(oracles):
+            _, _, od, _ = o.step(int(ah[200 * j]))
+            if od:
+                o.reset()
+    assert total_done > 0 and int(env.episodes.sum()) == total_done
+    got = env.boards_u64()
+    for j, o in enumerate(oracles):
+        assert got[200 * j] == G.pack_board(o.board) and int(env.spawn_ctr[200 * j]) == o.s.spawn_ctr
