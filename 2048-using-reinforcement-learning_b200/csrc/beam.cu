@@ -92,6 +92,70 @@ __device__ __forceinline__ void agent_children(Board b, const uint16_t *row, Boa
 
 __device__ __forceinline__ int tile_value(uint32_t e) { return e ? (1 << e) : 0; }
 
+
+// Phase B for candidate c of this level: spawn (agent:155), evaluate (agent:158-161), sort key.
+// Branch-free on purpose (the Philox block is computed for every lane and masked by `draws`) so that
+// two rounds issued back to back form one basic block the scheduler can interleave: a warp
+// working alone at the tail of a whole-game run is bound by dependent-issue latency.
+template <bool kFull>
+__device__ __forceinline__ uint32_t spawn_and_score(int c, int n_valid, uint32_t lane_lt, uint32_t &spawn_base,
+                                                    const BeamParams &P, uint32_t game, uint32_t call, int phase,
+                                                    WarpScratch &ws)
+{
+    const bool active = c < n_valid;
+    Board b = active ? Board(ws.cand[c]) : Board(0u, 0u);
+    const uint32_t fe = active ? ws.first[c] : 0u;
+    uint32_t zl = zero_flags(b.lo), zh = zero_flags(b.hi);
+    int n_empty = __popc(zl) + __popc(zh);
+    const bool draws = active && n_empty > 0;                   // agent:262-263: no draw on a full board
+    const uint32_t bal = __ballot_sync(FULL, draws);
+    const SpawnWords w = spawn_words(P.K, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lane_lt));
+    spawn_base += (uint32_t)__popc(bal);
+    Board spawned = b;
+    const Spawned sp = place_tile_flags(spawned, zl, zh, max(n_empty, 1), w.pos, w.val);
+    const uint32_t flag = sp.tile >> (sp.exponent - 1u);
+    if (draws) {
+        b = spawned;
+        zl &= sp.in_hi ? ~0u : ~flag;
+        zh &= sp.in_hi ? ~flag : ~0u;
+        n_empty -= 1;
+    }
+    const uint32_t pmax = fe >> 2;                              // parent's largest exponent
+    const uint32_t emax = pmax + ((pmax < 15u && has_exponent(b, pmax + 1u)) ? 1u : 0u);
+    const uint32_t tail = ((uint32_t)(127 - c) << 2) | (fe & 3u);
+    uint32_t key;
+    double score = 0.0;
+    if (kFull) {
+        score = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase);
+        key = tail;                                             // rank field filled in by the caller
+    } else {
+        key = ((uint32_t)fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax) << 9) | tail;
+    }
+    if (active) {
+        ws.cand[c] = b.u64();
+        ws.first[c] = (uint8_t)((fe & 3u) | (emax << 2));
+        if (kFull) ws.score[c] = score;
+    }
+    return active ? key : 0u;
+}
+
+// two independent 32-key sorts in lockstep (same network, twice the ILP)
+__device__ __forceinline__ void sort_desc32_x2(uint32_t &a, uint32_t &b, uint32_t lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+        bool lower = (lane & (k >> 1)) == 0;
+        a = exchange(a, k - 1, lower);
+        b = exchange(b, k - 1, lower);
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            lower = (lane & j) == 0;
+            a = exchange(a, j, lower);
+            b = exchange(b, j, lower);
+        }
+    }
+}
+
 // All 32 lanes call this with the same root / parameters.
 __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_given, const BeamParams &P, uint32_t game,
                                        uint32_t call, const uint16_t *row, WarpScratch &ws)
@@ -178,40 +242,19 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         // ---- B: spawn + evaluate ---------------------------------------------------------------
         const bool full_level = d >= 1 && d <= 3;                       // agent:139,158-161
         uint32_t key[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (r * 32 < n_valid) {
-                const int c = r * 32 + (int)lane;
-                const bool active = c < n_valid;
-                Board b = active ? Board(ws.cand[c]) : Board(0u, 0u);
-                uint32_t zl = zero_flags(b.lo), zh = zero_flags(b.hi);
-                int n_empty = __popc(zl) + __popc(zh);
-                const bool draws = active && n_empty > 0;               // agent:262-263: no draw on a full board
-                uint32_t bal = __ballot_sync(FULL, draws);
-                if (draws) {
-                    SpawnWords w = spawn_words(P.K, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lt_mask));
-                    Spawned sp = place_tile_flags(b, zl, zh, n_empty, w.pos, w.val);
-                    uint32_t flag = sp.tile >> (sp.exponent - 1u);
-                    zl &= sp.in_hi ? ~0u : ~flag;
-                    zh &= sp.in_hi ? ~flag : ~0u;
-                    n_empty -= 1;
-                }
-                spawn_base += (uint32_t)__popc(bal);
-                if (active) {
-                    const uint32_t fe = ws.first[c];
-                    const uint32_t pmax = fe >> 2;                      // parent's largest exponent
-                    const uint32_t emax = pmax + ((pmax < 15u && has_exponent(b, pmax + 1u)) ? 1u : 0u);
-                    const uint32_t tail = ((uint32_t)(127 - c) << 2) | (fe & 3u);
-                    ws.cand[c] = b.u64();
-                    ws.first[c] = (uint8_t)((fe & 3u) | (emax << 2));
-                    if (full_level) {
-                        ws.score[c] = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase);
-                        key[r] = tail;                                  // rank field filled in below
-                    } else {
-                        key[r] = ((uint32_t)fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax) << 9) | tail;
-                    }
-                }
-            }
+        const int L = (int)lane;
+        if (full_level) {
+            key[0] = spawn_and_score<true>(L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 32) key[1] = spawn_and_score<true>(32 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 64) key[2] = spawn_and_score<true>(64 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 96) key[3] = spawn_and_score<true>(96 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+        } else if (n_valid > 32) {                                      // the common case: two rounds, one basic block
+            key[0] = spawn_and_score<false>(L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            key[1] = spawn_and_score<false>(32 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 64) key[2] = spawn_and_score<false>(64 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 96) key[3] = spawn_and_score<false>(96 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+        } else {
+            key[0] = spawn_and_score<false>(L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
         }
         __syncwarp();
         if (full_level) {
@@ -237,10 +280,19 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         }
 
         // ---- C: stable top-k ------------------------------------------------------------------------
-        uint32_t top = sort_desc32(key[0], lane);
-#pragma unroll
-        for (int r = 1; r < 4; ++r)
-            if (r * 32 < n_valid) top = merge_top32(top, sort_desc32(key[r], lane), lane);
+        uint32_t top;
+        if (n_valid > 32) {
+            sort_desc32_x2(key[0], key[1], lane);
+            top = merge_top32(key[0], key[1], lane);
+            if (n_valid > 96) {
+                sort_desc32_x2(key[2], key[3], lane);
+                top = merge_top32(top, merge_top32(key[2], key[3], lane), lane);
+            } else if (n_valid > 64) {
+                top = merge_top32(top, sort_desc32(key[2], lane), lane);
+            }
+        } else {
+            top = sort_desc32(key[0], lane);
+        }
         nb = min(P.width, n_valid);                                     // agent:132,175
         const int pick = 127 - (int)((top >> 2) & 127u);
         if ((int)lane < nb) {
