@@ -161,7 +161,10 @@ struct RolloutArgs {
 
 // `steps` env.step calls per env with the board in registers; random-policy actions from the
 // Philox action stream (one block = 64 actions), auto-reset on game over.
-constexpr int kRolloutThreads = 512;
+#ifndef G2048_ROLLOUT_THREADS
+#define G2048_ROLLOUT_THREADS 512
+#endif
+constexpr int kRolloutThreads = G2048_ROLLOUT_THREADS;
 #ifndef G2048_ROLLOUT_UNROLL
 #define G2048_ROLLOUT_UNROLL 1
 #endif

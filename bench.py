@@ -320,7 +320,7 @@ def run_ours(args):
     # ---- CPU baseline: oracle port on the host cores, bounded sample ---------------------------------------
     from oracle import pyoracle as O
     threads = O.max_threads()
-    cpu_n, cpu_steps, cpu_roots = 16384, 500, 4096
+    cpu_n, cpu_steps, cpu_roots = 16384, 1500, 16384         # ~15-25 core-seconds in total
     cpu_value = cpu_env_sample(O, cpu_n, cpu_steps, threads)
     cpu_beam = cpu_beam_sample(O, cpu_roots, threads)
 

@@ -1,0 +1,125 @@
+"""Turns ncu reports / launch lists brought back in gpurun_out/ into the small text summaries
+committed under profiles/ (the .ncu-rep files themselves are scratch).
+
+usage: python profiles/summarize.py <round-tag>     e.g. r01
+"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+RAW_KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "sm__cycles_elapsed.max", "gpc__cycles_elapsed.avg.per_second",
+]
+
+
+def ncu(args):
+    return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
+
+
+def raw_summary(rep, label, units=None):
+    rows = list(csv.reader(ncu(["-i", rep, "--page", "raw", "--csv"]).splitlines()))
+    hdr, unit, val = rows[0], rows[1], rows[2]
+    lines = [f"## {label}", f"report: {os.path.basename(rep)} (ncu --set full --clock-control none, one launch)", ""]
+    d = dict(zip(hdr, zip(unit, val)))
+    lines.append(f"kernel: {d['Kernel Name'][1]}")
+    for k in RAW_KEYS:
+        if k in d:
+            lines.append(f"{k:75s} {d[k][1]:>16s} {d[k][0]}")
+    stalls = sorted(((float(v[1] or 0), k) for k, v in d.items()
+                     if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and "not_issued" not in k), reverse=True)
+    lines.append("")
+    lines.append("warp stall reasons (warps per issue-active cycle), top 8:")
+    for v, k in stalls[:8]:
+        lines.append(f"  {k.split('issue_stalled_')[1].replace('_per_issue_active.ratio', ''):28s} {v:6.2f}")
+    if units:
+        inst = float(d["smsp__inst_executed.sum"][1])
+        lines.append("")
+        lines.append(f"warp instructions per {units[0]}: {inst / units[1]:.1f}   ({units[2]})")
+    return lines, d
+
+
+def opcode_hist(rep, per, per_name):
+    rows = list(csv.reader(ncu(["-i", rep, "--page", "source", "--csv"]).splitlines()))
+    hdr = rows[1]
+    i_src, i_ex = hdr.index("Source"), hdr.index("Instructions Executed")
+    hist = collections.Counter()
+    for r in rows[2:]:
+        if len(r) <= i_ex:
+            continue
+        ins = r[i_src].strip()
+        if ins.startswith("@"):
+            ins = ins.split(None, 1)[1]
+        hist[ins.split()[0].rstrip(";").split(".")[0]] += int(r[i_ex])
+    tot = sum(hist.values())
+    lines = ["", f"executed warp instructions by opcode, per {per_name} (top 16):"]
+    for op, n in hist.most_common(16):
+        lines.append(f"  {op:10s} {n / per:8.2f}  {100 * n / tot:5.1f}%")
+    return lines
+
+
+def launch_list(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr = rows[h]
+    ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[h + 1:]:
+        if len(r) > iv:
+            try:
+                v = float(r[iv].replace(",", ""))
+            except ValueError:
+                continue
+            k = r[ik].split("(")[0]
+            agg[k][0] += 1
+            agg[k][1] += v
+    tot = sum(v[1] for v in agg.values())
+    lines = [f"## launch list ({os.path.basename(path)}: ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 10 --warmup 3`)",
+             "per-launch times are cold-cache and serialised: compare SHARES, not absolutes", "",
+             f"{'kernel':72s} {'launches':>8s} {'total ms':>10s} {'avg us':>9s} {'share':>7s}"]
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+        lines.append(f"{k[:72]:72s} {n:8d} {t / 1e6:10.3f} {t / n / 1e3:9.2f} {100 * t / tot:6.1f}%")
+    return lines
+
+
+def main():
+    text = [f"# ncu summaries, round {tag} (B200, sm_100a)", ""]
+    ll = os.path.join(OUT, f"launches_{tag}.csv")
+    if os.path.exists(ll):
+        text += launch_list(ll) + [""]
+    n_steps = 65536 * 2000 / 32
+    rep = os.path.join(OUT, f"prof_rollout_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        lines, d = raw_summary(rep, "env_rollout_kernel (headline kernel)", ("board-step (warp-step = 32 board-steps)", n_steps, "65,536 envs x 2,000 steps per launch"))
+        text += lines + opcode_hist(rep, n_steps, "warp-step") + [""]
+    rep = os.path.join(OUT, f"prof_beam_r01.ncu-rep".replace("r01", tag))
+    if os.path.exists(rep):
+        lines, d = raw_summary(rep, "beam_search_kernel (width 20, depth 40, 10,000 roots)")
+        text += lines + [""]
+    rep = os.path.join(OUT, f"prof_step_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        lines, d = raw_summary(rep, "env_step_kernel<global tables> (per-step API, 65,536 envs per launch)")
+        text += lines + [""]
+    path = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.md")
+    with open(path, "w") as f:
+        f.write("\n".join(text) + "\n")
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

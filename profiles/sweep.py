@@ -8,7 +8,8 @@ from g2048_b200 import _lib
 
 tag = sys.argv[1] if len(sys.argv) > 1 else os.path.basename(G.LIB_PATH)
 dev = "cuda:0"
-env = G.BatchedGame2048Env(65536, dev, seed=1234)
+N = int(os.environ.get("SWEEP_ENVS", 65536))
+env = G.BatchedGame2048Env(N, dev, seed=1234)
 env.reset()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def timed(fn, reps):
@@ -22,7 +23,9 @@ def timed(fn, reps):
         tot += s.elapsed_time(e)
     return tot / reps
 ms = timed(lambda: env.rollout(2000), 10)
-res = {"tag": tag, "rollout_ms": ms, "steps_per_s": 65536 * 2000 / ms * 1e3}
+res = {"tag": tag, "envs": N, "rollout_ms": ms, "steps_per_s": N * 2000 / ms * 1e3}
+if os.environ.get("SWEEP_ROLLOUT_ONLY"):
+    print(json.dumps(res)); sys.exit(0)
 for (W, D) in ((20, 40), (15, 20)):
     roots = torch.empty(10000, dtype=torch.int64, device=dev)
     _lib.check(_lib.use_device(0).g2048_synthetic_boards(roots.data_ptr(), 10000, 1234, 0, torch.cuda.current_stream().cuda_stream))
