@@ -38,6 +38,12 @@ BYTES_PER_STEP = 22          # 8 rd board + 1 rd action + 8 wr boar
 BYTES_PER_NODE = 21          # 8 rd parent + 8 wr child + 4 wr score + 1 wr first action
 SEED = 1234
 BEAM_W, BEAM_D, BEAM_ROOTS = 20, 40, 10000
+# From the committed ncu capture of the same command (profiles/ncu_summary_r01.md): executed warp
+# instructions per warp-step of env_rollout_kernel, its DRAM traffic per launch, and pipe utilisation.
+NCU_ROLLOUT = {"warp_inst_per_warp_step": 436.3, "dram_bytes_per_launch": 2150144, "alu_pipe_pct_of_peak": 64.2,
+               "issue_active_pct": 67.9, "fma_pipe_pct_of_peak": 17.1, "source": "profiles/ncu_summary_r01.md"}
+NCU_BEAM = {"alu_pipe_pct_of_peak": 71.9, "issue_active_pct": 66.6, "dram_bytes_per_launch": 269056,
+            "source": "profiles/ncu_summary_r01.md"}
 
 
 def dist_env():
@@ -327,6 +333,10 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     achieved = BYTES_PER_STEP * (n * env_steps) / (kernel_ms * 1e-3) / 1e9       # per launch, one rank
     beam_achieved = BYTES_PER_NODE * (nodes_total / world / args.steps) / (beam_ms / args.steps * 1e-3) / 1e9
+    # ALU/issue view of the same launch: warp instructions issued per second over the SM issue peak
+    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6 if clocks else 1965.0e6
+    issue_peak = 148 * 4 * sm_hz                                   # 1 warp-instruction / clk / scheduler
+    issue_rate = (value / world) / 32.0 * NCU_ROLLOUT["warp_inst_per_warp_step"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -344,8 +354,13 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "env_rollout_kernel", "peak_source": peak_src,
-                     "note": "algorithmic 22 B per board-step (SURVEY 8d); the kernel is ALU-issue bound, see DESIGN.md"},
+                     "traffic": NCU_ROLLOUT["dram_bytes_per_launch"], "kernel": "env_rollout_kernel", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_STEP * n * env_steps,
+                     "note": "algorithmic 22 B per board-step (SURVEY 8d) as if every step round-tripped HBM; the fused "
+                             "rollout keeps boards in registers (measured DRAM traffic = `traffic`), so the binding "
+                             "roofline is ALU-pipe issue, reported in `issue`"},
+        "issue": {"bound": "alu", "achieved": issue_rate, "peak": issue_peak, "unit": "warp-inst/s",
+                  "frac": issue_rate / issue_peak, "ncu": NCU_ROLLOUT},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{cpu_n} envs x {cpu_steps} steps, oracle/orc2048.c on {threads} threads"},
         "per_step_api": {"value": per_step_api_value, "unit": UNIT,
@@ -356,7 +371,8 @@ def run_ours(args):
                  "unit": "nodes/s", "roots_per_gpu": args.beam_roots, "nodes_per_step": nodes_total // max(1, args.steps),
                  "ms_per_step": beam_ms / args.steps, "e2e": {"value": beam_e2e, "unit": "nodes/s", "api": "g2048_host_beam_search"},
                  "roofline": {"bound": "hbm", "achieved": beam_achieved, "peak": peak, "unit": "GB/s",
-                              "frac": beam_achieved / peak, "traffic": None, "kernel": "beam_search_kernel"},
+                              "frac": beam_achieved / peak, "traffic": NCU_BEAM["dram_bytes_per_launch"],
+                              "kernel": "beam_search_kernel", "ncu": NCU_BEAM},
                  "cpu_baseline": {"value": cpu_beam, "unit": "nodes/s", "cores": threads, "kind": "port",
                                   "sample": f"{cpu_roots} synthetic roots, oracle/orc2048.c on {threads} threads"}},
         "highest_tile_histogram": {str(1 << e): int(c) for e, c in enumerate(hist.tolist()) if c},
