@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -216,7 +216,6 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - wall0
     launches = G.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
     dev_ms = max_over_ranks(dev_ms)
     value = world * n * env_steps * args.steps / (dev_ms * 1e-3)
@@ -312,6 +311,8 @@ def run_ours(args):
     _lib.check(lib.g2048_host_beam_search(P(hroots), None, None, 100, P(ha8), P(hp), None, P(hk), args.beam_roots, BEAM_W, BEAM_D,
                                           512, 1024, SEED, rank * args.beam_roots))
     beam_e2e = world * int(hk.sum()) / max_over_ranks(time.perf_counter() - t0)
+
+    clocks = sampler.stop() if rank == 0 else None      # sampled across all GPU timed regions above
 
     # final histogram all-reduce (the only collective of the workload; not on the hot path)
     hist = torch.bincount(env.highest_exp.to(torch.int64), minlength=18)
