@@ -62,24 +62,26 @@ def test_out_of_range_action_is_an_invalid_move(orc):
 
 
 def test_dead_full_and_single_tile_boards(orc):
-    dead = [[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 2]]
+    dead = [[4, 8, 2, 4], [16, 2, 8, 2], [4, 64, 4, 1024], [2, 4, 2, 4096]]      # SURVEY 8c board L2
+    dead_symmetric = [[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 2]]      # rot180 == itself: even the agent sees no move
     full_mergeable = [[2, 2, 4, 8], [4, 8, 16, 32], [2, 4, 8, 16], [32, 64, 128, 256]]
     single = [[0, 0, 0, 0], [0, 2, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]
     top = [[32768, 16384, 8192, 4096], [256, 512, 1024, 2048], [128, 64, 32, 16], [2, 4, 8, 2]]
-    vals = np.array([dead, full_mergeable, single, top], np.int32).reshape(4, 16)
+    vals = np.array([dead, full_mergeable, single, top, dead_symmetric], np.int32).reshape(5, 16)
     packed = G.pack_boards(vals)
     e, a = X.host_legal(packed)
     assert e[0] == 0 and a[0] == 8                        # dead board: the agent still believes in DOWN
-    for i in range(4):
+    assert e[4] == 0 and a[4] == 0
+    for i in range(5):
         assert e[i] == orc.env_legal_mask(vals[i]) and a[i] == orc.agent_legal_mask(vals[i])
     act, p, s, k = X.host_beam(packed, 15, 20, SEED)
-    for i in range(4):
+    for i in range(5):
         o = orc.beam_get_action(vals[i], None, 15, 20, SEED, i, 0)
         assert (act[i], p[i], k[i], s[i]) == (o.action, o.prob, o.nodes, o.best_score)
     for action in range(4):
-        b = packed.copy(); sc = np.zeros(4, np.int32); h = X.exps(vals).max(axis=1).astype(np.uint8); c = np.zeros(4, np.uint32)
-        r, sd, v, l, d = X.host_step(b, np.full(4, action, np.uint8), sc, h, c, SEED, game0=50)
-        for i in range(4):
+        b = packed.copy(); sc = np.zeros(5, np.int32); h = X.exps(vals).max(axis=1).astype(np.uint8); c = np.zeros(5, np.uint32)
+        r, sd, v, l, d = X.host_step(b, np.full(5, action, np.uint8), sc, h, c, SEED, game0=50)
+        for i in range(5):
             env = orc.Env(SEED, 50 + i, ctor_reset=False)
             env.set_board(vals[i], score=0, highest_tile=int(vals[i].max()))
             ob, orw, od, oi = env.step(action)
@@ -92,7 +94,7 @@ def test_maximum_beam_width_and_depth(orc):
     act, p, s, k = X.host_beam(packed, 32, 60, SEED, game0=808)
     oa, op, on, ob = orc.beam_batch(vals, 32, 60, SEED, 808, 0)
     assert (act == oa).all() and (k == on).all() and (s == ob).all()
-    assert k.max() <= 4 + 39 * 128                          # depth 60 is capped by the adaptive rule at 25 / 10 / 60 -> <= 60 levels
+    assert k.max() <= 4 + 59 * 128                          # at most 4 root children + 59 levels of 4 * 32
 
 
 def test_reference_style_training_loop_runs_on_the_facades():
