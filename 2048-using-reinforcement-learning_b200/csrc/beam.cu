@@ -13,6 +13,7 @@
 //                        stable sort, agent:131,174).
 #include "common.cuh"
 #include "env.cuh"
+#include "stage.cuh"
 
 #ifndef G2048_BEAM_WARPS
 #define G2048_BEAM_WARPS 24
@@ -312,10 +313,7 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
 
 __device__ __forceinline__ void stage_row_table(uint8_t *smem, const uint16_t *row)
 {
-    const uint4 *src = reinterpret_cast<const uint4 *>(row);
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (uint32_t i = threadIdx.x; i < kRowTableBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    __syncthreads();
+    stage_bulk(smem, row, (uint32_t)kRowTableBytes, nullptr, nullptr, 0u);       // TMA bulk copy, stage.cuh
 }
 
 struct BeamArgs {

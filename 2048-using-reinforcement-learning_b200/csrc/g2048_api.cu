@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "env.cuh"
 #include "row_tables.h"
+#include "stage.cuh"
 
 namespace g2048 {
 
@@ -57,18 +58,10 @@ DeviceState *current_device_state()
 constexpr int kEnvThreads = 256;
 constexpr int kEnvSharedThreads = 512;   // one 192 KiB block per SM
 
-// Copies both row tables into dynamic shared memory (192 KiB), 16 bytes per thread per trip.
+// Both row tables into dynamic shared memory (192 KiB) by TMA bulk copy (stage.cuh).
 __device__ __forceinline__ void stage_tables(uint8_t *smem, const uint16_t *row, const uint8_t *code, bool with_code)
 {
-    const uint4 *src = reinterpret_cast<const uint4 *>(row);
-    uint4 *dst = reinterpret_cast<uint4 *>(smem);
-    for (uint32_t i = threadIdx.x; i < kRowTableBytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    if (with_code) {
-        const uint4 *src2 = reinterpret_cast<const uint4 *>(code);
-        uint4 *dst2 = reinterpret_cast<uint4 *>(smem + kRowTableBytes);
-        for (uint32_t i = threadIdx.x; i < kCodeTableBytes / 16; i += blockDim.x) dst2[i] = __ldg(src2 + i);
-    }
-    __syncthreads();
+    stage_bulk(smem, row, (uint32_t)kRowTableBytes, smem + kRowTableBytes, code, with_code ? (uint32_t)kCodeTableBytes : 0u);
 }
 
 struct StepArgs {
@@ -165,10 +158,6 @@ struct RolloutArgs {
 #define G2048_ROLLOUT_THREADS 512
 #endif
 constexpr int kRolloutThreads = G2048_ROLLOUT_THREADS;
-#ifndef G2048_ROLLOUT_UNROLL
-#define G2048_ROLLOUT_UNROLL 1
-#endif
-constexpr int kRolloutUnroll = G2048_ROLLOUT_UNROLL;   // steps per loop trip (ILP across steps)
 
 // Uniform random action of step t from the cached Philox action block (64 actions per block).
 __device__ __forceinline__ uint32_t cached_action(Philox4 &act, uint32_t t, bool first, uint32_t game,
