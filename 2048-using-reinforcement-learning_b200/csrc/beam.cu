@@ -351,12 +351,48 @@ __global__ void __launch_bounds__(kBeamThreads, 1) beam_search_kernel(BeamArgs a
     }
 }
 
+// A game that can be resumed exactly: every random draw is addressed by (game, call / spawn
+// counter), so the state below is all there is.
+struct GameState {
+    uint64_t board;
+    long long nodes;
+    int32_t score, moves, valid, invalid;
+    uint32_t highest, spawn_ctr, index;      // index = position in the caller's output arrays
+    int32_t ms[8];
+};
+
 struct GamesArgs {
     int64_t n; BeamParams P; int max_moves; uint32_t game0;
     int32_t *score; uint8_t *highest; int32_t *moves; int32_t *valid; int32_t *invalid;
     int32_t *milestone; int64_t *nodes; uint64_t *final_board;
-    const uint16_t *row; const uint8_t *code; unsigned long long *overflow; unsigned int *work;
+    const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
+    unsigned int *work;            // queue head of this launch
+    GameState *pending;            // stalled games handed to finish_games_kernel (may be nullptr)
+    unsigned int *pending_count;
 };
+
+__device__ __forceinline__ void write_game(const GamesArgs &a, const GameState &g)
+{
+    const uint32_t i = g.index;
+    if (a.score) a.score[i] = g.score;
+    if (a.highest) a.highest[i] = (uint8_t)g.highest;
+    if (a.moves) a.moves[i] = g.moves;
+    if (a.valid) a.valid[i] = g.valid;
+    if (a.invalid) a.invalid[i] = g.invalid;
+    if (a.milestone)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a.milestone[8 * i + m] = g.ms[m];
+    if (a.nodes) a.nodes[i] = g.nodes;
+    if (a.final_board) a.final_board[i] = g.board;
+}
+
+// Consecutive invalid moves after which a game is handed to the stall breaker.  The reference's
+// agent keeps choosing its fake-valid DOWN on some boards for thousands of moves
+// (report.md: games reaching the move limit); one warp would grind through them one call at a time.
+#ifndef G2048_STALL_STREAK
+#define G2048_STALL_STREAK 32
+#endif
+constexpr int kStallStreak = G2048_STALL_STREAK;
 
 // Whole games (evaluate_beam_search.py:16-98): one warp plays one game from Game2048Env() to
 // game over, fetching the next game id from a global queue so long games do not strand SMs.
@@ -378,37 +414,100 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         s.spawn_ctr = 0u;
         env_reset(s, a.P.K, game);      // Game2048Env() -> __init__ calls reset (env:27)
         env_reset(s, a.P.K, game);      // state = env.reset() (evaluate_beam_search.py:30)
-        int moves = 0, n_valid = 0, n_invalid = 0;
-        long long nodes = 0;
-        int ms[8];
+        GameState gs;
+        gs.index = g; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) ms[m] = -1;
+        for (int m = 0; m < 8; ++m) gs.ms[m] = -1;
         bool done = false;
-        while (!done && moves < a.max_moves) {
-            BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)moves, row, ws);
-            nodes += r.nodes;
+        int streak = 0;
+        while (!done && gs.moves < a.max_moves && streak < kStallStreak) {
+            BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
+            gs.nodes += r.nodes;
             StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
             done = st.done;
             // evaluate_beam_search.py:59-64 records the move index BEFORE `moves += 1` (:86)
 #pragma unroll
             for (int m = 0; m < 8; ++m)
-                if (ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) ms[m] = moves;
-            if (st.valid) ++n_valid; else ++n_invalid;
-            ++moves;
+                if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
+            if (st.valid) { ++gs.valid; streak = 0; } else { ++gs.invalid; streak = a.pending ? streak + 1 : 0; }
+            ++gs.moves;
         }
+        gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
         if (lane == 0) {
-            if (a.score) a.score[g] = s.score;
-            if (a.highest) a.highest[g] = (uint8_t)s.highest;
-            if (a.moves) a.moves[g] = moves;
-            if (a.valid) a.valid[g] = n_valid;
-            if (a.invalid) a.invalid[g] = n_invalid;
-            if (a.milestone)
-#pragma unroll
-                for (int m = 0; m < 8; ++m) a.milestone[8 * g + m] = ms[m];
-            if (a.nodes) a.nodes[g] = nodes;
-            if (a.final_board) a.final_board[g] = s.board.u64();
+            if (!done && gs.moves < a.max_moves) a.pending[atomicAdd(a.pending_count, 1u)] = gs;   // stalled: resume later
+            else write_game(a, gs);
         }
         __syncwarp();
+    }
+}
+
+// Stall breaker: kSpecWarps warps per game search the next kSpecWarps get_action calls of the SAME
+// board at once.  An invalid move changes nothing in the env (no spawn, no counter), so call m+1
+// sees the board of call m whenever move m is invalid: the first call whose action is valid is the
+// one the sequential loop would have reached, the calls before it are its invalid moves, the calls
+// after it are discarded.  Exact, and up to kSpecWarps times faster through a stall.
+// kSpecWarps = 8 (three games per block) when many games may be stalled, = 24 (one game per
+// block) when the launch is small enough that a whole SM per stalled game is available.
+struct SpecSlot { uint32_t action; int32_t nodes; };
+
+template <int kSpecWarps>
+__global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs a, unsigned int *queue)
+{
+    constexpr int kSpecGroups = kBeamWarps / kSpecWarps;
+    static_assert(kSpecGroups * kSpecWarps == kBeamWarps, "groups must tile the block");
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ SpecSlot slots[kSpecGroups][2][kSpecWarps];
+    __shared__ unsigned int next_game[kSpecGroups];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int warp = threadIdx.x >> 5;
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
+    const uint32_t lane = threadIdx.x & 31u;
+    const int group = warp / kSpecWarps, w = warp % kSpecWarps;
+    const unsigned int total = *a.pending_count;
+    auto group_barrier = [&]() { asm volatile("barrier.sync %0, %1;" ::"r"(1 + group), "r"(kSpecWarps * 32) : "memory"); };
+    for (;;) {
+        if (w == 0 && lane == 0) next_game[group] = atomicAdd(queue, 1u);
+        group_barrier();
+        const unsigned int p = next_game[group];
+        group_barrier();                                   // everyone has read it before the next round rewrites it
+        if (p >= total) break;
+        GameState gs = a.pending[p];                       // every warp of the group keeps an identical copy
+        const uint32_t game = a.game0 + gs.index;
+        EnvState s;
+        s.board = Board(gs.board); s.score = gs.score; s.highest = gs.highest; s.spawn_ctr = gs.spawn_ctr;
+        bool done = false;
+        int buf = 0;
+        while (!done && gs.moves < a.max_moves) {
+            const int allowed = min(kSpecWarps, a.max_moves - gs.moves);
+            if (w < allowed) {
+                BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(gs.moves + w), row, ws);
+                if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
+            }
+            group_barrier();
+            const uint32_t legal = env_legal_mask(s.board);
+            int first_valid = -1;
+            for (int j = 0; j < allowed; ++j) {
+                gs.nodes += slots[group][buf][j].nodes;
+                if ((legal >> slots[group][buf][j].action) & 1u) { first_valid = j; break; }
+            }
+            const int n_invalid = first_valid >= 0 ? first_valid : allowed;
+            gs.invalid += n_invalid;
+            gs.moves += n_invalid;                          // invalid moves: nothing else changes (env:188-192)
+            if (first_valid >= 0) {
+                StepResult st = env_step<true, false, false>(s, slots[group][buf][first_valid].action, row, a.code, a.P.K,
+                                                             game, nullptr, a.overflow);
+                done = st.done;
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
+                ++gs.valid;
+                ++gs.moves;
+            }
+            buf ^= 1;
+        }
+        gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
+        if (w == 0 && lane == 0) write_game(a, gs);
     }
 }
 
@@ -428,6 +527,8 @@ static int ensure_attrs()
     if (!g_attr_done[dev]) {
         G2048_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         g_attr_done[dev] = 1;
     }
     return G2048_OK;
@@ -458,16 +559,39 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
 {
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
+    // scratch for stalled games (grow-only, library-owned; see common.cuh)
+    if ((size_t)n > st->pending_cap) {
+        if (st->pending) { G2048_CUDA(cudaDeviceSynchronize()); G2048_CUDA(cudaFree(st->pending)); st->pending = nullptr; }
+        size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        G2048_CUDA(cudaMalloc(&st->pending, cap * sizeof(GameState)));
+        st->pending_cap = cap;
+    }
     unsigned int *work = next_work_counter(st);
+    unsigned int *pending_count = next_work_counter(st);
+    unsigned int *queue = next_work_counter(st);
     G2048_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned int), stream));
+    G2048_CUDA(cudaMemsetAsync(pending_count, 0, sizeof(unsigned int), stream));
+    G2048_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
-                st->row, st->code, st->overflow, work};
+                st->row, st->code, st->overflow, work, static_cast<GameState *>(st->pending), pending_count};
     int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
     int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
     play_games_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
     count_launch();
-    return check_cuda(cudaGetLastError(), "play_games_kernel");
+    G2048_CUDA(cudaGetLastError());
+    // stalled games: kSpecWarps warps each (how many there are is only known on the device, so the
+    // grid is sized for the worst case and surplus groups leave at once)
+    if (n <= 2048) {            // ~5 % of games stall: up to ~100 of them, one SM each
+        int grid2 = (int)(n < st->sm_count ? n : st->sm_count);
+        finish_games_kernel<kBeamWarps><<<grid2, kBeamThreads, kBeamSmemBytes, stream>>>(a, queue);
+    } else {
+        int64_t groups = (n + 2) / 3;
+        int grid2 = (int)(groups < st->sm_count ? groups : st->sm_count);
+        finish_games_kernel<8><<<grid2, kBeamThreads, kBeamSmemBytes, stream>>>(a, queue);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "finish_games_kernel");
 }
 
 }  // namespace g2048

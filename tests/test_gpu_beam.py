@@ -146,3 +146,19 @@ def test_run_evaluation_writes_reference_results(orc, tmp_path):
     doc = json.load(open(tmp_path / "results" / "overall_results.json"))
     assert doc["scores"] == res["scores"] and doc["parameters"]["num_games"] == 12
     assert res["summary"]["games"] == 12 and res["summary"]["max_score"] == max(res["scores"])
+
+
+def test_stall_breaker_path_matches_sequential_oracle(orc):
+    """Games whose agent keeps choosing the fake-valid DOWN are finished by finish_games_kernel
+    (8 speculative get_action calls per round); per-game results must equal the sequential loop."""
+    n, W, D, cap = 160, 6, 8, 2500
+    out = X.host_play(n, W, D, SEED, game0=4000, max_moves=cap)
+    stalled = (out["moves"] == cap) | (out["invalid"] >= 32)
+    assert stalled.sum() >= 3, "choose parameters that exercise the stall path"
+    ref = orc.play_games(SEED, 4000, n, W, D, max_moves=cap)
+    for i in range(n):
+        r = ref[i]
+        assert (out["score"][i], 1 << int(out["highest"][i]), out["moves"][i], out["valid"][i], out["invalid"][i],
+                out["nodes"][i]) == (r.score, r.highest_tile, r.moves, r.valid_moves, r.invalid_moves, r.nodes), i
+        assert list(out["milestone"][i]) == list(r.milestone_move)
+    assert out["stats"][22] == n
