@@ -281,7 +281,8 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         }
 
         // ---- C: stable top-k ------------------------------------------------------------------------
-        uint32_t top;
+        nb = min(P.width, n_valid);                                     // agent:132,175
+        uint32_t top = 0u;
         if (n_valid > 32) {
             sort_desc32_x2(key[0], key[1], lane);
             top = merge_top32(key[0], key[1], lane);
@@ -294,7 +295,6 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         } else {
             top = sort_desc32(key[0], lane);
         }
-        nb = min(P.width, n_valid);                                     // agent:132,175
         const int pick = 127 - (int)((top >> 2) & 127u);
         if ((int)lane < nb) {
             mine = Board(ws.cand[pick]);
