@@ -301,3 +301,27 @@ def test_reset_done_on_device(orc):
     got = env.boards_u64()
     for j, o in enumerate(oracles):
         assert got[200 * j] == G.pack_board(o.board) and int(env.spawn_ctr[200 * j]) == o.s.spawn_ctr
+
+
+def test_cfg1_facade_one_board_random_legal_moves(orc):
+    """BASELINE config 1 on the drop-in facade: 1 board, uniform random legal moves, <= 2,000 steps,
+    step for step against the oracle (which tests/test_oracle_vs_reference.py holds to the live reference)."""
+    import random
+    policy = random.Random(2048)
+    env = G.Game2048Env(seed=SEED, game_id=77)
+    o = orc.Env(SEED, 77)
+    state = env.reset()
+    assert (o.reset() == state).all()
+    steps = 0
+    while steps < 2000:
+        vm = env.get_valid_moves()
+        if not any(vm):
+            break
+        a = policy.choice([k for k in range(4) if vm[k]])
+        state, r, done, info = env.step(a)
+        ob, orw, od, oi = o.step(a)
+        assert (state == ob).all() and float(r) == orw and done == od and int(info["score"]) == oi["score"]
+        steps += 1
+        if done:
+            break
+    assert steps > 50 and env.game_over == done

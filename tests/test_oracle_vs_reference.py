@@ -89,3 +89,30 @@ def test_ppo_features_vs_reference(orc):
         top = np.sort(b.flatten())[-4:]
         assert float(0.1 * sum(np.log2(t) for t in top if t > 0)) == orc.ppo_top4_bonus(b)
         assert (ppo.normalize_state(b) == orc.ppo_observe(b)).all()
+
+
+def test_cfg1_one_board_random_legal_moves(orc, ref):
+    """BASELINE config 1: the reference env, 1 board, uniform random LEGAL moves, <= 2,000 steps."""
+    import random
+    shim, game, _ = ref
+    policy = random.Random(2048)                      # the caller's own RNG, separate from the spawn stream
+    shim.select(P.DOM_ENV, 77, 0, 0)
+    env = game.Game2048Env()
+    state = env.reset()
+    o = orc.Env(SEED, 77)
+    assert (o.reset() == state).all()
+    steps = 0
+    while steps < 2000:
+        vm = env.get_valid_moves()
+        assert vm == [bool(orc.env_legal_mask(o.board) >> k & 1) for k in range(4)]
+        if not any(vm):
+            break
+        a = policy.choice([k for k in range(4) if vm[k]])
+        state, r, done, info = env.step(a)
+        ob, orw, od, oi = o.step(a)
+        assert (state == ob).all() and float(r) == orw and done == od and int(info["score"]) == oi["score"]
+        assert info["valid_move"]
+        steps += 1
+        if done:
+            break
+    assert steps > 50
