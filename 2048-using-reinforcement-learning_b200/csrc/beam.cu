@@ -559,13 +559,10 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
 {
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
-    // scratch for stalled games (grow-only, library-owned; see common.cuh)
-    if ((size_t)n > st->pending_cap) {
-        if (st->pending) { G2048_CUDA(cudaDeviceSynchronize()); G2048_CUDA(cudaFree(st->pending)); st->pending = nullptr; }
-        size_t cap = (size_t)n + (size_t)n / 4 + 1024;
-        G2048_CUDA(cudaMalloc(&st->pending, cap * sizeof(GameState)));
-        st->pending_cap = cap;
-    }
+    // per-launch scratch for stalled games from the stream-ordered allocator: concurrent launches on
+    // different streams never share it, and it is released when this launch's kernels are done
+    GameState *pending = nullptr;
+    G2048_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&pending), (size_t)n * sizeof(GameState), stream));
     unsigned int *work = next_work_counter(st);
     unsigned int *pending_count = next_work_counter(st);
     unsigned int *queue = next_work_counter(st);
@@ -574,7 +571,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     G2048_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
-                st->row, st->code, st->overflow, work, static_cast<GameState *>(st->pending), pending_count};
+                st->row, st->code, st->overflow, work, pending, pending_count};
     int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
     int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
     play_games_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
@@ -591,7 +588,8 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
         finish_games_kernel<8><<<grid2, kBeamThreads, kBeamSmemBytes, stream>>>(a, queue);
     }
     count_launch();
-    return check_cuda(cudaGetLastError(), "finish_games_kernel");
+    G2048_CUDA(cudaGetLastError());
+    return check_cuda(cudaFreeAsync(pending, stream), "cudaFreeAsync");
 }
 
 }  // namespace g2048

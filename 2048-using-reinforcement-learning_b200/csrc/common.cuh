@@ -20,8 +20,6 @@ struct DeviceState {
     unsigned long long *overflow = nullptr;  // sticky nibble-saturation counter
     unsigned int *work_counter = nullptr;    // ring of kWorkCounters queue heads (one per launch in flight)
     unsigned int next_counter = 0;
-    void *pending = nullptr;                 // GameState[pending_cap]: games handed from play_games to the stall breaker
-    size_t pending_cap = 0;
     int sm_count = 0;
 };
 
