@@ -159,34 +159,40 @@ struct RolloutArgs {
 #endif
 constexpr int kRolloutThreads = G2048_ROLLOUT_THREADS;
 
-// Uniform random action of step t from the cached Philox action block (64 actions per block).
-__device__ __forceinline__ uint32_t cached_action(Philox4 &act, uint32_t t, bool first, uint32_t game,
-                                                  const PhiloxKey &K)
-{
-    if ((t & 63u) == 0u && !first) act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, K);
-    const uint32_t sel = (t >> 4) & 3u;
-    const uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
-    return (word >> (2u * (t & 15u))) & 3u;
-}
-
 // Software-pipelined step loop: step_move(t) and step_reward(t-1) share a basic block.
+// Actions: one Philox block of the action stream holds 64 two-bit actions (16 per word), so the
+// loop nest is block -> word -> step and a step pays one AND and one shift for its action.
 template <bool kTrackMax>
 __device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &a, uint32_t game, const uint16_t *row,
                                               const uint8_t *code, double &rsum, int32_t &episodes)
 {
     if (a.steps <= 0) return;
-    Philox4 act = philox4x32_10(a.t0 >> 6, 0u, game, DOM_ACTION, a.K);
+    uint32_t t = a.t0;
+    const uint32_t end = a.t0 + (uint32_t)a.steps;
     uint32_t saturated = 0u;
-    bool full;
-    PendingReward pend = step_move<kTrackMax>(e, cached_action(act, a.t0, true, game, a.K), row, code,
-                                              a.K, game, saturated, full);
-    if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
-    for (int32_t step = 1; step < a.steps; ++step) {
-        const uint32_t action = cached_action(act, a.t0 + (uint32_t)step, false, game, a.K);
-        PendingReward cur = step_move<kTrackMax>(e, action, row, code, a.K, game, saturated, full);
-        rsum = __dadd_rn(rsum, step_reward(pend));          // float64 sum stays in step order
-        pend = cur;
-        if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
+    bool full, have = false;
+    PendingReward pend;
+    while (t < end) {
+        const Philox4 act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, a.K);
+        const uint32_t block_end = min(end, (t | 63u) + 1u);
+        while (t < block_end) {
+            const uint32_t sel = (t >> 4) & 3u;
+            uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
+            word >>= 2u * (t & 15u);
+            const uint32_t word_end = min(block_end, (t | 15u) + 1u);
+            if (!have) {                                     // first step of the launch: nothing to overlap with yet
+                pend = step_move<kTrackMax>(e, word & 3u, row, code, a.K, game, saturated, full);
+                if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
+                word >>= 2; ++t; have = true;
+            }
+            for (; t < word_end; ++t) {
+                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, a.K, game, saturated, full);
+                word >>= 2;
+                rsum = __dadd_rn(rsum, step_reward(pend));      // float64 sum stays in step order
+                pend = cur;
+                if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
+            }
+        }
     }
     rsum = __dadd_rn(rsum, step_reward(pend));
     if (saturated) atomicAdd(a.overflow, 1ull);
