@@ -90,3 +90,17 @@ def test_results_writer_matches_reference_layout(tmp_path):
     assert doc["parameters"] == {"beam_width": 15, "search_depth": 20, "num_games": 7}
     assert list(doc["milestones"]) == ["64", "128", "256", "512", "1024", "2048", "4096", "8192"]
     assert all(isinstance(v, int) for v in doc["scores"])
+
+
+def test_dropin_module_paths_resolve_to_the_engine():
+    """`PYTHONPATH=dropin` makes `environment.game_2048` / `agents.beam_search_agent` the GPU engine."""
+    import subprocess, sys
+    code = ("import environment.game_2048 as g, agents.beam_search_agent as a, g2048_b200 as G;"
+            "assert g.Game2048Env is G.Game2048Env and a.BeamSearchAgent is G.BeamSearchAgent;"
+            "assert g.Game2048Env.ACTIONS == {0: 'LEFT', 1: 'UP', 2: 'RIGHT', 3: 'DOWN'};"
+            "ag = a.BeamSearchAgent(beam_width=15, search_depth=20);"
+            "assert (ag.beam_width, ag.search_depth, ag.early_game_threshold, ag.mid_game_threshold) == (15, 20, 512, 1024);"
+            "assert ag.action_names[3] == 'DOWN'; ag.remember(1, 2, 3); ag.update(); print('ok')")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

@@ -162,3 +162,30 @@ def test_stall_breaker_path_matches_sequential_oracle(orc):
                 out["nodes"][i]) == (r.score, r.highest_tile, r.moves, r.valid_moves, r.invalid_moves, r.nodes), i
         assert list(out["milestone"][i]) == list(r.milestone_move)
     assert out["stats"][22] == n
+
+
+def test_dropin_modules_play_a_game_like_run_game(orc):
+    """evaluate_beam_search.run_game's call pattern (evaluate_beam_search.py:29-30,52-86) through the
+    drop-in module paths, against the oracle's whole-game driver."""
+    import importlib, os, random, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        for k in [k for k in sys.modules if k in ("environment", "agents") or k.startswith(("environment.", "agents."))]:
+            sys.modules.pop(k)
+        game_mod = importlib.import_module("environment.game_2048")
+        agent_mod = importlib.import_module("agents.beam_search_agent")
+    finally:
+        sys.path.pop(0)
+    agent = agent_mod.BeamSearchAgent(beam_width=4, search_depth=6, seed=SEED)
+    env = game_mod.Game2048Env(seed=SEED, game_id=agent._game)         # one game id -> the streams of orc.play_game
+    state = env.reset()
+    done, moves, valid, invalid = False, 0, 0, 0
+    while not done and moves < 10000:
+        action, _ = agent.get_action(state)
+        state, reward, done, info = env.step(action)
+        valid += info["valid_move"]; invalid += not info["valid_move"]
+        moves += 1
+    ref = orc.play_game(SEED, agent._game, 4, 6, max_moves=10000)
+    assert (int(info["score"]), int(np.max(state)), moves, valid, invalid) == \
+        (ref.score, ref.highest_tile, ref.moves, ref.valid_moves, ref.invalid_moves)
