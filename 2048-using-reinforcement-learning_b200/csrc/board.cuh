@@ -274,7 +274,7 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return o;
 }
 
-enum : uint32_t { DOM_ENV = 0, DOM_BEAM = 1, DOM_ACTION = 2, DOM_BOARD = 3 };
+enum : uint32_t { DOM_ENV = 0, DOM_BEAM = 1, DOM_ACTION = 2, DOM_BOARD = 3, DOM_HYBRID = 4 };
 
 struct SpawnWords { uint32_t pos, val; };
 // spawn i of stream (seed, game, call, domain): words 2(i&1), 2(i&1)+1 of block i>>1

@@ -338,6 +338,61 @@ __global__ void simulate_move_kernel(const uint64_t *boards, const uint8_t *acti
     }
 }
 
+// The hybrid agent's sampled expansion (agents/hybrid.py:578-692): one (board,
+// action) per thread -> up to 6 outcomes at index 8*i + k.  An invalid move gives the single
+// outcome (board, -1.0, not done).  Otherwise min(3, #empty) cells are picked by a partial
+// Fisher-Yates over the row-major empty list (one draw per pick, the shim's `random.sample`) and
+// each yields a 2-tile outcome (reward * 0.9) and a 4-tile outcome (reward * 0.1), with
+// reward = (sum(new) - sum(old)) + (new max if it grew) + 0.1 * #empty(new)  (hybrid.py:676-692).
+constexpr int kHybridStride = 8;
+__global__ void hybrid_expand_kernel(const uint64_t *boards, const uint8_t *actions, const uint32_t *call,
+                                     const uint32_t *draw0, uint64_t *out_boards, double *out_reward, uint8_t *out_done,
+                                     int32_t *count, uint32_t *draws, int64_t n, PhiloxKey K, uint32_t game0, uint32_t call0,
+                                     const uint16_t *row)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Board state(boards[i]);
+        const uint32_t action = actions[i];
+        Board moved = env_move<false>(state, action, row);
+        int k = 0;
+        uint32_t draw = draw0 ? draw0[i] : 0u, used = 0u;
+        if (moved == state) {
+            if (out_boards) out_boards[kHybridStride * i] = state.u64();
+            if (out_reward) out_reward[kHybridStride * i] = -1.0;
+            if (out_done) out_done[kHybridStride * i] = 0;
+            k = 1;
+        } else {
+            const uint64_t m64 = moved.u64();
+            int cells[16], ne = 0;
+            for (int c = 0; c < 16; ++c) if (((m64 >> (4 * c)) & 15ull) == 0ull) cells[ne++] = c;
+            const uint32_t old_max = max_exponent(state);
+            const int picks = ne < 3 ? ne : 3;
+            for (int p = 0; p < picks; ++p) {
+                Philox4 blk = philox4x32_10(draw >> 2, call ? call[i] : call0, game0 + (uint32_t)i, DOM_HYBRID, K);
+                const uint32_t word = (draw & 3u) == 0 ? blk.w[0] : (draw & 3u) == 1 ? blk.w[1] : (draw & 3u) == 2 ? blk.w[2] : blk.w[3];
+                ++draw; ++used;
+                const int j = p + (int)__umulhi(word, (uint32_t)(ne - p));
+                const int t = cells[p]; cells[p] = cells[j]; cells[j] = t;
+                for (uint32_t e = 1; e <= 2; ++e) {
+                    const uint64_t nb = m64 | ((uint64_t)e << (4 * cells[p]));
+                    // moves conserve the tile sum: sum(new) - sum(old) is the spawned tile
+                    const long long merge_reward = 1ll << e;
+                    const uint32_t new_max = max(max_exponent(moved), e);
+                    const long long bonus = new_max > old_max ? (1ll << new_max) : 0ll;
+                    const double empty_bonus = __dmul_rn((double)(ne - 1), 0.1);
+                    const double reward = __dadd_rn((double)(merge_reward + bonus), empty_bonus);
+                    if (out_boards) out_boards[kHybridStride * i + k] = nb;
+                    if (out_reward) out_reward[kHybridStride * i + k] = __dmul_rn(reward, e == 1 ? 0.9 : 0.1);
+                    if (out_done) out_done[kHybridStride * i + k] = 0;
+                    ++k;
+                }
+            }
+        }
+        if (count) count[i] = k;
+        if (draws) draws[i] = used;
+    }
+}
+
 // Game2048Env._evaluate_pattern (env:313-339): max(snake-weighted, corner-weighted tile sum) / 100
 __global__ void pattern_kernel(const uint64_t *boards, double *out, int64_t n)
 {
@@ -559,6 +614,17 @@ int g2048_simulate_move(const uint64_t *boards, const uint8_t *actions, const ui
     G2048_ENTER(boards && actions);
     simulate_move_kernel<<<grid_for(n, 128, st->sm_count, 16), 128, 0, s>>>(boards, actions, highest_exp, next_boards, reward,
                                                                           done, count, n, st->row, st->code);
+    G2048_LAUNCHED();
+}
+
+int g2048_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const uint32_t *call, uint32_t call0,
+                        const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                        uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards && actions);
+    hybrid_expand_kernel<<<grid_for(n, 128, st->sm_count, 16), 128, 0, s>>>(boards, actions, call, draw0, next_boards, reward,
+                                                                          done, count, draws, n, make_philox_key(seed), game0,
+                                                                          call0, st->row);
     G2048_LAUNCHED();
 }
 
@@ -909,6 +975,38 @@ int g2048_host_simulate_move(const uint64_t *boards, const uint8_t *actions, con
     G2048_TRY(to_host(a, done, d_d, 32 * n));
     G2048_TRY(to_host(a, count, d_c, n));
     G2048_TRY(to_host(a, pattern, d_p, n));
+    G2048_CUDA(cudaStreamSynchronize(a->stream));
+    return G2048_OK;
+}
+
+int g2048_host_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const uint32_t *call, uint32_t call0,
+                             const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                             uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0)
+{
+    if (!current_device_state()) return G2048_ENOTINIT;
+    if (n < 0 || !boards || !actions) return set_error(G2048_EINVAL, "g2048_host_hybrid_expand: bad argument");
+    if (n == 0) return G2048_OK;
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    Arena *a;
+    G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<uint8_t>(n) + 3 * arena_bytes<uint32_t>(n) +
+                                  arena_bytes<uint64_t>(8 * n) + arena_bytes<double>(8 * n) + arena_bytes<uint8_t>(8 * n) +
+                                  arena_bytes<int32_t>(n)));
+    uint64_t *d_b; uint8_t *d_a; uint32_t *d_call = nullptr, *d_d0 = nullptr;
+    G2048_TRY(to_device(a, &d_b, boards, n, true));
+    G2048_TRY(to_device(a, &d_a, actions, n, true));
+    if (call) G2048_TRY(to_device(a, &d_call, call, n, true));
+    if (draw0) G2048_TRY(to_device(a, &d_d0, draw0, n, true));
+    uint64_t *d_nb = arena_take<uint64_t>(a, 8 * n);
+    double *d_r = arena_take<double>(a, 8 * n);
+    uint8_t *d_dn = arena_take<uint8_t>(a, 8 * n);
+    int32_t *d_c = arena_take<int32_t>(a, n);
+    uint32_t *d_u = arena_take<uint32_t>(a, n);
+    G2048_TRY(g2048_hybrid_expand(d_b, d_a, d_call, call0, d_d0, d_nb, d_r, d_dn, d_c, d_u, n, seed, game0, a->stream));
+    G2048_TRY(to_host(a, next_boards, d_nb, 8 * n));
+    G2048_TRY(to_host(a, reward, d_r, 8 * n));
+    G2048_TRY(to_host(a, done, d_dn, 8 * n));
+    G2048_TRY(to_host(a, count, d_c, n));
+    G2048_TRY(to_host(a, draws, d_u, n));
     G2048_CUDA(cudaStreamSynchronize(a->stream));
     return G2048_OK;
 }

@@ -104,6 +104,15 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
 int g2048_simulate_move(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest_exp,
                         uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
                         int64_t n, void *stream);
+/* The hybrid agent's sampled one-move expansion, agents/hybrid.py:578-692 (its own simulate_move and
+ * _calculate_simulation_reward): outcome k of (boards[i], actions[i]) at index 8*i + k, count[i] <= 6.
+ * Invalid move: one outcome (board, -1.0, not done).  Else min(3, #empty) cells, picked by a partial
+ * Fisher-Yates over the row-major empty list with draws draw0[i].. of stream (seed, game0+i,
+ * call[i] or call0, domain 4), each as a 2-tile (reward*0.9) and a 4-tile (reward*0.1) outcome.
+ * draws[i] = picks made.  Optional: call, draw0, every output. */
+int g2048_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const uint32_t *call, uint32_t call0,
+                        const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                        uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0, void *stream);
 /* Game2048Env._evaluate_pattern (env:313-339): max(snake, corner weighted tile sums) / 100. */
 int g2048_evaluate_pattern(const uint64_t *boards, double *pattern, int64_t n, void *stream);
 
@@ -175,6 +184,9 @@ int g2048_host_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_ex
                            int64_t n, int32_t steps, uint32_t t0, uint64_t seed, uint32_t game0);
 int g2048_host_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n);
 int g2048_host_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t n);
+int g2048_host_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const uint32_t *call, uint32_t call0,
+                             const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                             uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0);
 int g2048_host_simulate_move(const uint64_t *boards, const uint8_t *actions, const uint8_t *highest_exp,
                              uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count, double *pattern, int64_t n);
 int g2048_host_ppo_features(const uint64_t *boards, float *obs, double *heuristic, double *top4_bonus, int64_t n);

@@ -202,7 +202,7 @@ def main():
 
     # ---- Game2048Env.simulate_move (game_2048.py:341-387) and _evaluate_pattern (:313-339)
     sims = []
-    for b in boards[:40]:
+    for b in boards[:18]:
         if b.max() == 0:
             continue
         for a in range(4):
@@ -215,6 +215,18 @@ def main():
         env.board = b.reshape(4, 4).copy()
         sims[-1]["pattern"] = float(env._evaluate_pattern()).hex()
     G["simulate_move"] = sims
+
+    # ---- the hybrid agent's own simulate_move (agents/hybrid.py:578-692), SURVEY 8f row 4
+    HEnv = R.load_hybrid_env_class(shim)
+    henv = HEnv.__new__(HEnv); henv.size = 4
+    hyb = []
+    for g, b in enumerate(boards[:24]):
+        for a in range(4):
+            shim.select(P.DOM_HYBRID, g, 2, 0)
+            outs = henv.simulate_move(b.reshape(4, 4).copy(), a)
+            hyb.append({"board": L(b), "action": a, "game": g, "call": 2, "draws": shim.draw,
+                        "outcomes": [{"state": L(s_), "reward": float(r_).hex(), "done": bool(d_)} for s_, r_, d_ in outs]})
+    G["hybrid_expand"] = hyb
 
     # ---- PPO-side features (agents/ppo_agent.py:184-195, 251-254, 271-333), SURVEY 8f row 1
     PPO = R.load_ppo_agent_class()

@@ -269,6 +269,54 @@ int orc_env_simulate_move(const int32_t state[16], int action, int32_t highest_t
     return k;
 }
 
+/* agents/hybrid.py:578-635: the hybrid agent's own Game2048Env.simulate_move (monkey-patched onto a
+ * private copy of the env class, hybrid.py:695-697) with _calculate_simulation_reward (:676-692).
+ * An invalid move yields the single outcome (board, -1.0, False).  Otherwise min(3, #empty) cells
+ * are drawn with random.sample -- served by the shim as a partial Fisher-Yates over the row-major
+ * empty list, one draw per pick, j = i + floor(u * (n - i) / 2^32) -- and each yields a 2-tile
+ * outcome (reward * 0.9) and a 4-tile outcome (reward * 0.1).  *draw is the sequential draw index
+ * in stream (seed, game, call, ORC_DOM_HYBRID), advanced by the picks made. */
+int orc_hybrid_simulate_move(const int32_t board[16], int action, uint64_t seed, uint32_t game, uint32_t call,
+                             uint32_t *draw, int32_t out_boards[6][16], double out_reward[6], int32_t out_done[6])
+{
+    int32_t moved[16];
+    memcpy(moved, board, sizeof moved);
+    orc_env_move(moved, action);                                       /* hybrid.py:588-602 (true directions) */
+    if (memcmp(moved, board, sizeof moved) == 0) {                     /* :605-609 */
+        memcpy(out_boards[0], moved, sizeof moved); out_reward[0] = -1.0; out_done[0] = 0;
+        return 1;
+    }
+    int cells[16], n = 0;
+    for (int i = 0; i < 16; ++i) if (moved[i] == 0) cells[n++] = i;    /* :612 */
+    if (n == 0) { memcpy(out_boards[0], moved, sizeof moved); out_reward[0] = 0.0; out_done[0] = 1; return 1; }   /* :613-615 */
+    int k = n < 3 ? n : 3, count = 0;                                  /* :621-622 */
+    int64_t old_sum = 0; int32_t old_max = max_tile(board);
+    for (int i = 0; i < 16; ++i) old_sum += board[i];
+    for (int i = 0; i < k; ++i) {
+        uint32_t w[4];
+        stream_block(seed, game, call, ORC_DOM_HYBRID, *draw >> 2, w);
+        int j = i + pick_index(w[*draw & 3], n - i);
+        *draw += 1;
+        int t = cells[i]; cells[i] = cells[j]; cells[j] = t;
+        for (int tile = 2; tile <= 4; tile += 2) {                     /* :624-634 */
+            int32_t nb[16];
+            memcpy(nb, moved, sizeof nb);
+            nb[cells[i]] = tile;
+            int64_t new_sum = 0; int32_t new_max = max_tile(nb);
+            for (int c = 0; c < 16; ++c) new_sum += nb[c];
+            int64_t merge_reward = new_sum - old_sum;                  /* :679-681 */
+            int64_t bonus = new_max > old_max ? new_max : 0;           /* :684-688 */
+            double empty_bonus = (double)count_empty(nb) * 0.1;        /* :691 */
+            double reward = (double)(merge_reward + bonus) + empty_bonus;
+            memcpy(out_boards[count], nb, sizeof nb);
+            out_reward[count] = reward * (tile == 2 ? 0.9 : 0.1);
+            out_done[count] = 0;
+            ++count;
+        }
+    }
+    return count;
+}
+
 /* env:313-339 _evaluate_pattern (never called by the reference): max of the snake-weighted and the
  * corner-weighted sum of tile VALUES, each / 100. */
 double orc_env_pattern(const int32_t b[16])

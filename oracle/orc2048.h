@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 /* Random stream domains (word c3 of the Philox counter). */
-enum { ORC_DOM_ENV = 0, ORC_DOM_BEAM = 1, ORC_DOM_ACTION = 2, ORC_DOM_BOARD = 3 };
+enum { ORC_DOM_ENV = 0, ORC_DOM_BEAM = 1, ORC_DOM_ACTION = 2, ORC_DOM_BOARD = 3, ORC_DOM_HYBRID = 4 };
 
 /* Philox4x32-10.  ctr/key/out are plain uint32 words. */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
@@ -69,6 +69,9 @@ double orc_env_reward(int valid, const int32_t prev_board[16], const int32_t new
 int orc_env_simulate_move(const int32_t state[16], int action, int32_t highest_tile,
                           int32_t out_boards[30][16], double out_reward[30], int32_t out_done[30]);
 double orc_env_pattern(const int32_t board[16]);
+/* agents/hybrid.py:578-692: the hybrid agent's sampled one-move expansion */
+int orc_hybrid_simulate_move(const int32_t board[16], int action, uint64_t seed, uint32_t game, uint32_t call,
+                             uint32_t *draw, int32_t out_boards[6][16], double out_reward[6], int32_t out_done[6]);
 
 /* ---- beam-search agent (beam_search_agent.py) ---- */
 /* :194-258 incl. the DOWN quirk.  Returns valid flag. */

@@ -21,7 +21,7 @@ M0, M1 = 0xD2511F53, 0xCD9E8D57
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = 0xFFFFFFFF
 
-DOM_ENV, DOM_BEAM, DOM_ACTION, DOM_BOARD = 0, 1, 2, 3
+DOM_ENV, DOM_BEAM, DOM_ACTION, DOM_BOARD, DOM_HYBRID = 0, 1, 2, 3, 4
 TILE2_THRESHOLD = 3865470567  # ceil(0.9 * 2**32)
 
 
@@ -86,3 +86,12 @@ class StreamShim:
 
     def random(self):
         return self._next() / 4294967296.0
+
+    def sample(self, population, k):
+        """random.sample (agents/hybrid.py:622): partial Fisher-Yates, one draw per pick."""
+        pool = list(population)
+        n = len(pool)
+        for i in range(k):
+            j = i + ((self._next() * (n - i)) >> 32)
+            pool[i], pool[j] = pool[j], pool[i]
+        return pool[:k]

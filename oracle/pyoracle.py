@@ -65,6 +65,9 @@ def lib():
         L.orc_env_reward.restype = C.c_double
         L.orc_env_simulate_move.argtypes = [i32p, C.c_int, C.c_int32, C.POINTER(C.c_int32 * 16), C.POINTER(C.c_double), i32p]
         L.orc_env_simulate_move.restype = C.c_int
+        L.orc_hybrid_simulate_move.argtypes = [i32p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_int32 * 16), C.POINTER(C.c_double), i32p]
+        L.orc_hybrid_simulate_move.restype = C.c_int
         L.orc_env_pattern.argtypes = [i32p]
         L.orc_env_pattern.restype = C.c_double
         L.orc_agent_move.argtypes = [i32p, C.c_int, i32p, C.POINTER(C.c_int64)]
@@ -135,6 +138,13 @@ def env_simulate_move(board, action, highest_tile):
     ob = ((C.c_int32 * 16) * 30)(); rw = (C.c_double * 30)(); dn = (C.c_int32 * 30)()
     k = lib().orc_env_simulate_move(_b(board), action, int(highest_tile), ob, rw, dn)
     return [(np.array(ob[i], dtype=np.int32), rw[i], bool(dn[i])) for i in range(k)]
+
+
+def hybrid_simulate_move(board, action, seed, game, call, draw=0):
+    """-> (list of (int32[16], reward, done), draws consumed), agents/hybrid.py:578-692"""
+    ob = ((C.c_int32 * 16) * 6)(); rw = (C.c_double * 6)(); dn = (C.c_int32 * 6)(); d = C.c_uint32(draw)
+    k = lib().orc_hybrid_simulate_move(_b(board), action, seed, game, call, C.byref(d), ob, rw, dn)
+    return [(np.array(ob[i], dtype=np.int32), rw[i], bool(dn[i])) for i in range(k)], d.value - draw
 
 
 def env_pattern(board):

@@ -57,3 +57,29 @@ def load_ppo_agent_class():
             sys.modules.pop(k)
         sys.modules.update(saved)
     return mod.PPOAgent
+
+
+def load_hybrid_env_class(shim):
+    """agents/hybrid.py's private, monkey-patched copy of Game2048Env (hybrid.py:566-697) with the
+    module-level `random` := shim.  hybrid.py imports matplotlib at import time; it is not installed
+    here and plays no part on this path, so it is stubbed."""
+    from unittest import mock
+    if not available():
+        raise RuntimeError("reference tree not present")
+    sys.dont_write_bytecode = True
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k in ("environment", "agents") or k.startswith(("environment.", "agents."))}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            mod = importlib.import_module("agents.hybrid")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k in ("environment", "agents") or k.startswith(("environment.", "agents."))]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
+    mod.random = shim
+    return mod.Game2048Env

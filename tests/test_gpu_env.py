@@ -325,3 +325,31 @@ def test_cfg1_facade_one_board_random_legal_moves(orc):
         if done:
             break
     assert steps > 50 and env.game_over == done
+
+
+def test_hybrid_expand_vs_golden_and_oracle(orc, golden):
+    """SURVEY 8f row 4 (engine part): agents/hybrid.py's sampled expansion."""
+    from g2048_b200 import _lib
+    recs = [r for r in golden["hybrid_expand"] if max(r["board"]) <= 16384]
+    for r in recs:
+        b = np.array([G.pack_board(r["board"])], np.uint64); a = np.array([r["action"]], np.uint8)
+        nb = np.zeros(8, np.uint64); rw = np.zeros(8, np.float64); dn = np.zeros(8, np.uint8)
+        cnt = np.zeros(1, np.int32); used = np.zeros(1, np.uint32)
+        _lib.check(X.lib().g2048_host_hybrid_expand(X.P(b), X.P(a), None, r["call"], None, X.P(nb), X.P(rw), X.P(dn), X.P(cnt),
+                                                    X.P(used), 1, golden["seed"], r["game"]))
+        assert cnt[0] == len(r["outcomes"]) and used[0] == r["draws"]
+        for k, want in enumerate(r["outcomes"]):
+            assert nb[k] == G.pack_board(want["state"]) and rw[k] == float.fromhex(want["reward"]) and bool(dn[k]) == want["done"]
+    # batched, with per-item calls and draw offsets, against the oracle
+    vals, packed = X.synthetic(orc, 2000, SEED, 31337)
+    n = 2000
+    acts = (np.arange(n) % 4).astype(np.uint8); call = (np.arange(n) % 13).astype(np.uint32); d0 = (np.arange(n) % 7).astype(np.uint32)
+    nb = np.zeros((n, 8), np.uint64); rw = np.zeros((n, 8), np.float64); dn = np.zeros((n, 8), np.uint8)
+    cnt = np.zeros(n, np.int32); used = np.zeros(n, np.uint32)
+    _lib.check(X.lib().g2048_host_hybrid_expand(X.P(packed), X.P(acts), X.P(call), 0, X.P(d0), X.P(nb), X.P(rw), X.P(dn), X.P(cnt),
+                                                X.P(used), n, SEED, 31337))
+    for i in range(n):
+        want, draws = orc.hybrid_simulate_move(vals[i], int(acts[i]), SEED, 31337 + i, int(call[i]), draw=int(d0[i]))
+        assert cnt[i] == len(want) and used[i] == draws
+        for k, (s2, r2, d2) in enumerate(want):
+            assert nb[i, k] == G.pack_board(s2) and rw[i, k] == r2 and bool(dn[i, k]) == d2

@@ -103,3 +103,11 @@ def test_simulate_move_and_pattern(orc, golden):
             assert s.tolist() == want["state"] and r == float.fromhex(want["reward"]) and d == want["done"]
         if "pattern" in rec:
             assert orc.env_pattern(rec["board"]) == float.fromhex(rec["pattern"])
+
+
+def test_hybrid_expand(orc, golden):
+    for rec in golden["hybrid_expand"]:
+        outs, draws = orc.hybrid_simulate_move(rec["board"], rec["action"], golden["seed"], rec["game"], rec["call"])
+        assert draws == rec["draws"] and len(outs) == len(rec["outcomes"])
+        for (s, r, d), want in zip(outs, rec["outcomes"]):
+            assert s.tolist() == want["state"] and r == float.fromhex(want["reward"]) and d == want["done"]

@@ -116,3 +116,18 @@ def test_cfg1_one_board_random_legal_moves(orc, ref):
         if done:
             break
     assert steps > 50
+
+
+def test_hybrid_simulate_move_vs_reference(orc):
+    shim = P.StreamShim(SEED)
+    HEnv = R.load_hybrid_env_class(shim)
+    env = HEnv.__new__(HEnv); env.size = 4
+    for g in range(250):
+        b = orc.synthetic_board(SEED, 8000 + g)
+        for a in range(4):
+            shim.select(P.DOM_HYBRID, g, 9, 4)
+            outs = env.simulate_move(b.reshape(4, 4).copy(), a)
+            want, draws = orc.hybrid_simulate_move(b, a, SEED, g, 9, draw=4)
+            assert len(outs) == len(want) and shim.draw - 4 == draws
+            for (s1, r1, d1), (s2, r2, d2) in zip(outs, want):
+                assert (np.asarray(s1).flatten() == s2).all() and float(r1) == r2 and bool(d1) == d2
