@@ -269,8 +269,8 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n * env_steps * args.steps / e2e_s
     # one env.step per call with host buffers (the reference's call granularity, batched)
-    ha = np.random.default_rng(0).integers(0, 4, n).astype(np.uint8)
-    hrw = np.zeros(n, np.float64); hv = np.zeros(n, np.uint8); hl = np.zeros(n, np.uint8); hd = np.zeros(n, np.uint8)
+    ha = pin(torch.uint8); ha[:] = np.random.default_rng(0).integers(0, 4, n).astype(np.uint8)
+    hrw = pin(torch.float64); hv = pin(torch.uint8); hl = pin(torch.uint8); hd = pin(torch.uint8)
     for _ in range(3):
         _lib.check(lib.g2048_host_env_step(P(hb), P(ha), None, P(hs), P(hh), P(hc), P(hrw), None, P(hv), P(hl), P(hd), n, SEED, rank * n))
     t0 = time.perf_counter()
