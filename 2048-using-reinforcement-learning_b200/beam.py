@@ -111,16 +111,22 @@ class BatchedBeamSearch:
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
-    def get_actions(self, boards, legal=None, call=0, game0=0):
+    def new_outputs(self, g):
+        t = self.torch
+        return dict(action=t.empty(g, dtype=t.uint8, device=self.device),
+                    prob=t.empty(g, dtype=t.float32, device=self.device),
+                    best_score=t.empty(g, dtype=t.float64, device=self.device),
+                    nodes=t.empty(g, dtype=t.int32, device=self.device))
+
+    def get_actions(self, boards, legal=None, call=0, game0=0, out=None):
         """boards: int64[G] packed (device).  legal: None or uint8[G] masks.  call: int or int32[G].
+        out: optional dict from `new_outputs(G)` to write into (no allocation on the call path).
 
         Returns dict(action uint8[G], prob float32[G], best_score float64[G], nodes int32[G])."""
         t = self.torch
         g = boards.numel()
-        out = dict(action=t.empty(g, dtype=t.uint8, device=self.device),
-                   prob=t.empty(g, dtype=t.float32, device=self.device),
-                   best_score=t.empty(g, dtype=t.float64, device=self.device),
-                   nodes=t.empty(g, dtype=t.int32, device=self.device))
+        if out is None:
+            out = self.new_outputs(g)
         call_ptr, call0 = (call.contiguous().data_ptr(), 0) if t.is_tensor(call) else (0, int(call))
         _lib.check(_lib.use_device(self.index).g2048_beam_search(
             boards.contiguous().data_ptr(), 0 if legal is None else legal.contiguous().data_ptr(), call_ptr, call0,

@@ -38,6 +38,7 @@ BYTES_PER_STEP = 22          # 8 rd board + 1 rd action + 8 wr boar
 BYTES_PER_NODE = 21          # 8 rd parent + 8 wr child + 4 wr score + 1 wr first action
 SEED = 1234
 BEAM_W, BEAM_D, BEAM_ROOTS = 20, 40, 10000
+SLEEP_CYCLES = 1_000_000     # torch.cuda._sleep before each timed launch (see run_ours)
 # From the committed ncu capture of the same command (profiles/ncu_summary_r01.md): executed warp
 # instructions per warp-step of env_rollout_kernel, its DRAM traffic per launch, and pipe utilisation.
 NCU_ROLLOUT = {"warp_inst_per_warp_step": 431.4, "dram_bytes_per_launch": 2150144, "alu_pipe_pct_of_peak": 65.1,
@@ -210,14 +211,15 @@ def run_ours(args):
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                                          # evict L2 between timed iterations
-        starts[i].record()
+        torch.cuda._sleep(SLEEP_CYCLES)                                # GPU idles ~0.5 ms so the host is always ahead:
+        starts[i].record()                                             # no enqueue latency between the two events
         env.rollout(env_steps)
         ends[i].record()
     barrier()
     wall = time.perf_counter() - wall0
     launches = G.launch_count() - launches0
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    dev_ms = max_over_ranks(dev_ms)
+    step_times = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    dev_ms = max_over_ranks(sum(step_times))
     value = world * n * env_steps * args.steps / (dev_ms * 1e-3)
     kernel_ms = dev_ms / args.steps
 
@@ -289,14 +291,16 @@ def run_ours(args):
     bs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     be = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     nodes_total = 0
-    outs = []
+    outs = [search.new_outputs(args.beam_roots) for _ in range(args.steps)]     # no allocation inside the timed region
     for i in range(args.steps):
         flush.fill_(i & 0xFF)
+        torch.cuda._sleep(SLEEP_CYCLES)
         bs[i].record()
-        outs.append(search.get_actions(roots, call=100 + i, game0=rank * args.beam_roots))
+        search.get_actions(roots, call=100 + i, game0=rank * args.beam_roots, out=outs[i])
         be[i].record()
     barrier()
-    beam_ms = max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(bs, be)))
+    beam_times = [s.elapsed_time(e) for s, e in zip(bs, be)]
+    beam_ms = max_over_ranks(sum(beam_times))
     nodes_total = sum(int(o["nodes"].sum().item()) for o in outs)
     if world > 1:
         t = torch.tensor([nodes_total], dtype=torch.int64, device=dev)
@@ -347,7 +351,7 @@ def run_ours(args):
                    "envs_per_gpu": n, "env_steps": env_steps, "seed": SEED,
                    "l2": "flushed between timed iterations (256 MiB write); the 512 KiB working set is re-read from HBM",
                    "timing": "CUDA events around each rollout launch on the launching stream, max over ranks",
-                   "wall_s_bracket": wall},
+                   "wall_s_bracket": wall, "ms_min_max": [min(step_times), max(step_times)]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "g2048_host_env_rollout (pinned host state in/out per call)",
                 "per_env_step_call": {"value": e2e_step_value, "unit": UNIT,
@@ -370,7 +374,8 @@ def run_ours(args):
                                         "note": "64 x (g2048_env_step + g2048_env_reset_done) captured in one CUDA graph"}},
         "beam": {"metric": "beam-search nodes/sec (BeamSearchAgent.get_action, width 20 depth 40)", "value": beam_value,
                  "unit": "nodes/s", "roots_per_gpu": args.beam_roots, "nodes_per_step": nodes_total // max(1, args.steps),
-                 "ms_per_step": beam_ms / args.steps, "e2e": {"value": beam_e2e, "unit": "nodes/s", "api": "g2048_host_beam_search"},
+                 "ms_per_step": beam_ms / args.steps, "ms_min_max": [min(beam_times), max(beam_times)],
+                 "e2e": {"value": beam_e2e, "unit": "nodes/s", "api": "g2048_host_beam_search"},
                  "roofline": {"bound": "hbm", "achieved": beam_achieved, "peak": peak, "unit": "GB/s",
                               "frac": beam_achieved / peak, "traffic": NCU_BEAM["dram_bytes_per_launch"],
                               "kernel": "beam_search_kernel", "ncu": NCU_BEAM},
