@@ -35,6 +35,23 @@ def best_games(scores, k=5):
     return best
 
 
+GAME_KEYS = ("score", "highest_exp", "moves", "valid", "invalid", "milestone")
+
+
+def gather_games(host, group=None):
+    """Per-rank per-game arrays (each rank holds the contiguous game-id range of `shard_range`) ->
+    the full arrays in global game order on rank 0; other ranks keep their shard.  No-op without
+    torch.distributed."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return host
+    gathered = [None] * dist.get_world_size(group)
+    dist.all_gather_object(gathered, host, group=group)
+    if dist.get_rank(group) == 0:
+        return {k: np.concatenate([g[k] for g in gathered]) for k in host}
+    return host
+
+
 def compile_results(score, highest_exp, moves, valid, invalid, milestone, beam_width, search_depth):
     """Per-game arrays (host) -> the reference's `results` dict (evaluate_beam_search.py:127-135)."""
     score = [int(v) for v in score]
@@ -87,13 +104,7 @@ def run_evaluation(num_games=1000, beam_width=15, search_depth=20, render_freq=N
     search = BatchedBeamSearch(beam_width, search_depth, device, seed=seed)
     out = search.play_games(hi - lo, max_moves=max_moves, game0=lo)
     stats = all_reduce_stats(out["stats"])
-    keys = ("score", "highest_exp", "moves", "valid", "invalid", "milestone")
-    host = {k: out[k].cpu().numpy() for k in keys}
-    if distributed:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, host)
-        if rank == 0:
-            host = {k: np.concatenate([g[k] for g in gathered]) for k in keys}
+    host = gather_games({k: out[k].cpu().numpy() for k in GAME_KEYS})
     results = compile_results(host["score"], host["highest_exp"], host["moves"], host["valid"], host["invalid"],
                               host["milestone"], beam_width, search_depth)
     results["parameters"]["num_games"] = num_games

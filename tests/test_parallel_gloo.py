@@ -60,6 +60,40 @@ def test_stats_all_reduce_world2():
     assert d["games"] == total and d["max_score"] == int(score.max())
 
 
+def _gather_main(rank, world, port, total, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from g2048_b200.evaluation import gather_games, compile_results
+    lo, hi = G.shard_range(total, rank, world)
+    g = np.arange(lo, hi)
+    ms = -np.ones((hi - lo, 8), np.int32); ms[:, 0] = g
+    host = gather_games({"score": (g * 3).astype(np.int32), "highest_exp": (g % 9 + 3).astype(np.uint8),
+                         "moves": (g + 100).astype(np.int32), "valid": g.astype(np.int32), "invalid": (g % 5).astype(np.int32),
+                         "milestone": ms})
+    if rank == 0:
+        res = compile_results(host["score"], host["highest_exp"], host["moves"], host["valid"], host["invalid"],
+                              host["milestone"], 20, 40)
+        out.put((res["scores"], res["milestones"][64], res["best_games"]))
+    dist.destroy_process_group()
+
+
+def test_sharded_games_gather_in_global_order_world3():
+    total, world = 50, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_main, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    scores, ms64, best = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert scores == [3 * g for g in range(total)] and ms64 == list(range(total))
+    assert best == [49, 48, 47, 46, 45]
+
+
 def test_single_process_all_reduce_is_identity():
     s = torch.arange(_lib.STATS_LEN, dtype=torch.int64)
     assert torch.equal(G.all_reduce_stats(s.clone()), s)
