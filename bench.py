@@ -119,13 +119,14 @@ def oracle_env_state(O, n, seed, game0):
     return boards, score, hi, ctr
 
 
-def cpu_env_sample(O, n, steps, threads):
+def cpu_env_sample(O, n, steps, threads, return_seconds=False):
     """Board-steps/s of the oracle on `threads` host threads over n envs x steps (same workload, smaller)."""
     st = oracle_env_state(O, n, SEED, 0)
     rs = np.zeros(n, np.float64); ep = np.zeros(n, np.int32)
     t = time.perf_counter()
     O.rollout(st[0], st[1], st[2], st[3], rs, ep, steps, 0, SEED, 0, threads)
-    return n * steps / (time.perf_counter() - t)
+    dt = time.perf_counter() - t
+    return (n * steps / dt) if not return_seconds else dt
 
 
 def cpu_beam_sample(O, roots, threads):
@@ -146,10 +147,9 @@ def run_reference(args):
     n, steps = 16384, 200                     # bounded sample of the 65,536 x 2,000 workload per step
     for _ in range(args.warmup):
         cpu_env_sample(O, n, 10, threads)
-    t = time.perf_counter()
+    dt = 0.0                                  # the rollout itself; building the initial states is not timed
     for _ in range(args.steps):
-        cpu_env_sample(O, n, steps, threads)
-    dt = time.perf_counter() - t
+        dt += cpu_env_sample(O, n, steps, threads, return_seconds=True)
     value = n * steps * args.steps / dt
     sample = f"{n} envs x {steps} steps per bench step (oracle/orc2048.c, pthreads)"
     print(json.dumps({
