@@ -140,20 +140,34 @@ __device__ __forceinline__ uint32_t spawn_and_score(int c, int n_valid, uint32_t
     return active ? key : 0u;
 }
 
-// two independent 32-key sorts in lockstep (same network, twice the ILP)
-__device__ __forceinline__ void sort_desc32_x2(uint32_t &a, uint32_t &b, uint32_t lane)
+// kRows independent 32-key sorts in lockstep: same network, kRows exchanges per stage that do not
+// depend on one another, so a lone warp hides the shuffle latency of one behind the others.
+template <int kRows>
+__device__ __forceinline__ void sort_desc32_rows(uint32_t (&k)[4], uint32_t lane)
 {
 #pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-        bool lower = (lane & (k >> 1)) == 0;
-        a = exchange(a, k - 1, lower);
-        b = exchange(b, k - 1, lower);
+    for (int blk = 2; blk <= 32; blk <<= 1) {
+        bool lower = (lane & (blk >> 1)) == 0;
 #pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
+        for (int r = 0; r < kRows; ++r) k[r] = exchange(k[r], blk - 1, lower);
+#pragma unroll
+        for (int j = blk >> 2; j > 0; j >>= 1) {
             lower = (lane & j) == 0;
-            a = exchange(a, j, lower);
-            b = exchange(b, j, lower);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) k[r] = exchange(k[r], j, lower);
         }
+    }
+}
+// top-32 of (a0 U b0) and of (a1 U b1) in lockstep
+__device__ __forceinline__ void merge_top32_x2(uint32_t &a0, uint32_t b0, uint32_t &a1, uint32_t b1, uint32_t lane)
+{
+    a0 = max(a0, __shfl_sync(FULL, b0, 31 - lane));
+    a1 = max(a1, __shfl_sync(FULL, b1, 31 - lane));
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const bool lower = (lane & j) == 0;
+        a0 = exchange(a0, j, lower);
+        a1 = exchange(a1, j, lower);
     }
 }
 
@@ -283,15 +297,16 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         // ---- C: stable top-k ------------------------------------------------------------------------
         nb = min(P.width, n_valid);                                     // agent:132,175
         uint32_t top = 0u;
-        if (n_valid > 32) {
-            sort_desc32_x2(key[0], key[1], lane);
+        if (n_valid > 96) {
+            sort_desc32_rows<4>(key, lane);
+            merge_top32_x2(key[0], key[1], key[2], key[3], lane);
+            top = merge_top32(key[0], key[2], lane);
+        } else if (n_valid > 64) {
+            sort_desc32_rows<3>(key, lane);
+            top = merge_top32(merge_top32(key[0], key[1], lane), key[2], lane);
+        } else if (n_valid > 32) {
+            sort_desc32_rows<2>(key, lane);
             top = merge_top32(key[0], key[1], lane);
-            if (n_valid > 96) {
-                sort_desc32_x2(key[2], key[3], lane);
-                top = merge_top32(top, merge_top32(key[2], key[3], lane), lane);
-            } else if (n_valid > 64) {
-                top = merge_top32(top, sort_desc32(key[2], lane), lane);
-            }
         } else {
             top = sort_desc32(key[0], lane);
         }
