@@ -58,6 +58,7 @@ _SIGNATURES = {
     "g2048_synthetic_boards": ([_vp, _i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_reset": ([_vp, _vp, _vp, _vp, _i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_reset_done": ([_vp] * 6 + [_i64, _u64, _u32, _vp], C.c_int),
+    "g2048_env_step_autoreset": ([_vp] * 12 + [_i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_step": ([_vp] * 12 + [_i64, _u64, _u32, _vp], C.c_int),
     "g2048_legal_masks": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "g2048_env_rollout": ([_vp] * 6 + [_i64, _i32, _u32, _u64, _u32, _vp], C.c_int),

@@ -55,7 +55,10 @@ DeviceState *current_device_state()
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-constexpr int kEnvThreads = 256;
+#ifndef G2048_ENV_THREADS
+#define G2048_ENV_THREADS 256
+#endif
+constexpr int kEnvThreads = G2048_ENV_THREADS;
 constexpr int kEnvSharedThreads = 512;   // one 192 KiB block per SM
 
 // Both row tables into dynamic shared memory (192 KiB) by TMA bulk copy (stage.cuh).
@@ -70,6 +73,7 @@ struct StepArgs {
     double *reward; float *reward32; int32_t *score_delta; uint8_t *valid; uint8_t *legal; uint8_t *done;
     int64_t n; PhiloxKey K; uint32_t game0;
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
+    int32_t *episodes;             // non-null: reset an env right after the step that ended its game
 };
 
 // Game2048Env.step for n envs, one env per thread, one launch per step.
@@ -97,6 +101,10 @@ __global__ void __launch_bounds__(kThreads) env_step_kernel(StepArgs a)
         StepResult r = want_reward
             ? env_step<kShared, kShared, true>(s, action, row, code, a.K, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow)
             : env_step<kShared, kShared, false>(s, action, row, code, a.K, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow);
+        if (a.episodes && r.done) {                       // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
+            env_reset(s, a.K, a.game0 + (uint32_t)i);
+            a.episodes[i] += 1;
+        }
         a.boards[i] = s.board.u64();
         if (a.score) a.score[i] = s.score;
         if (a.highest) a.highest[i] = (uint8_t)s.highest;
@@ -667,6 +675,23 @@ int g2048_env_reset_done(uint64_t *boards, int32_t *score, uint8_t *highest_exp,
     G2048_LAUNCHED();
 }
 
+// set by g2048_env_step_autoreset around its call of g2048_env_step (same thread)
+static thread_local int32_t *g_step_episodes = nullptr;
+
+int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
+                             int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                             double *reward, float *reward32, int32_t *score_delta,
+                             uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
+                             int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    if (!episodes || !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_autoreset: episodes and spawn_ctr are required");
+    g_step_episodes = episodes;
+    int rc = g2048_env_step(boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta, valid, legal,
+                            done, n, seed, game0, stream);
+    g_step_episodes = nullptr;
+    return rc;
+}
+
 int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
                    int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
                    double *reward, float *reward32, int32_t *score_delta,
@@ -675,11 +700,11 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
 {
     G2048_ENTER(boards && actions);
     StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, make_philox_key(seed), game0, st->row, st->code, st->overflow};
+               valid, legal, done, n, make_philox_key(seed), game0, st->row, st->code, st->overflow, g_step_episodes};
     if (use_shared_tables(n, st->sm_count)) {
         env_step_kernel<true, kEnvSharedThreads><<<st->sm_count, kEnvSharedThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
     } else {
-        env_step_kernel<false, kEnvThreads><<<grid_for(n, kEnvThreads, st->sm_count, 8), kEnvThreads, 0, s>>>(a);
+        env_step_kernel<false, kEnvThreads><<<grid_for(n, kEnvThreads, st->sm_count, 16), kEnvThreads, 0, s>>>(a);
     }
     G2048_LAUNCHED();
 }

@@ -207,13 +207,14 @@ class BatchedGame2048Env:
         if highest_exp is not None:
             self.highest_exp.copy_(t.as_tensor(highest_exp, dtype=t.uint8).to(self.device))
 
-    def step(self, actions, inject=None, want_reward=True):
+    def step(self, actions, inject=None, want_reward=True, auto_reset=False):
         """Game2048Env.step for every env.  actions: uint8[N] device tensor (0..3).
 
         Returns (boards, reward float64[N], done uint8[N], info) with info = dict(score, valid_move,
         highest_exp, legal_mask, score_delta, reward32); all are views of internal device tensors
         that the next call overwrites.  Only kernel launches on the current stream: the call is
-        CUDA-graph capturable (see `graph`).
+        CUDA-graph capturable (see `graph`).  auto_reset=True also resets, in the same launch, the
+        envs whose game this step ended (`done` still flags them; `episodes` counts them).
         """
         t = self.torch
         if actions.dtype != t.uint8:
@@ -222,6 +223,15 @@ class BatchedGame2048Env:
             actions = actions.contiguous()
         inj = 0 if inject is None else inject.contiguous().data_ptr()
         p = self._ptrs
+        if auto_reset:
+            rc = self._use().g2048_env_step_autoreset(
+                p["boards"], actions.data_ptr(), p["score"], p["highest_exp"], p["spawn_ctr"],
+                p["reward"] if want_reward else 0, p["reward32"] if want_reward else 0, p["score_delta"], p["valid"],
+                p["legal"], p["done"], p["episodes"], self.n, self.seed, self.game0, self._stream())
+            if rc:
+                _lib.check(rc)
+            self.t += 1
+            return self.boards, self.reward, self.done, self._info
         rc = self._use().g2048_env_step(
             p["boards"], actions.data_ptr(), inj, p["score"], p["highest_exp"], p["spawn_ctr"],
             p["reward"] if want_reward else 0, p["reward32"] if want_reward else 0, p["score_delta"], p["valid"],

@@ -239,8 +239,7 @@ def run_ours(args):
     # the same 64 per-step launches replayed as one CUDA graph (what a PPO loop would do)
     def sixty_four_steps():
         for i in range(64):
-            env.step(acts[i])
-            env.reset_done()
+            env.step(acts[i], auto_reset=True)
     graph = env.graph(sixty_four_steps)
     graph.replay()
     barrier()
@@ -371,7 +370,7 @@ def run_ours(args):
         "per_step_api": {"value": per_step_api_value, "unit": UNIT,
                          "note": "g2048_env_step, one launch per env step, device-resident tensors",
                          "cuda_graph": {"value": per_step_graph_value, "unit": UNIT,
-                                        "note": "64 x (g2048_env_step + g2048_env_reset_done) captured in one CUDA graph"}},
+                                        "note": "64 x g2048_env_step_autoreset (step + reset of finished envs) captured in one CUDA graph"}},
         "beam": {"metric": "beam-search nodes/sec (BeamSearchAgent.get_action, width 20 depth 40)", "value": beam_value,
                  "unit": "nodes/s", "roots_per_gpu": args.beam_roots, "nodes_per_step": nodes_total // max(1, args.steps),
                  "ms_per_step": beam_ms / args.steps, "ms_min_max": [min(beam_times), max(beam_times)],

@@ -116,6 +116,16 @@ int g2048_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const ui
 /* Game2048Env._evaluate_pattern (env:313-339): max(snake, corner weighted tile sums) / 100. */
 int g2048_evaluate_pattern(const uint64_t *boards, double *pattern, int64_t n, void *stream);
 
+/* g2048_env_step followed, for the envs whose game just ended, by Game2048Env.reset -- the
+ * `if done: state = env.reset()` of every training loop (train.py:49,107), in the same launch.
+ * done[i] still reports the end of the old game; boards/score/highest/legal describe the fresh one;
+ * episodes[i] += 1.  spawn_ctr and episodes are required. */
+int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
+                             int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                             double *reward, float *reward32, int32_t *score_delta,
+                             uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
+                             int64_t n, uint64_t seed, uint32_t game0, void *stream);
+
 /* Game2048Env.get_valid_moves (env:69-95) -> env_legal; BeamSearchAgent._check_valid_moves
  * (agent:183-192, DOWN quirk included) -> agent_legal.  Bit a = action a.  Either may be NULL. */
 int g2048_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal,

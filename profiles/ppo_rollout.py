@@ -55,11 +55,9 @@ def main():
                 actions = torch.distributions.Categorical(logits=logits).sample().to(torch.uint8)
             else:
                 actions = torch.randint(0, 4, (n,), device=dev, dtype=torch.uint8)
-            _, _, done, info = env.step(actions)
+            _, _, done, info = env.step(actions, auto_reset=True)           # step + `if done: env.reset()` in one launch
             rew_buf[t] = info["reward32"]
-            legal = info["legal_mask"]
-            env.reset_done()                                                  # harness-side `if done: env.reset()`, on device
-            legal = env.legal_masks()
+            legal = info["legal_mask"]                                        # of the (possibly fresh) board
         return obs_buf, rew_buf
 
     out = {"envs": n, "steps": steps}
@@ -76,8 +74,7 @@ def main():
 
     def env_side():
         obs_static.copy_(env.observe())
-        env.step(acts)
-        env.reset_done()
+        env.step(acts, auto_reset=True)
 
     graph = env.graph(env_side)
     for _ in range(10):

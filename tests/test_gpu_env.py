@@ -353,3 +353,20 @@ def test_hybrid_expand_vs_golden_and_oracle(orc, golden):
         assert cnt[i] == len(want) and used[i] == draws
         for k, (s2, r2, d2) in enumerate(want):
             assert nb[i, k] == G.pack_board(s2) and rw[i, k] == r2 and bool(dn[i, k]) == d2
+
+
+def test_step_autoreset_equals_step_then_reset_done():
+    import torch
+    n = 6000
+    a_env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=9); a_env.reset()
+    b_env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=9); b_env.reset()
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for t in range(300):
+        act = torch.randint(0, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+        a_env.step(act, auto_reset=True)
+        b_env.step(act); b_env.reset_done()
+        assert torch.equal(a_env.boards, b_env.boards) and torch.equal(a_env.done, b_env.done)
+        assert torch.equal(a_env.reward, b_env.reward) and torch.equal(a_env.score, b_env.score)
+    assert torch.equal(a_env.episodes, b_env.episodes) and int(a_env.episodes.sum()) > 0
+    assert torch.equal(a_env.spawn_ctr, b_env.spawn_ctr) and torch.equal(a_env.highest_exp, b_env.highest_exp)
+    assert torch.equal(a_env.legal, b_env.legal_masks())
