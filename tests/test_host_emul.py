@@ -237,3 +237,26 @@ def test_ppo_features_bit_exact(emul, orc):
         p = packing.pack_board(b)
         assert emul.emul_ppo_heuristic(p) == orc.ppo_heuristic(b), b
         assert emul.emul_ppo_top4(p) == orc.ppo_top4_bonus(b), b
+
+
+def test_row_tables_exhaustively_against_oracle(emul, orc):
+    """All 65,536 entries of both row tables (csrc/row_tables.h) against the oracle's row kernel."""
+    import ctypes as C
+    L = orc.lib()
+    board = (C.c_int32 * 16)()
+    checked = 0
+    for r in range(65536):
+        e = [(r >> (4 * j)) & 15 for j in range(4)]
+        for i in range(16):
+            board[i] = 0
+        for j in range(4):
+            board[4 + j] = (1 << e[j]) if e[j] else 0
+        score = L.orc_env_move(board, 0)
+        out = [board[4 + j] for j in range(4)]
+        got = emul.emul_row(r)
+        want = [min(v.bit_length() - 1, 15) if v else 0 for v in out]          # 65536 saturates the nibble
+        assert [(got >> (4 * j)) & 15 for j in range(4)] == want, r
+        code = emul.emul_code(r)
+        assert sum((2 << ((code >> s) & 15)) & ~3 for s in (0, 4)) == score, r
+        checked += 1
+    assert checked == 65536
