@@ -451,12 +451,14 @@ __device__ __forceinline__ void ordered_pairs(Board b, int line[4])
 // ordered_pairs() with the occupancy flags (bit 0 of every non-empty nibble) already known
 __device__ __forceinline__ void ordered_pairs_flags(Board b, uint32_t nzl, uint32_t nzh, int line[4])
 {
+    // "both cells non-empty and next >= previous" == "previous non-empty and next >= previous"
+    // (next >= previous >= 1 already makes next non-empty), so only the first cell's occupancy masks
     const uint32_t nl = nzl << 3, nh = nzh << 3;
-    uint32_t hl = ge_flags(b.lo >> 4, b.lo) & nl & (nl >> 4) & 0x08880888u;
-    uint32_t hh = ge_flags(b.hi >> 4, b.hi) & nh & (nh >> 4) & 0x08880888u;
-    uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16), nbl = __funnelshift_r(nl, nh, 16);
-    uint32_t vl = ge_flags(below_lo, b.lo) & nl & nbl;
-    uint32_t vh = ge_flags(b.hi >> 16, b.hi) & nh & (nh >> 16) & 0x00008888u;
+    uint32_t hl = ge_flags(b.lo >> 4, b.lo) & nl & 0x08880888u;
+    uint32_t hh = ge_flags(b.hi >> 4, b.hi) & nh & 0x08880888u;
+    uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16);
+    uint32_t vl = ge_flags(below_lo, b.lo) & nl;
+    uint32_t vh = ge_flags(b.hi >> 16, b.hi) & nh & 0x00008888u;
     uint32_t v = vl | (vh << 1);
     line[0] = __popc(hl & 0x0000FFFFu) + __popc(v & 0x00080018u);
     line[1] = __popc(hl & 0xFFFF0000u) + __popc(v & 0x00800180u);
