@@ -560,9 +560,11 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
                BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                game0, st->row, next_work_counter(st)};
     G2048_CUDA(cudaMemsetAsync(a.work, 0, sizeof(unsigned int), stream));
-    int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
-    int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
-    beam_search_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
+    // one block per SM; a small batch gets fewer warps per block so that it is spread over all SMs
+    int grid = (int)(n < st->sm_count ? n : st->sm_count);
+    int64_t warps = (n + grid - 1) / grid;
+    int threads = 32 * (int)(warps < kBeamWarps ? warps : kBeamWarps);
+    beam_search_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a);
     count_launch();
     return check_cuda(cudaGetLastError(), "beam_search_kernel");
 }
@@ -587,9 +589,10 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
                 st->row, st->code, st->overflow, work, pending, pending_count};
-    int64_t blocks = (n + kBeamWarps - 1) / kBeamWarps;
-    int grid = (int)(blocks < st->sm_count ? blocks : st->sm_count);
-    play_games_kernel<<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
+    int grid = (int)(n < st->sm_count ? n : st->sm_count);          // spread small runs over all SMs (see beam search)
+    int64_t warps = (n + grid - 1) / grid;
+    int threads = 32 * (int)(warps < kBeamWarps ? warps : kBeamWarps);
+    play_games_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a);
     count_launch();
     G2048_CUDA(cudaGetLastError());
     // stalled games: kSpecWarps warps each (how many there are is only known on the device, so the
