@@ -493,8 +493,12 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
         s.board = Board(gs.board); s.score = gs.score; s.highest = gs.highest; s.spawn_ctr = gs.spawn_ctr;
         bool done = false;
         int buf = 0;
+        // speculation width: the game arrives inside a stall (full width); after a valid move the next
+        // call most likely is valid too, so only one warp searches (no contention, no wasted searches)
+        // and the width doubles again with every round that finds no valid move
+        int width = kSpecWarps;
         while (!done && gs.moves < a.max_moves) {
-            const int allowed = min(kSpecWarps, a.max_moves - gs.moves);
+            const int allowed = min(width, a.max_moves - gs.moves);
             if (w < allowed) {
                 BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(gs.moves + w), row, ws);
                 if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
@@ -518,6 +522,9 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
                     if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
                 ++gs.valid;
                 ++gs.moves;
+                width = 1;
+            } else {
+                width = min(kSpecWarps, 2 * width);
             }
             buf ^= 1;
         }
