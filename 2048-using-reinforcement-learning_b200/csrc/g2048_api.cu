@@ -675,21 +675,21 @@ int g2048_env_reset_done(uint64_t *boards, int32_t *score, uint8_t *highest_exp,
     G2048_LAUNCHED();
 }
 
-// set by g2048_env_step_autoreset around its call of g2048_env_step (same thread)
-static thread_local int32_t *g_step_episodes = nullptr;
-
-int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
-                             int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
-                             double *reward, float *reward32, int32_t *score_delta,
-                             uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
-                             int64_t n, uint64_t seed, uint32_t game0, void *stream)
+static int env_step_launch(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
+                           int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                           double *reward, float *reward32, int32_t *score_delta,
+                           uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
+                           int64_t n, uint64_t seed, uint32_t game0, void *stream)
 {
-    if (!episodes || !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_autoreset: episodes and spawn_ctr are required");
-    g_step_episodes = episodes;
-    int rc = g2048_env_step(boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta, valid, legal,
-                            done, n, seed, game0, stream);
-    g_step_episodes = nullptr;
-    return rc;
+    G2048_ENTER(boards && actions);
+    StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
+               valid, legal, done, n, make_philox_key(seed), game0, st->row, st->code, st->overflow, episodes};
+    if (use_shared_tables(n, st->sm_count)) {
+        env_step_kernel<true, kEnvSharedThreads><<<st->sm_count, kEnvSharedThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
+    } else {
+        env_step_kernel<false, kEnvThreads><<<grid_for(n, kEnvThreads, st->sm_count, 16), kEnvThreads, 0, s>>>(a);
+    }
+    G2048_LAUNCHED();
 }
 
 int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
@@ -698,15 +698,19 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
                    uint8_t *valid, uint8_t *legal, uint8_t *done,
                    int64_t n, uint64_t seed, uint32_t game0, void *stream)
 {
-    G2048_ENTER(boards && actions);
-    StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, make_philox_key(seed), game0, st->row, st->code, st->overflow, g_step_episodes};
-    if (use_shared_tables(n, st->sm_count)) {
-        env_step_kernel<true, kEnvSharedThreads><<<st->sm_count, kEnvSharedThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
-    } else {
-        env_step_kernel<false, kEnvThreads><<<grid_for(n, kEnvThreads, st->sm_count, 16), kEnvThreads, 0, s>>>(a);
-    }
-    G2048_LAUNCHED();
+    return env_step_launch(boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta, valid,
+                           legal, done, nullptr, n, seed, game0, stream);
+}
+
+int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
+                             int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                             double *reward, float *reward32, int32_t *score_delta,
+                             uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
+                             int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    if (!episodes || !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_autoreset: episodes and spawn_ctr are required");
+    return env_step_launch(boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta, valid, legal,
+                           done, episodes, n, seed, game0, stream);
 }
 
 int g2048_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n, void *stream)

@@ -104,3 +104,18 @@ def test_dropin_module_paths_resolve_to_the_engine():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "dropin"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_plain_c_client_links_against_the_abi(built, tmp_path):
+    """examples/abi_client.c: gcc only (no CUDA headers); without a GPU it must fail loudly with ENODEVICE."""
+    import subprocess, torch
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.dirname(built.LIB_PATH)
+    subprocess.run(["gcc", os.path.join(ROOT, "examples", "abi_client.c"), "-I", os.path.join(ROOT, "include"),
+                    "-L", libdir, "-l:libg2048.so", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert "libg2048 ABI version 1" in out.stdout
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and out.stdout.count("score") == 4, out.stdout
+    else:
+        assert out.returncode == 3 and "no CUDA device" in out.stdout, out.stdout
