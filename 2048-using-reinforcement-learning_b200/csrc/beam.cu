@@ -29,7 +29,7 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 struct __align__(16) WarpScratch {
     uint64_t cand[kMaxCand];     // children of this level, generation order
     double score[kMaxCand];      // float64 scores of the full-evaluation levels
-    uint8_t first[kMaxCand];     // first action of the path each child belongs to
+    uint8_t first[kMaxCand];     // bits 0-1: first action of the child's path; bits 2-5: its largest exponent
 };
 constexpr size_t kBeamSmemBytes = kRowTableBytes + kBeamWarps * sizeof(WarpScratch);
 
@@ -92,7 +92,6 @@ __device__ __forceinline__ void agent_children(Board b, const uint16_t *row, Boa
 }
 
 __device__ __forceinline__ int tile_value(uint32_t e) { return e ? (1 << e) : 0; }
-
 
 // Phase B for candidate c of this level: spawn (agent:155), evaluate (agent:158-161), sort key.
 // Branch-free on purpose (the Philox block is computed for every lane and masked by `draws`) so that
