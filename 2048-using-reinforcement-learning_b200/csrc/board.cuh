@@ -487,7 +487,7 @@ __device__ __forceinline__ double shaped_reward_tracked(bool valid, int empty_be
     float inner = pow2_sum(cur.hi, 0x00000110u, pow2_sum(cur.lo, 0x01100000u, 0.0f));
     float corners = pow2_sum(cur.hi, 0x10010000u, pow2_sum(cur.lo, 0x00001001u, 0.0f));
     uint32_t edge = total - (uint32_t)inner + (uint32_t)corners;
-    reward = __dadd_rn(reward, __dmul_rn(__ddiv_rn((double)edge, (double)total), 1.0));
+    reward = __dadd_rn(reward, __ddiv_rn((double)edge, (double)total));      // `* 1.0` (env:259) is the identity in IEEE-754
     if (empty_after <= 2) reward = __dadd_rn(reward, -2.0);
     int line[4];
     ordered_pairs_flags(cur, nzl, nzh, line);
@@ -515,7 +515,7 @@ __device__ __forceinline__ double shaped_reward(bool valid, int empty_before, Bo
     uint32_t inner = tile_sum_half(cur.lo, 0x01100000u) + tile_sum_half(cur.hi, 0x00000110u);
     uint32_t corners = tile_sum_half(cur.lo, 0x00001001u) + tile_sum_half(cur.hi, 0x10010000u);
     uint32_t edge = total - inner + corners;
-    reward = __dadd_rn(reward, __dmul_rn(__ddiv_rn((double)edge, (double)total), 1.0));
+    reward = __dadd_rn(reward, __ddiv_rn((double)edge, (double)total));      // `* 1.0` (env:259) is the identity in IEEE-754
     if (empty_after <= 2) reward = __dadd_rn(reward, -2.0);
     int line[4];
     ordered_pairs(cur, line);

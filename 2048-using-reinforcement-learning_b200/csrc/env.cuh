@@ -173,10 +173,10 @@ __device__ __forceinline__ double step_reward(const PendingReward &p)
 // nibble exactly where a real pair is equal; "any zero nibble" via the borrow trick is exact.
 __device__ __forceinline__ bool full_board_game_over(Board b)
 {
-    auto any_zero = [](uint32_t v) { return ((v - LSB4) & ~v & MSB4) != 0u; };
-    bool h = any_zero((b.lo ^ (b.lo >> 4)) | 0xF000F000u) || any_zero((b.hi ^ (b.hi >> 4)) | 0xF000F000u);
-    bool v = any_zero(b.lo ^ __funnelshift_r(b.lo, b.hi, 16)) || any_zero((b.hi ^ (b.hi >> 16)) | 0xFFFF0000u);
-    return !(h || v);
+    auto zero_nibbles = [](uint32_t v) { return (v - LSB4) & ~v; };        // bit 3 of the lowest zero nibble (and maybe above it)
+    uint32_t z = zero_nibbles((b.lo ^ (b.lo >> 4)) | 0xF000F000u) | zero_nibbles((b.hi ^ (b.hi >> 4)) | 0xF000F000u) |
+                 zero_nibbles(b.lo ^ __funnelshift_r(b.lo, b.hi, 16)) | zero_nibbles((b.hi ^ (b.hi >> 16)) | 0xFFFF0000u);
+    return (z & MSB4) == 0u;                                                // no equal neighbours anywhere
 }
 
 }  // namespace g2048
