@@ -44,7 +44,7 @@ SLEEP_CYCLES = 1_000_000     # torch.cuda._sleep before each timed launch (see r
 NCU_ROLLOUT = {"warp_inst_per_warp_step": 431.4,   # at capture time; later commits trimmed the loop to ~420
                 "dram_bytes_per_launch": 2150144, "alu_pipe_pct_of_peak": 65.1,
                "issue_active_pct": 69.0, "fma_pipe_pct_of_peak": 17.1, "source": "profiles/ncu_summary_r01.md"}
-NCU_BEAM = {"alu_pipe_pct_of_peak": 72.0, "issue_active_pct": 66.6, "dram_bytes_per_launch": 269056,
+NCU_BEAM = {"alu_pipe_pct_of_peak": 72.3, "issue_active_pct": 66.9, "dram_bytes_per_launch": 272128,
             "source": "profiles/ncu_summary_r01.md"}
 
 
