@@ -41,9 +41,8 @@ BEAM_W, BEAM_D, BEAM_ROOTS = 20, 40, 10000
 SLEEP_CYCLES = 1_000_000     # torch.cuda._sleep before each timed launch (see run_ours)
 # From the committed ncu capture of the same command (profiles/ncu_summary_r01.md): executed warp
 # instructions per warp-step of env_rollout_kernel, its DRAM traffic per launch, and pipe utilisation.
-NCU_ROLLOUT = {"warp_inst_per_warp_step": 431.4,   # at capture time; later commits trimmed the loop to ~420
-                "dram_bytes_per_launch": 2150144, "alu_pipe_pct_of_peak": 65.1,
-               "issue_active_pct": 69.0, "fma_pipe_pct_of_peak": 17.1, "source": "profiles/ncu_summary_r01.md"}
+NCU_ROLLOUT = {"warp_inst_per_warp_step": 416.4, "dram_bytes_per_launch": 2147584, "alu_pipe_pct_of_peak": 65.1,
+               "issue_active_pct": 68.7, "fma_pipe_pct_of_peak": 17.1, "source": "profiles/ncu_summary_r01.md"}
 NCU_BEAM = {"alu_pipe_pct_of_peak": 72.3, "issue_active_pct": 66.9, "dram_bytes_per_launch": 272128,
             "source": "profiles/ncu_summary_r01.md"}
 
