@@ -13,7 +13,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 STATS_LEN = 40
 STATS_MAXSCORE = 23
-MAX_BEAM_WIDTH = 32
+MAX_BEAM_WIDTH = 32          # warp-shuffle fast path; also the limit of play_games
+MAX_WIDE_BEAM_WIDTH = 128    # get_action / get_actions accept up to this (slower shared-memory path above 32)
 
 
 class G2048Error(RuntimeError):

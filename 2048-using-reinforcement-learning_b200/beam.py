@@ -23,8 +23,8 @@ class BeamSearchAgent:
     the DOWN rotation bug of _make_move, leaf-only ranking, adaptive depth."""
 
     def __init__(self, beam_width=10, search_depth=15, seed=None, device=0):
-        if not 1 <= int(beam_width) <= _lib.MAX_BEAM_WIDTH:
-            raise ValueError(f"beam_width must be in 1..{_lib.MAX_BEAM_WIDTH}")
+        if not 1 <= int(beam_width) <= _lib.MAX_WIDE_BEAM_WIDTH:
+            raise ValueError(f"beam_width must be in 1..{_lib.MAX_WIDE_BEAM_WIDTH}")
         self.beam_width = beam_width
         self.search_depth = search_depth
         self.action_names = {0: "LEFT", 1: "UP", 2: "RIGHT", 3: "DOWN"}
@@ -96,8 +96,8 @@ class BatchedBeamSearch:
     def __init__(self, beam_width=10, search_depth=15, device="cuda:0", seed=0,
                  early_game_threshold=512, mid_game_threshold=1024):
         import torch
-        if not 1 <= int(beam_width) <= _lib.MAX_BEAM_WIDTH:
-            raise ValueError(f"beam_width must be in 1..{_lib.MAX_BEAM_WIDTH}")
+        if not 1 <= int(beam_width) <= _lib.MAX_WIDE_BEAM_WIDTH:
+            raise ValueError(f"beam_width must be in 1..{_lib.MAX_WIDE_BEAM_WIDTH}")
         self.torch = torch
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -140,6 +140,8 @@ class BatchedBeamSearch:
         Returns dict of per-game device tensors (score, highest_exp, moves, valid, invalid,
         milestone[G,8], nodes, final_board) and, if stats, an int64[STATS_LEN] tensor ready for
         an all-reduce across ranks (see parallel.all_reduce_stats)."""
+        if self.beam_width > _lib.MAX_BEAM_WIDTH:
+            raise ValueError(f"play_games supports beam_width <= {_lib.MAX_BEAM_WIDTH} (get_actions: <= {_lib.MAX_WIDE_BEAM_WIDTH})")
         t = self.torch
         g = int(num_games)
         z = dict(device=self.device)

@@ -97,17 +97,25 @@ __device__ __forceinline__ int tile_value(uint32_t e) { return e ? (1 << e) : 0;
 // Branch-free on purpose (the Philox block is computed for every lane and masked by `draws`) so that
 // two rounds issued back to back form one basic block the scheduler can interleave: a warp
 // working alone at the tail of a whole-game run is bound by dependent-issue latency.
-template <bool kFull>
-__device__ __forceinline__ uint32_t spawn_and_score(int c, int n_valid, uint32_t lane_lt, uint32_t &spawn_base,
+struct ChildEval {
+    bool active;
+    int fast;          // _fast_evaluate (valid when !kFull)
+    double full;       // _evaluate_state (valid when kFull; also stored to ws.score[c])
+    uint32_t first;    // first action of the child's path
+};
+
+template <bool kFull, typename Scratch>
+__device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t lane_lt, uint32_t &spawn_base,
                                                     const BeamParams &P, uint32_t game, uint32_t call, int phase,
-                                                    WarpScratch &ws)
+                                                    Scratch &ws)
 {
-    const bool active = c < n_valid;
-    Board b = active ? Board(ws.cand[c]) : Board(0u, 0u);
-    const uint32_t fe = active ? ws.first[c] : 0u;
+    ChildEval ev;
+    ev.active = c < n_valid;
+    Board b = ev.active ? Board(ws.cand[c]) : Board(0u, 0u);
+    const uint32_t fe = ev.active ? ws.first[c] : 0u;
     uint32_t zl = zero_flags(b.lo), zh = zero_flags(b.hi);
     int n_empty = __popc(zl) + __popc(zh);
-    const bool draws = active && n_empty > 0;                   // agent:262-263: no draw on a full board
+    const bool draws = ev.active && n_empty > 0;                // agent:262-263: no draw on a full board
     const uint32_t bal = __ballot_sync(FULL, draws);
     const SpawnWords w = spawn_words(P.K, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lane_lt));
     spawn_base += (uint32_t)__popc(bal);
@@ -122,21 +130,29 @@ __device__ __forceinline__ uint32_t spawn_and_score(int c, int n_valid, uint32_t
     }
     const uint32_t pmax = fe >> 2;                              // parent's largest exponent
     const uint32_t emax = pmax + ((pmax < 15u && has_exponent(b, pmax + 1u)) ? 1u : 0u);
-    const uint32_t tail = ((uint32_t)(127 - c) << 2) | (fe & 3u);
-    uint32_t key;
-    double score = 0.0;
-    if (kFull) {
-        score = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase);
-        key = tail;                                             // rank field filled in by the caller
-    } else {
-        key = ((uint32_t)fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax) << 9) | tail;
-    }
-    if (active) {
+    ev.first = fe & 3u;
+    ev.fast = 0;
+    ev.full = 0.0;
+    if (kFull) ev.full = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase);
+    else       ev.fast = fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax);
+    if (ev.active) {
         ws.cand[c] = b.u64();
-        ws.first[c] = (uint8_t)((fe & 3u) | (emax << 2));
-        if (kFull) ws.score[c] = score;
+        ws.first[c] = (uint8_t)(ev.first | (emax << 2));
+        if (kFull) ws.score[c] = ev.full;
     }
-    return active ? key : 0u;
+    return ev;
+}
+
+// fast path (width <= 32): unique 32-bit sort key (score, 127 - generation index, first action)
+template <bool kFull>
+__device__ __forceinline__ uint32_t spawn_and_score(int c, int n_valid, uint32_t lane_lt, uint32_t &spawn_base,
+                                                    const BeamParams &P, uint32_t game, uint32_t call, int phase,
+                                                    WarpScratch &ws)
+{
+    const ChildEval ev = spawn_and_eval<kFull>(c, n_valid, lane_lt, spawn_base, P, game, call, phase, ws);
+    const uint32_t tail = ((uint32_t)(127 - c) << 2) | ev.first;
+    const uint32_t key = kFull ? tail : (((uint32_t)ev.fast << 9) | tail);   // kFull: rank field filled in by the caller
+    return ev.active ? key : 0u;
 }
 
 // kRows independent 32-key sorts in lockstep: same network, kRows exchanges per stage that do not
@@ -365,6 +381,155 @@ __global__ void __launch_bounds__(kBeamThreads, 1) beam_search_kernel(BeamArgs a
     }
 }
 
+// ---- wide beams (33 <= beam_width <= 128) ---------------------------------------------------------
+// Same algorithm with the beam and up to 512 candidates per level in shared memory and the stable
+// top-k done by counting (rank = #candidates ahead; score as float64 on every level, ties by
+// generation index).  O(n^2 / 32) per lane and level: a compatibility path for wide beams, not a
+// tuned one -- the reference's own configurations use widths 10-20.
+constexpr int kWideMaxWidth = 128;
+constexpr int kWideMaxCand = 4 * kWideMaxWidth;
+constexpr int kWideWarps = 8;
+struct __align__(16) WideScratch {
+    uint64_t beam[kWideMaxWidth];
+    uint64_t cand[kWideMaxCand];
+    double score[kWideMaxCand];
+    uint8_t beam_first[kWideMaxWidth];     // first action | largest exponent << 2, as in WarpScratch::first
+    uint8_t first[kWideMaxCand];
+    uint16_t slot[kWideMaxWidth];          // slot[rank] = candidate index
+};
+constexpr size_t kWideSmemBytes = kRowTableBytes + kWideWarps * sizeof(WideScratch);
+
+__device__ BeamResult beam_search_wide_warp(Board root, int legal_given, const BeamParams &P, uint32_t game,
+                                            uint32_t call, const uint16_t *row, WideScratch &ws)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const int L = (int)lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    BeamResult res;
+    res.nodes = 0;
+    res.best = 0.0;
+    Board root_child = agent_child_any(root, lane & 3u, row);
+    bool root_child_valid = root_child != root;
+    uint32_t agent_mask = __ballot_sync(FULL, root_child_valid) & 15u;
+    uint32_t vm = legal_given >= 0 ? ((uint32_t)legal_given & 15u) : agent_mask;
+    if (vm == 0u) { res.action = 0u; res.prob = 0.5f; return res; }
+    if ((vm & (vm - 1u)) == 0u) { res.action = (uint32_t)__ffs((int)vm) - 1u; res.prob = 1.0f; return res; }
+    const uint32_t root_emax = max_exponent(root);
+    const int root_max = tile_value(root_emax);
+    const int phase = root_max < P.early_thr ? 0 : root_max < P.mid_thr ? 1 : 2;
+    const int n0 = count_empty(root);
+    const int depth = max(1, n0 <= 4 ? min(P.depth + 5, 25) : n0 >= 10 ? min(P.depth - 5, 10) : P.depth);
+    int nb = 0;
+    uint32_t spawn_base = 0u;
+    for (int d = 0; d < depth; ++d) {
+        int n_valid = 0;
+        if (d == 0) {
+            bool is_cand = lane < 4u && ((vm >> lane) & 1u) && root_child_valid;
+            uint32_t bal = __ballot_sync(FULL, is_cand);
+            if (is_cand) {
+                int pos = __popc(bal & lt_mask);
+                ws.cand[pos] = root_child.u64();
+                ws.first[pos] = (uint8_t)(lane | (root_emax << 2));
+            }
+            n_valid = __popc(bal);
+        } else {
+            for (int p0 = 0; p0 < nb; p0 += 32) {                     // parents in rank order, 32 at a time
+                const int p = p0 + L;
+                Board c[4];
+                uint32_t v = 0u;
+                Board mine(0u, 0u);
+                if (p < nb) {
+                    mine = Board(ws.beam[p]);
+                    agent_children(mine, row, c);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) v |= (c[a] != mine) ? (1u << a) : 0u;
+                }
+                int incl = __popc(v);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(FULL, incl, o);
+                    if (L >= o) incl += t;
+                }
+                int pos = n_valid + incl - __popc(v);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    if ((v >> a) & 1u) { ws.cand[pos] = c[a].u64(); ws.first[pos] = ws.beam_first[p]; ++pos; }
+                n_valid += __shfl_sync(FULL, incl, 31);
+            }
+        }
+        __syncwarp();
+        if (n_valid == 0) {
+            if (d > 0) break;
+            Philox4 pw = philox4x32_10(0u, call, game, DOM_BEAM, P.K);
+            int pick = (int)__umulhi(pw.w[0], (uint32_t)__popc(vm));
+            uint32_t msk = vm;
+            for (int i = 0; i < pick; ++i) msk &= msk - 1u;
+            res.action = (uint32_t)__ffs((int)msk) - 1u;
+            res.prob = 0.5f;
+            return res;
+        }
+        res.nodes += n_valid;
+        const bool full_level = d >= 1 && d <= 3;
+        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+            if (full_level) {
+                spawn_and_eval<true>(c0 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            } else {
+                ChildEval ev = spawn_and_eval<false>(c0 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+                if (ev.active) ws.score[c0 + L] = (double)ev.fast;
+            }
+        }
+        __syncwarp();
+        nb = min(P.width, n_valid);
+        for (int c = L; c < n_valid; c += 32) {                       // stable rank by counting
+            const double s = ws.score[c];
+            int rank = 0;
+            for (int j = 0; j < n_valid; ++j) {
+                const double sj = ws.score[j];
+                rank += (sj > s || (sj == s && j < c)) ? 1 : 0;
+            }
+            if (rank < nb) ws.slot[rank] = (uint16_t)c;
+        }
+        __syncwarp();
+        for (int r = L; r < nb; r += 32) {
+            const int c = ws.slot[r];
+            ws.beam[r] = ws.cand[c];
+            ws.beam_first[r] = ws.first[c];
+        }
+        res.best = ws.score[ws.slot[0]];
+        __syncwarp();
+    }
+    res.action = ws.beam_first[0] & 3u;
+    res.prob = 1.0f;
+    return res;
+}
+
+__global__ void __launch_bounds__(kWideWarps * 32, 1) beam_search_wide_kernel(BeamArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int warp = threadIdx.x >> 5;
+    WideScratch &ws = reinterpret_cast<WideScratch *>(smem + kRowTableBytes)[warp];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(a.work, 1u);
+        i = __shfl_sync(FULL, i, 0);
+        if ((int64_t)i >= a.n) break;
+        Board root(a.roots[i]);
+        int legal = a.legal ? (int)a.legal[i] : -1;
+        uint32_t call = a.call ? a.call[i] : a.call0;
+        BeamResult r = beam_search_wide_warp(root, legal, a.P, a.game0 + (uint32_t)i, call, row, ws);
+        if (lane == 0) {
+            a.action[i] = (uint8_t)r.action;
+            if (a.prob) a.prob[i] = r.prob;
+            if (a.best) a.best[i] = r.best;
+            if (a.nodes) a.nodes[i] = r.nodes;
+        }
+        __syncwarp();
+    }
+}
+
 // A game that can be resumed exactly: every random draw is addressed by (game, call / spawn
 // counter), so the state below is all there is.
 struct GameState {
@@ -547,6 +712,7 @@ static int ensure_attrs()
     G2048_CUDA(cudaGetDevice(&dev));
     if (!g_attr_done[dev]) {
         G2048_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(beam_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
@@ -566,6 +732,14 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
                BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                game0, st->row, next_work_counter(st)};
     G2048_CUDA(cudaMemsetAsync(a.work, 0, sizeof(unsigned int), stream));
+    if (beam_width > 32) {                                          // wide beams: shared-memory beam, counting top-k
+        int wgrid = (int)(n < st->sm_count ? n : st->sm_count);
+        int64_t wwarps = (n + wgrid - 1) / wgrid;
+        int wthreads = 32 * (int)(wwarps < kWideWarps ? wwarps : kWideWarps);
+        beam_search_wide_kernel<<<wgrid, wthreads, kWideSmemBytes, stream>>>(a);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "beam_search_wide_kernel");
+    }
     // one block per SM; a small batch gets fewer warps per block so that it is spread over all SMs
     int grid = (int)(n < st->sm_count ? n : st->sm_count);
     int64_t warps = (n + grid - 1) / grid;

@@ -747,7 +747,7 @@ int g2048_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_
                       int64_t n, int32_t beam_width, int32_t search_depth,
                       int32_t early_thr, int32_t mid_thr, uint64_t seed, uint32_t game0, void *stream)
 {
-    G2048_ENTER(roots && action && beam_width >= 1 && beam_width <= G2048_MAX_BEAM_WIDTH && search_depth >= 1);
+    G2048_ENTER(roots && action && beam_width >= 1 && beam_width <= G2048_MAX_WIDE_BEAM_WIDTH && search_depth >= 1);
     return launch_beam_search(st, roots, legal, call, call0, action, prob, best_score, nodes, n, beam_width,
                               search_depth, early_thr, mid_thr, seed, game0, s);
 }

@@ -43,7 +43,8 @@ enum {
     G2048_ENODEVICE = -4    /* no CUDA device: there is no CPU fallback */
 };
 
-#define G2048_MAX_BEAM_WIDTH 32
+#define G2048_MAX_BEAM_WIDTH 32          /* warp-shuffle fast path, and the limit of g2048_play_games */
+#define G2048_MAX_WIDE_BEAM_WIDTH 128    /* g2048_beam_search accepts widths up to this (shared-memory path) */
 
 /* ---- lifecycle ---------------------------------------------------------- */
 int         g2048_abi_version(void);
@@ -150,7 +151,7 @@ int g2048_evaluate(const uint64_t *boards, int32_t *fast, double *full, int64_t 
  *   call     : NULL or uint32[n] per-root call index for the beam stream; else `call0` for all
  *   out      : action[n], prob[n] (0.5 / 1.0 as the reference returns), best_score[n]
  *              (score of candidates[0] at the last level), nodes[n] (evaluated children)
- *   beam_width 1..G2048_MAX_BEAM_WIDTH, search_depth >= 1,
+ *   beam_width 1..G2048_MAX_WIDE_BEAM_WIDTH (33 and up take a slower shared-memory path), search_depth >= 1,
  *   early_thr / mid_thr = agent.early_game_threshold / mid_game_threshold (512 / 1024). */
 int g2048_beam_search(const uint64_t *roots, const uint8_t *legal, const uint32_t *call, uint32_t call0,
                       uint8_t *action, float *prob, double *best_score, int32_t *nodes,

@@ -34,9 +34,10 @@ for it in range(rounds):
     assert (b == G.pack_boards(ob)).all() and (s == osc).all() and (c == octr).all() and (rs == ors).all() and (ep == oep).all()
     tot["env_board_steps"] += n * steps
     # ---- beam: random width / depth / thresholds / caller-supplied legality on the boards just reached
-    W = int(rng.integers(1, 33)); D = int(rng.integers(1, 46))
+    W = int(rng.integers(1, 33)) if rng.random() < 0.85 else int(rng.integers(33, 129))      # 15 %: wide-beam path
+    D = int(rng.integers(1, 46))
     early = int(2 ** rng.integers(3, 12)); mid = early * int(2 ** rng.integers(0, 3))
-    m = min(n, 400)
+    m = min(n, 400 if W <= 32 else 48)
     vals = ob[:m]; packed = b[:m].copy()
     legal = None
     if rng.random() < 0.5:

@@ -25,12 +25,12 @@ def test_argument_errors_are_reported_not_thrown():
     b = np.zeros(4, np.uint64); a = np.zeros(4, np.uint8)
     lib = X.lib()
     assert lib.g2048_host_env_step(None, X.P(a), None, None, None, None, None, None, None, None, None, 4, 1, 0) == -1
-    assert lib.g2048_host_beam_search(X.P(b), None, None, 0, X.P(a), None, None, None, 4, 33, 15, 512, 1024, 1, 0) == -1   # width > 32
+    assert lib.g2048_host_beam_search(X.P(b), None, None, 0, X.P(a), None, None, None, 4, 129, 15, 512, 1024, 1, 0) == -1   # width > 128
     assert lib.g2048_host_beam_search(X.P(b), None, None, 0, X.P(a), None, None, None, 4, 10, 0, 512, 1024, 1, 0) == -1    # depth < 1
     assert lib.g2048_host_legal_masks(X.P(b), None, None, -1) == -1
     assert b"bad argument" in lib.g2048_last_error()
     with pytest.raises(ValueError):
-        G.BeamSearchAgent(beam_width=40)
+        G.BeamSearchAgent(beam_width=200)
     with pytest.raises(ValueError):
         G.Game2048Env(size=5)
 
@@ -127,3 +127,18 @@ def test_reference_style_training_loop_runs_on_the_facades():
             best_tile = max(best_tile, int(info["highest_tile"]))
     assert steps > 50 and best_tile >= 16 and len(agent.memory) == steps
     assert isinstance(reward, float) and state.dtype == np.int32 and state.shape == (16,)
+
+
+@pytest.mark.parametrize("W,D,n", [(33, 12, 96), (50, 20, 64), (64, 8, 64), (100, 6, 48), (128, 10, 32)])
+def test_wide_beams_vs_oracle(orc, W, D, n):
+    """Widths above 32 take the shared-memory path (counting top-k); same results as the reference algorithm."""
+    vals, packed = X.synthetic(orc, n, SEED, 555 + W)
+    legal = np.array([orc.env_legal_mask(v) for v in vals], np.uint8) if W % 2 == 0 else None
+    act, p, s, k = X.host_beam(packed, W, D, SEED, game0=555 + W, call0=3, legal=legal)
+    for i in range(n):
+        o = orc.beam_get_action(vals[i], None if legal is None else int(legal[i]), W, D, SEED, 555 + W + i, 3)
+        assert (act[i], p[i], k[i], s[i]) == (o.action, o.prob, o.nodes, o.best_score), (W, i)
+    with pytest.raises(ValueError):
+        G.BatchedBeamSearch(W, D, "cuda:0").play_games(4)
+    a1, _ = G.BeamSearchAgent(beam_width=W, search_depth=D, seed=SEED).get_action(vals[0])
+    assert 0 <= a1 <= 3
