@@ -13,8 +13,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 STATS_LEN = 40
 STATS_MAXSCORE = 23
-MAX_BEAM_WIDTH = 32          # warp-shuffle fast path; also the limit of play_games
-MAX_WIDE_BEAM_WIDTH = 128    # get_action / get_actions accept up to this (slower shared-memory path above 32)
+MAX_BEAM_WIDTH = 32          # widths up to this take the warp-shuffle fast path
+MAX_WIDE_BEAM_WIDTH = 128    # accepted maximum (33 and up: slower shared-memory path)
 
 
 class G2048Error(RuntimeError):

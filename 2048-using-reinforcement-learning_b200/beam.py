@@ -140,8 +140,6 @@ class BatchedBeamSearch:
         Returns dict of per-game device tensors (score, highest_exp, moves, valid, invalid,
         milestone[G,8], nodes, final_board) and, if stats, an int64[STATS_LEN] tensor ready for
         an all-reduce across ranks (see parallel.all_reduce_stats)."""
-        if self.beam_width > _lib.MAX_BEAM_WIDTH:
-            raise ValueError(f"play_games supports beam_width <= {_lib.MAX_BEAM_WIDTH} (get_actions: <= {_lib.MAX_WIDE_BEAM_WIDTH})")
         t = self.torch
         g = int(num_games)
         z = dict(device=self.device)

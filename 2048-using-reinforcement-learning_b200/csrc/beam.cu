@@ -620,6 +620,48 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
     }
 }
 
+// Whole games with a wide beam (33..128): the same loop on the shared-memory search path, one warp
+// per game, no stall breaker (a compatibility path like beam_search_wide_kernel).
+__global__ void __launch_bounds__(kWideWarps * 32, 1) play_games_wide_kernel(GamesArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int warp = threadIdx.x >> 5;
+    WideScratch &ws = reinterpret_cast<WideScratch *>(smem + kRowTableBytes)[warp];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned int g = 0;
+        if (lane == 0) g = atomicAdd(a.work, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if ((int64_t)g >= a.n) break;
+        const uint32_t game = a.game0 + g;
+        EnvState s;
+        s.spawn_ctr = 0u;
+        env_reset(s, a.P.K, game);
+        env_reset(s, a.P.K, game);
+        GameState gs;
+        gs.index = g; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) gs.ms[m] = -1;
+        bool done = false;
+        while (!done && gs.moves < a.max_moves) {
+            BeamResult r = beam_search_wide_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
+            gs.nodes += r.nodes;
+            StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
+            done = st.done;
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
+            if (st.valid) ++gs.valid; else ++gs.invalid;
+            ++gs.moves;
+        }
+        gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
+        if (lane == 0) write_game(a, gs);
+        __syncwarp();
+    }
+}
+
 // Stall breaker: kSpecWarps warps per game search the next kSpecWarps get_action calls of the SAME
 // board at once.  An invalid move changes nothing in the env (no spawn, no counter), so call m+1
 // sees the board of call m whenever move m is invalid: the first call whose action is valid is the
@@ -713,6 +755,7 @@ static int ensure_attrs()
     if (!g_attr_done[dev]) {
         G2048_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(beam_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(play_games_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
@@ -756,6 +799,19 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
 {
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
+    if (beam_width > 32) {                                          // wide beams: compatibility path, no stall breaker
+        unsigned int *wwork = next_work_counter(st);
+        G2048_CUDA(cudaMemsetAsync(wwork, 0, sizeof(unsigned int), stream));
+        GamesArgs wa{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
+                     max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
+                     st->row, st->code, st->overflow, wwork, nullptr, nullptr};
+        int wgrid = (int)(n < st->sm_count ? n : st->sm_count);
+        int64_t wwarps = (n + wgrid - 1) / wgrid;
+        int wthreads = 32 * (int)(wwarps < kWideWarps ? wwarps : kWideWarps);
+        play_games_wide_kernel<<<wgrid, wthreads, kWideSmemBytes, stream>>>(wa);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "play_games_wide_kernel");
+    }
     // per-launch scratch for stalled games from the stream-ordered allocator: concurrent launches on
     // different streams never share it, and it is released when this launch's kernels are done
     GameState *pending = nullptr;

@@ -757,7 +757,7 @@ int g2048_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
                      int32_t *score, uint8_t *highest_exp, int32_t *moves, int32_t *valid, int32_t *invalid,
                      int32_t *milestone, int64_t *nodes, uint64_t *final_board, void *stream)
 {
-    G2048_ENTER(beam_width >= 1 && beam_width <= G2048_MAX_BEAM_WIDTH && search_depth >= 1 && max_moves >= 0);
+    G2048_ENTER(beam_width >= 1 && beam_width <= G2048_MAX_WIDE_BEAM_WIDTH && search_depth >= 1 && max_moves >= 0);
     return launch_play_games(st, n, beam_width, search_depth, early_thr, mid_thr, max_moves, seed, game0, score,
                              highest_exp, moves, valid, invalid, milestone, nodes, final_board, s);
 }

@@ -43,8 +43,8 @@ enum {
     G2048_ENODEVICE = -4    /* no CUDA device: there is no CPU fallback */
 };
 
-#define G2048_MAX_BEAM_WIDTH 32          /* warp-shuffle fast path, and the limit of g2048_play_games */
-#define G2048_MAX_WIDE_BEAM_WIDTH 128    /* g2048_beam_search accepts widths up to this (shared-memory path) */
+#define G2048_MAX_BEAM_WIDTH 32          /* widths up to this take the warp-shuffle fast path */
+#define G2048_MAX_WIDE_BEAM_WIDTH 128    /* widths up to this are accepted (33 and up: shared-memory path) */
 
 /* ---- lifecycle ---------------------------------------------------------- */
 int         g2048_abi_version(void);

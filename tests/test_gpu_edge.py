@@ -138,7 +138,13 @@ def test_wide_beams_vs_oracle(orc, W, D, n):
     for i in range(n):
         o = orc.beam_get_action(vals[i], None if legal is None else int(legal[i]), W, D, SEED, 555 + W + i, 3)
         assert (act[i], p[i], k[i], s[i]) == (o.action, o.prob, o.nodes, o.best_score), (W, i)
-    with pytest.raises(ValueError):
-        G.BatchedBeamSearch(W, D, "cuda:0").play_games(4)
+    if W in (33, 64):                                     # whole games on the wide path
+        out = X.host_play(6, W, 4, SEED, game0=77, max_moves=250)
+        ref = orc.play_games(SEED, 77, 6, W, 4, max_moves=250)
+        for i in range(6):
+            r = ref[i]
+            assert (out["score"][i], out["moves"][i], out["valid"][i], out["invalid"][i], out["nodes"][i]) == \
+                (r.score, r.moves, r.valid_moves, r.invalid_moves, r.nodes)
+            assert list(out["milestone"][i]) == list(r.milestone_move)
     a1, _ = G.BeamSearchAgent(beam_width=W, search_depth=D, seed=SEED).get_action(vals[0])
     assert 0 <= a1 <= 3
