@@ -42,7 +42,13 @@ SLEEP_CYCLES = 1_000_000     # torch.cuda._sleep before each timed launch (see r
 # From the committed ncu capture of the same command (profiles/ncu_summary_r01.md): executed warp
 # instructions per warp-step of env_rollout_kernel, its DRAM traffic per launch, and pipe utilisation.
 NCU_ROLLOUT = {"warp_inst_per_warp_step": 416.4, "dram_bytes_per_launch": 2147584, "alu_pipe_pct_of_peak": 65.1,
-               "issue_active_pct": 68.7, "fma_pipe_pct_of_peak": 17.1, "source": "profiles/ncu_summary_r01.md"}
+               "issue_active_pct": 68.7, "fma_pipe_pct_of_peak": 17.1, "source": "profiles/ncu_summary_r01.md",
+               # ALU-pipe instructions per warp-step = pct_of_peak x 0.5 inst/clk/SMSP x SMSP cycles per warp-step
+               "alu_warp_inst_per_warp_step": 225.6}
+# Measured pipe peaks of this pool's B200 (profiles/int32_peak.cu -> profiles/int32_peak_r01.json): a pure
+# LOP3/SHF/PRMT stream sustains 5.79e11 warp-inst/s (0.5 per clock per scheduler), an ALU+IMAD mix 1.13e12.
+INT32_PEAKS = {"alu_pipe_warp_inst_per_s": 5.79e11, "alu_plus_fma_warp_inst_per_s": 1.13e12,
+               "source": "profiles/int32_peak_r01.json"}
 NCU_BEAM = {"alu_pipe_pct_of_peak": 72.3, "issue_active_pct": 66.9, "dram_bytes_per_launch": 272128,
             "source": "profiles/ncu_summary_r01.md"}
 
@@ -341,6 +347,7 @@ def run_ours(args):
     sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6 if clocks else 1965.0e6
     issue_peak = 148 * 4 * sm_hz                                   # 1 warp-instruction / clk / scheduler
     issue_rate = (value / world) / 32.0 * NCU_ROLLOUT["warp_inst_per_warp_step"]
+    alu_rate = (value / world) / 32.0 * NCU_ROLLOUT["alu_warp_inst_per_warp_step"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,7 +371,11 @@ def run_ours(args):
                              "rollout keeps boards in registers (measured DRAM traffic = `traffic`), so the binding "
                              "roofline is ALU-pipe issue, reported in `issue`"},
         "issue": {"bound": "alu", "achieved": issue_rate, "peak": issue_peak, "unit": "warp-inst/s",
-                  "frac": issue_rate / issue_peak, "ncu": NCU_ROLLOUT},
+                  "frac": issue_rate / issue_peak, "ncu": NCU_ROLLOUT,
+                  "alu_pipe": {"achieved": alu_rate, "peak": INT32_PEAKS["alu_pipe_warp_inst_per_s"],
+                               "frac": alu_rate / INT32_PEAKS["alu_pipe_warp_inst_per_s"], "unit": "warp-inst/s",
+                               "peak_source": INT32_PEAKS["source"]},
+                  "measured_issue_peak": INT32_PEAKS["alu_plus_fma_warp_inst_per_s"]},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{cpu_n} envs x {cpu_steps} steps, oracle/orc2048.c on {threads} threads"},
         "per_step_api": {"value": per_step_api_value, "unit": UNIT,
