@@ -162,6 +162,46 @@ __device__ __forceinline__ bool codes_saturated(uint32_t codes)
     return ((((codes & 0x77777777u) + LSB4) & codes) & MSB4) != 0u;
 }
 
+// ---- pair tables of the fused rollout (512 x u32, shared memory) ------------------------------
+// Entry b < 256: sum of the two tile values whose exponents are the nibbles of byte b (0 = empty).
+// Entry 256 + c: score of the (up to two) merges a code byte c describes (2 << nibble each), plus
+// kPairSaturated when a nibble is 15, i.e. a merge produced 2^16.  One lookup replaces two
+// shift/mask/FMA extractions on the ALU pipe, which is the pipe the rollout is bound by.
+constexpr int kPairEntries = 512;
+constexpr uint32_t kPairSaturated = 1u << 28;          // above any sum of four row scores (< 2^20)
+__host__ __device__ __forceinline__ uint32_t pair_table_entry(uint32_t i)
+{
+    const uint32_t lo = i & 15u, hi = (i >> 4) & 15u;
+    if (i < 256u) return (lo ? 1u << lo : 0u) + (hi ? 1u << hi : 0u);
+    return (lo ? 2u << lo : 0u) + (hi ? 2u << hi : 0u) + ((lo == 15u || hi == 15u) ? kPairSaturated : 0u);
+}
+// pairs[offset4 / 4] for a byte offset that is already a multiple of 4 (saves the index scaling)
+__device__ __forceinline__ uint32_t pair_at(const uint32_t *pairs, uint32_t offset4)
+{
+    return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(pairs) + offset4);
+}
+// Score of a LEFT move of all four rows; bits 28.. count the rows with a saturated merge.
+template <bool kShared>
+__device__ __forceinline__ uint32_t merge_score_pairs(Board b, const uint8_t *code, const uint32_t *pairs)
+{
+    uint32_t c0 = lut8<kShared>(code, b.lo & 0xFFFFu);
+    uint32_t c1 = lut8<kShared>(code, b.lo >> 16);
+    uint32_t c2 = lut8<kShared>(code, b.hi & 0xFFFFu);
+    uint32_t c3 = lut8<kShared>(code, b.hi >> 16);
+    const uint32_t *m = pairs + 256;
+    return (m[c0] + m[c1]) + (m[c2] + m[c3]);
+}
+// edge_sum of env:254-259 = total - inner 2x2 + corners (a corner is counted by a row and a column)
+__device__ __forceinline__ uint32_t edge_sum_pairs(Board b, uint32_t total, const uint32_t *pairs)
+{
+    uint32_t inner = pair_at(pairs, (b.lo >> 18) & 0x3FCu) + pair_at(pairs, (b.hi >> 2) & 0x3FCu);   // cells 5,6 and 9,10
+    // cells 15 and 0 are neighbours in the rotated 64-bit word; cells 3 and 12 after a byte pick
+    uint32_t c015 = __funnelshift_l(b.hi, b.lo, 6) & 0x3FCu;
+    uint32_t c312 = (__byte_perm(b.lo, b.hi, 0x0061) >> 2) & 0x3FCu;
+    uint32_t corners = pair_at(pairs, c015) + pair_at(pairs, c312);
+    return total - inner + corners;
+}
+
 // Direction wrappers.  `to_line` brings the rows the tiles travel along into LEFT-move
 // position, `from_line` undoes it.  Lane-varying actions use selects, not branches.
 __device__ __forceinline__ Board select(bool p, Board a, Board b) { return Board(p ? a.lo : b.lo, p ? a.hi : b.hi); }
@@ -459,11 +499,13 @@ __device__ __forceinline__ void ordered_pairs_flags(Board b, uint32_t nzl, uint3
     uint32_t below_lo = __funnelshift_r(b.lo, b.hi, 16);
     uint32_t vl = ge_flags(below_lo, b.lo) & nl;
     uint32_t vh = ge_flags(b.hi >> 16, b.hi) & nh & 0x00008888u;
-    uint32_t v = vl | (vh << 1);
-    line[0] = __popc(hl & 0x0000FFFFu) + __popc(v & 0x00080018u);
-    line[1] = __popc(hl & 0xFFFF0000u) + __popc(v & 0x00800180u);
-    line[2] = __popc(hh & 0x0000FFFFu) + __popc(v & 0x08001800u);
-    line[3] = __popc(hh & 0xFFFF0000u) + __popc(v & 0x80018000u);
+    // all 24 flags in one word: rows 0,1 on bit 3 of their nibbles, rows 2,3 on bit 2, column pairs
+    // (0,1),(1,2) on bit 1 and (2,3) on bit 0; one popc per line instead of two
+    uint32_t x = hl | (hh >> 1) | (vl >> 2) | (vh >> 3);
+    line[0] = __popc(x & 0x0002088Bu);
+    line[1] = __popc(x & 0x08A80030u);
+    line[2] = __popc(x & 0x02000744u);
+    line[3] = __popc(x & 0x24443000u);
 }
 
 // shaped_reward() for callers that track the tile total (moves conserve it, a spawn adds its
@@ -471,7 +513,7 @@ __device__ __forceinline__ void ordered_pairs_flags(Board b, uint32_t nzl, uint3
 __device__ __forceinline__ double shaped_reward_tracked(bool valid, int empty_before, Board cur, int empty_after,
                                                         uint32_t nzl, uint32_t nzh, uint32_t score_delta,
                                                         uint32_t highest_exp_before, uint32_t prev_max_exp,
-                                                        uint32_t total)
+                                                        uint32_t total, const uint32_t *pairs)
 {
     double reward = __dmul_rn((double)score_delta, 0.25);
     if (highest_exp_before > prev_max_exp) {                               // env:229-241
@@ -483,10 +525,7 @@ __device__ __forceinline__ double shaped_reward_tracked(bool valid, int empty_be
     }
     if (!valid) reward = __dadd_rn(reward, -2.0);
     reward = __dadd_rn(reward, __dmul_rn((double)(empty_after - empty_before), 0.5));
-    // edge_sum = total - inner 2x2 + corners (corners are counted by a row and by a column)
-    float inner = pow2_sum(cur.hi, 0x00000110u, pow2_sum(cur.lo, 0x01100000u, 0.0f));
-    float corners = pow2_sum(cur.hi, 0x10010000u, pow2_sum(cur.lo, 0x00001001u, 0.0f));
-    uint32_t edge = total - (uint32_t)inner + (uint32_t)corners;
+    uint32_t edge = edge_sum_pairs(cur, total, pairs);
     reward = __dadd_rn(reward, __ddiv_rn((double)edge, (double)total));      // `* 1.0` (env:259) is the identity in IEEE-754
     if (empty_after <= 2) reward = __dadd_rn(reward, -2.0);
     int line[4];

@@ -112,8 +112,8 @@ struct PendingReward {
 
 template <bool kTrackMax>
 __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t action, const uint16_t *row,
-                                                   const uint8_t *code, const PhiloxKey &K, uint32_t game,
-                                                   uint32_t &saturated, bool &full)
+                                                   const uint8_t *code, const uint32_t *pairs, const PhiloxKey &K,
+                                                   uint32_t game, uint32_t &saturated, bool &full)
 {
     PendingReward p;
     EnvState &s = t.s;
@@ -123,9 +123,9 @@ __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t actio
     const SpawnWords w = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr);
     const Board line = to_line(prev, action);
     Board next = from_line(move_left<true>(line, row), action);
-    const uint32_t codes = merge_codes<true>(line, code);                   // action is always 0..3 here
-    p.score_delta = decode_score_fma(codes);
-    saturated |= codes_saturated(codes) ? 1u : 0u;
+    const uint32_t gained = merge_score_pairs<true>(line, code, pairs);      // action is always 0..3 here
+    p.score_delta = gained & (kPairSaturated - 1u);
+    saturated |= gained;                                                    // bits 28.. : see rollout_saturated()
     s.score += (int32_t)p.score_delta;
     p.valid = next != prev;
     uint32_t zl = zero_flags(next.lo), zh = zero_flags(next.hi);
@@ -152,6 +152,7 @@ __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t actio
     p.prev_max = kTrackMax ? t.bmax : 0u;
     if (kTrackMax) {
         // two tiles of the current maximum merged <=> some merge code equals bmax
+        const uint32_t codes = merge_codes<true>(line, code);
         uint32_t bmax = t.bmax + (zero_flags(codes ^ (t.bmax * LSB4)) != 0u ? 1u : 0u);
         bmax = max(bmax, spawn_exp);
         s.highest = max(s.highest, bmax);
@@ -163,11 +164,13 @@ __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t actio
     return p;
 }
 
-__device__ __forceinline__ double step_reward(const PendingReward &p)
+__device__ __forceinline__ double step_reward(const PendingReward &p, const uint32_t *pairs)
 {
     return shaped_reward_tracked(p.valid, p.empty_before, p.cur, p.empty_after, p.nzl, p.nzh, p.score_delta,
-                                 p.highest_before, p.prev_max, p.total);
+                                 p.highest_before, p.prev_max, p.total, pairs);
 }
+// `saturated` of step_move() accumulates raw table sums; some merge produced 2^16 iff a flag bit is set
+__device__ __forceinline__ bool rollout_saturated(uint32_t saturated) { return (saturated & ~(kPairSaturated - 1u)) != 0u; }
 
 // A full board is over when no two neighbours are equal.  (x ^ shifted) | guard has a zero
 // nibble exactly where a real pair is equal; "any zero nibble" via the borrow trick is exact.

@@ -172,7 +172,8 @@ constexpr int kRolloutThreads = G2048_ROLLOUT_THREADS;
 // loop nest is block -> word -> step and a step pays one AND and one shift for its action.
 template <bool kTrackMax>
 __device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &a, uint32_t game, const uint16_t *row,
-                                              const uint8_t *code, double &rsum, int32_t &episodes)
+                                              const uint8_t *code, const uint32_t *pairs, double &rsum,
+                                              int32_t &episodes)
 {
     if (a.steps <= 0) return;
     uint32_t t = a.t0;
@@ -189,28 +190,30 @@ __device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &
             word >>= 2u * (t & 15u);
             const uint32_t word_end = min(block_end, (t | 15u) + 1u);
             if (!have) {                                     // first step of the launch: nothing to overlap with yet
-                pend = step_move<kTrackMax>(e, word & 3u, row, code, a.K, game, saturated, full);
+                pend = step_move<kTrackMax>(e, word & 3u, row, code, pairs, a.K, game, saturated, full);
                 if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
                 word >>= 2; ++t; have = true;
             }
             for (; t < word_end; ++t) {
-                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, a.K, game, saturated, full);
+                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, pairs, a.K, game, saturated, full);
                 word >>= 2;
-                rsum = __dadd_rn(rsum, step_reward(pend));      // float64 sum stays in step order
+                rsum = __dadd_rn(rsum, step_reward(pend, pairs));      // float64 sum stays in step order
                 pend = cur;
                 if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
             }
         }
     }
-    rsum = __dadd_rn(rsum, step_reward(pend));
-    if (saturated) atomicAdd(a.overflow, 1ull);
+    rsum = __dadd_rn(rsum, step_reward(pend, pairs));
+    if (rollout_saturated(saturated)) atomicAdd(a.overflow, 1ull);
     if (!kTrackMax) e.s.highest = max_exponent(e.s.board);
 }
 
 __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(RolloutArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    stage_tables(smem, a.row, a.code, true);
+    __shared__ uint32_t pairs[kPairEntries];
+    for (int i = threadIdx.x; i < kPairEntries; i += blockDim.x) pairs[i] = pair_table_entry(i);
+    stage_tables(smem, a.row, a.code, true);                                  // its block-wide barrier also publishes `pairs`
     const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
     const uint8_t *code = smem + kRowTableBytes;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -226,8 +229,8 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(Rollout
         // highest > board max only if the caller poked it (env:229): such warps take the
         // variant that maintains both per step; everybody else skips that bookkeeping.
         const bool poked = __any_sync(__activemask(), e.s.highest > e.bmax);
-        if (poked) rollout_steps<true>(e, a, game, row, code, rsum, episodes);
-        else       rollout_steps<false>(e, a, game, row, code, rsum, episodes);
+        if (poked) rollout_steps<true>(e, a, game, row, code, pairs, rsum, episodes);
+        else       rollout_steps<false>(e, a, game, row, code, pairs, rsum, episodes);
         a.boards[i] = e.s.board.u64();
         a.score[i] = e.s.score;
         a.highest[i] = (uint8_t)e.s.highest;

@@ -22,6 +22,10 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u));
 }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    return (uint32_t)((((((uint64_t)hi) << 32) | lo) << (sh & 31u)) >> 32);
+}
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s)
 {
     uint64_t v = (((uint64_t)b) << 32) | a;
@@ -63,11 +67,16 @@ using namespace g2048;
 // the product's own table builder (csrc/row_tables.h), so the tables are under test too
 static uint16_t g_row[65536];
 static uint8_t g_code[65536];
+static uint32_t g_pairs[kPairEntries];
 static unsigned long long g_overflow;
 
 extern "C" {
 
-void emul_init(void) { build_row_tables(g_row, g_code); }
+void emul_init(void)
+{
+    build_row_tables(g_row, g_code);
+    for (int i = 0; i < kPairEntries; ++i) g_pairs[i] = pair_table_entry(i);
+}
 uint32_t emul_row(uint32_t r) { return g_row[r & 0xFFFF]; }
 uint32_t emul_code(uint32_t r) { return g_code[r & 0xFFFF]; }
 uint64_t emul_transpose(uint64_t b) { return transpose(Board(b)).u64(); }
@@ -142,13 +151,13 @@ static void rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, u
     uint32_t saturated = 0;
     for (int i = 0; i < steps; ++i) {
         bool full;
-        PendingReward p = step_move<kTrackMax>(t, random_action(K, game, t0 + i), g_row, g_code, K, game, saturated, full);
-        *reward_sum += step_reward(p);
+        PendingReward p = step_move<kTrackMax>(t, random_action(K, game, t0 + i), g_row, g_code, g_pairs, K, game, saturated, full);
+        *reward_sum += step_reward(p, g_pairs);
         bool done = full && full_board_game_over(t.s.board);
         if (full && done != env_game_over(t.s.board)) __builtin_trap();   // the two game-over tests must agree
         if (done) { ++*episodes; env_reset(t.s, K, game); track(t); }
     }
-    g_overflow += saturated;
+    g_overflow += rollout_saturated(saturated) ? 1u : 0u;
     if (!kTrackMax) t.s.highest = max_exponent(t.s.board);
     e->board = t.s.board.u64(); e->score = t.s.score; e->highest = t.s.highest; e->spawn_ctr = t.s.spawn_ctr;
 }
