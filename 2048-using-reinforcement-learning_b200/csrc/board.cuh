@@ -515,16 +515,18 @@ __device__ __forceinline__ double shaped_reward_tracked(bool valid, int empty_be
                                                         uint32_t highest_exp_before, uint32_t prev_max_exp,
                                                         uint32_t total, const uint32_t *pairs)
 {
-    double reward = __dmul_rn((double)score_delta, 0.25);
-    if (highest_exp_before > prev_max_exp) {                               // env:229-241
-        reward = __dadd_rn(reward, __dmul_rn(2.0, (double)highest_exp_before));
-        if (highest_exp_before >= 8)  reward = __dadd_rn(reward, 50.0);
-        if (highest_exp_before >= 9)  reward = __dadd_rn(reward, 100.0);
-        if (highest_exp_before >= 10) reward = __dadd_rn(reward, 200.0);
-        if (highest_exp_before >= 11) reward = __dadd_rn(reward, 500.0);
+    // env:225-251: score/4, the "new highest tile" bonuses, -2 for an invalid move and
+    // 0.5 per empty cell gained are all multiples of 0.25 far below 2^53, so every partial sum of the
+    // reference's float64 sequence is exact and the four terms can be added as integers (in quarters)
+    int quarters = (int)score_delta + 2 * (empty_after - empty_before) - (valid ? 0 : 8);
+    if (highest_exp_before > prev_max_exp) {
+        quarters += 8 * (int)highest_exp_before;
+        if (highest_exp_before >= 8)  quarters += 4 * 50;
+        if (highest_exp_before >= 9)  quarters += 4 * 100;
+        if (highest_exp_before >= 10) quarters += 4 * 200;
+        if (highest_exp_before >= 11) quarters += 4 * 500;
     }
-    if (!valid) reward = __dadd_rn(reward, -2.0);
-    reward = __dadd_rn(reward, __dmul_rn((double)(empty_after - empty_before), 0.5));
+    double reward = __dmul_rn((double)quarters, 0.25);
     uint32_t edge = edge_sum_pairs(cur, total, pairs);
     reward = __dadd_rn(reward, __ddiv_rn((double)edge, (double)total));      // `* 1.0` (env:259) is the identity in IEEE-754
     if (empty_after <= 2) reward = __dadd_rn(reward, -2.0);

@@ -92,6 +92,33 @@ __device__ __forceinline__ void track(TrackedEnv &t)
     t.bmax = max_exponent(t.s.board);
 }
 
+// env_reset() + track() for the fused rollout.  Same two spawns; a fresh board is known without
+// looking at it (14 empty cells, two tiles of exponent 1 or 2), the k-th empty cell of an empty
+// board is cell k, and one Philox block serves both spawns when the spawn counter is even.
+__device__ __forceinline__ void reset_tracked(TrackedEnv &t, const PhiloxKey &K, uint32_t game)
+{
+    EnvState &s = t.s;
+    const uint32_t i = s.spawn_ctr;
+    const Philox4 p = philox4x32_10(i >> 1, 0u, game, DOM_ENV, K);
+    uint32_t pos0 = p.w[0], val0 = p.w[1], pos1 = p.w[2], val1 = p.w[3];
+    if (i & 1u) {
+        const Philox4 q = philox4x32_10((i >> 1) + 1u, 0u, game, DOM_ENV, K);
+        pos0 = p.w[2]; val0 = p.w[3]; pos1 = q.w[0]; val1 = q.w[1];
+    }
+    const uint32_t e0 = val0 < 3865470567u ? 1u : 2u, e1 = val1 < 3865470567u ? 1u : 2u;
+    const uint32_t c0 = pos0 >> 28;                                  // (pos * 16) >> 32
+    const uint32_t k1 = __umulhi(pos1, 15u);
+    const uint32_t c1 = k1 + (k1 >= c0 ? 1u : 0u);                   // k1-th of the 15 cells left
+    const uint32_t t0 = e0 << ((4u * c0) & 31u), t1 = e1 << ((4u * c1) & 31u);
+    s.board = Board((c0 < 8u ? t0 : 0u) | (c1 < 8u ? t1 : 0u), (c0 < 8u ? 0u : t0) | (c1 < 8u ? 0u : t1));
+    s.score = 0;
+    s.spawn_ctr = i + 2u;
+    s.highest = max(e0, e1);
+    t.n_empty = 14;
+    t.total = 2u * (e0 + e1);                                        // 2^1 = 2*1, 2^2 = 2*2
+    t.bmax = s.highest;
+}
+
 // The step is split in two so that a caller can software-pipeline it: `step_move` produces
 // the next board (move, spawn, game-over test) and everything the reward needs; `step_reward`
 // turns that into the float64 reward.  The reward of step t does not feed step t+1, so a loop

@@ -191,7 +191,7 @@ __device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &
             const uint32_t word_end = min(block_end, (t | 15u) + 1u);
             if (!have) {                                     // first step of the launch: nothing to overlap with yet
                 pend = step_move<kTrackMax>(e, word & 3u, row, code, pairs, a.K, game, saturated, full);
-                if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
+                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, a.K, game); }
                 word >>= 2; ++t; have = true;
             }
             for (; t < word_end; ++t) {
@@ -199,7 +199,7 @@ __device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &
                 word >>= 2;
                 rsum = __dadd_rn(rsum, step_reward(pend, pairs));      // float64 sum stays in step order
                 pend = cur;
-                if (full && full_board_game_over(e.s.board)) { ++episodes; env_reset(e.s, a.K, game); track(e); }
+                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, a.K, game); }
             }
         }
     }

@@ -27,11 +27,12 @@ constexpr int kChains = 8;
 constexpr int kUnroll = 8;
 constexpr int kThreads = 1024;
 
-enum Op { LOP3, SHF, IADD3, PRMT, POPC, IMAD, FFMA, DADD, DMUL, MIX_ALU_FMA, MIX_LOP_SHF, LDS16, kOps };
+enum Op { LOP3, SHF, IADD3, PRMT, POPC, IMAD, FFMA, DADD, DMUL, MIX_ALU_FMA, MIX_LOP_SHF, LDS16, IMADHI, IMADWIDE, SEL, I2FD, kOps };
 static const char *kOpName[kOps] = {"lop3",      "shf",  "iadd", "prmt", "popc", "imad", "ffma",
-                                    "dadd",      "dmul", "mix_alu_fma",   "mix_lop3_shf", "lds_u16"};
+                                    "dadd",      "dmul", "mix_alu_fma",   "mix_lop3_shf", "lds_u16",
+                                    "imad_hi",   "imad_wide", "sel", "i2f_f64"};
 // instructions per chain step
-static const int kOpInstr[kOps] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 1};
+static const int kOpInstr[kOps] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 1, 1, 2, 2, 2};   // imad_wide, sel, i2f carry one helper op
 
 template <int OP>
 __device__ __forceinline__ void step(uint32_t &x, double &d, uint32_t a, uint32_t b, const uint16_t *tab) {
@@ -55,6 +56,18 @@ __device__ __forceinline__ void step(uint32_t &x, double &d, uint32_t a, uint32_
     if (OP == MIX_LOP_SHF) {
         asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b));
         asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+    }
+    if (OP == IMADHI) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x) : "r"(a));
+    if (OP == IMADWIDE) {
+        uint64_t w;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x), "r"(a));
+        x = (uint32_t)(w >> 32) ^ (uint32_t)w;      // one extra LOP3 per step (counted below as 1 instruction pair)
+    }
+    if (OP == SEL) asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(x) : "r"(a), "r"(b));
+    if (OP == I2FD) {
+        double t;
+        asm volatile("cvt.rn.f64.s32 %0, %1;" : "=d"(t) : "r"(x));
+        x = (uint32_t)__double_as_longlong(t) + (uint32_t)(__double_as_longlong(t) >> 32);
     }
     if (OP == LDS16) x = tab[x];   // dependent 16-bit table lookups, lane-random addresses
 }
@@ -168,7 +181,11 @@ int main() {
     run<DMUL>(sms, clock_khz, false);
     run<MIX_ALU_FMA>(sms, clock_khz, false);
     run<MIX_LOP_SHF>(sms, clock_khz, false);
-    run<LDS16>(sms, clock_khz, true);
+    run<LDS16>(sms, clock_khz, false);
+    run<IMADHI>(sms, clock_khz, false);
+    run<IMADWIDE>(sms, clock_khz, false);
+    run<SEL>(sms, clock_khz, false);
+    run<I2FD>(sms, clock_khz, true);
     printf("}\n");
     return 0;
 }

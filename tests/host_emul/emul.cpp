@@ -155,7 +155,7 @@ static void rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, u
         *reward_sum += step_reward(p, g_pairs);
         bool done = full && full_board_game_over(t.s.board);
         if (full && done != env_game_over(t.s.board)) __builtin_trap();   // the two game-over tests must agree
-        if (done) { ++*episodes; env_reset(t.s, K, game); track(t); }
+        if (done) { ++*episodes; reset_tracked(t, K, game); }
     }
     g_overflow += rollout_saturated(saturated) ? 1u : 0u;
     if (!kTrackMax) t.s.highest = max_exponent(t.s.board);

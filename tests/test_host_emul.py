@@ -219,10 +219,12 @@ def test_tracked_rollout_step_matches_oracle(emul, orc):
         env = orc.Env(SEED, 700 + i, ctor_reset=False)
         env.reset()
         ob[i] = env.board; ohi[i] = env.s.highest_tile; octr[i] = env.s.spawn_ctr
-    start = ob.copy()
+        if i % 4 == 3:
+            ohi[i] = 1 << (7 + i % 5)      # highest_tile poked above the board: env:229 pays its bonuses
+    start = ob.copy(); start_hi = ohi.copy()
     orc.rollout(ob, osc, ohi, octr, ors, oep, steps, 3, SEED, 700)
     for i in range(n):
-        e = EmulEnv(packing.pack_board(start[i]), 0, int(start[i].max()).bit_length() - 1, 2)
+        e = EmulEnv(packing.pack_board(start[i]), 0, int(start_hi[i]).bit_length() - 1, 2)
         rs = C.c_double(0.0); ep = C.c_int(0)
         emul.emul_rollout_tracked(C.byref(e), steps, 3, SEED, 700 + i, C.byref(rs), C.byref(ep), i & 1)
         assert e.board == packing.pack_board(ob[i]) and e.score == osc[i] and e.spawn_ctr == octr[i]
