@@ -26,9 +26,11 @@ constexpr int kBeamThreads = kBeamWarps * 32;
 constexpr int kMaxCand = 4 * G2048_MAX_BEAM_WIDTH;          // 128 children per level at most
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
+constexpr uint32_t kSpawnRing = 128;                        // spawn ordinals held per warp (power of two)
 struct __align__(16) WarpScratch {
     uint64_t cand[kMaxCand];     // children of this level, generation order
     double score[kMaxCand];      // float64 scores of the full-evaluation levels
+    uint4 rng[kSpawnRing / 2];   // spawn words of ordinals [ring_end - 128, ring_end): one Philox block per entry
     uint8_t first[kMaxCand];     // bits 0-1: first action of the child's path; bits 2-5: its largest exponent
 };
 constexpr size_t kBeamSmemBytes = kRowTableBytes + kBeamWarps * sizeof(WarpScratch);
@@ -104,6 +106,34 @@ struct ChildEval {
     uint32_t first;    // first action of the child's path
 };
 
+// The beam stream hands out spawn words in ordinal order, two ordinals per Philox block.  One pass
+// of this loop has lane j compute block ring_end / 2 + j, i.e. 64 ordinals for the instructions a
+// per-batch draw would spend on 32 (or on far fewer: the last batch of a level is mostly idle
+// lanes), and what a level leaves over serves the next one.  Callers ask for at most 64 ordinals
+// past spawn_base at a time, so everything they still need stays inside the 128-ordinal ring.
+__device__ __forceinline__ void fill_spawn_ring(WarpScratch &ws, uint32_t &ring_end, uint32_t need_end,
+                                                const BeamParams &P, uint32_t game, uint32_t call, uint32_t lane)
+{
+    if (ring_end >= need_end) return;                           // warp-uniform
+    __syncwarp();
+    do {
+        const Philox4 p = philox4x32_10((ring_end >> 1) + lane, call, game, DOM_BEAM, P.K);
+        ws.rng[((ring_end & (kSpawnRing - 1u)) >> 1) + lane] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
+        ring_end += 64u;
+    } while (ring_end < need_end);
+    __syncwarp();
+}
+template <typename Scratch> struct HasSpawnRing { static constexpr bool value = false; };
+template <> struct HasSpawnRing<WarpScratch> { static constexpr bool value = true; };
+template <typename Scratch>
+__device__ __forceinline__ SpawnWords ring_words(const Scratch &, uint32_t) { return SpawnWords{0u, 0u}; }
+template <>
+__device__ __forceinline__ SpawnWords ring_words<WarpScratch>(const WarpScratch &ws, uint32_t ordinal)
+{
+    const uint2 w = reinterpret_cast<const uint2 *>(ws.rng)[ordinal & (kSpawnRing - 1u)];
+    return SpawnWords{w.x, w.y};
+}
+
 template <bool kFull, typename Scratch>
 __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t lane_lt, uint32_t &spawn_base,
                                                     const BeamParams &P, uint32_t game, uint32_t call, int phase,
@@ -117,7 +147,10 @@ __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t
     int n_empty = __popc(zl) + __popc(zh);
     const bool draws = ev.active && n_empty > 0;                // agent:262-263: no draw on a full board
     const uint32_t bal = __ballot_sync(FULL, draws);
-    const SpawnWords w = spawn_words(P.K, game, call, DOM_BEAM, spawn_base + (uint32_t)__popc(bal & lane_lt));
+    const uint32_t ordinal = spawn_base + (uint32_t)__popc(bal & lane_lt);
+    // fast path: the caller has filled the ring (fill_spawn_ring); wide path: one block per child
+    const SpawnWords w = HasSpawnRing<Scratch>::value ? ring_words(ws, ordinal)
+                                                      : spawn_words(P.K, game, call, DOM_BEAM, ordinal);
     spawn_base += (uint32_t)__popc(bal);
     Board spawned = b;
     const Spawned sp = place_tile_flags(spawned, zl, zh, max(n_empty, 1), w.pos, w.val);
@@ -217,6 +250,7 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
     const uint32_t root_emax = max_exponent(root);
     int nb = 0;                  // beam entries alive
     uint32_t spawn_base = 0u;    // spawns drawn so far in this call
+    uint32_t ring_end = 0u;      // ws.rng holds the spawn words of ordinals [ring_end - 128, ring_end)
 
     for (int d = 0; d < depth; ++d) {
         // ---- A: expand ----------------------------------------------------------------------
@@ -273,15 +307,22 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         const bool full_level = d >= 1 && d <= 3;                       // agent:139,158-161
         uint32_t key[4] = {0u, 0u, 0u, 0u};
         const int L = (int)lane;
+        fill_spawn_ring(ws, ring_end, spawn_base + (uint32_t)min(n_valid, 64), P, game, call, lane);
         if (full_level) {
             key[0] = spawn_and_score<true>(L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
             if (n_valid > 32) key[1] = spawn_and_score<true>(32 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
-            if (n_valid > 64) key[2] = spawn_and_score<true>(64 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 64) {
+                fill_spawn_ring(ws, ring_end, spawn_base + (uint32_t)(n_valid - 64), P, game, call, lane);
+                key[2] = spawn_and_score<true>(64 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            }
             if (n_valid > 96) key[3] = spawn_and_score<true>(96 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
         } else if (n_valid > 32) {                                      // the common case: two rounds, one basic block
             key[0] = spawn_and_score<false>(L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
             key[1] = spawn_and_score<false>(32 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
-            if (n_valid > 64) key[2] = spawn_and_score<false>(64 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            if (n_valid > 64) {
+                fill_spawn_ring(ws, ring_end, spawn_base + (uint32_t)(n_valid - 64), P, game, call, lane);
+                key[2] = spawn_and_score<false>(64 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
+            }
             if (n_valid > 96) key[3] = spawn_and_score<false>(96 + L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
         } else {
             key[0] = spawn_and_score<false>(L, n_valid, lt_mask, spawn_base, P, game, call, phase, ws);
