@@ -47,6 +47,13 @@ struct BeamResult {
     int nodes;
 };
 
+// The block's corner table (board.cuh: corner_table_entry); stage_row_table() fills it.
+__device__ __forceinline__ uint32_t *corner_table()
+{
+    __shared__ uint32_t table[256];
+    return table;
+}
+
 // ---- warp-wide sorting network on unique uint32 keys, descending (lane 0 = largest) --------
 // Bitonic sort in its "flip" form: every compare-exchange keeps the larger key in the lower
 // lane, so the direction of a stage is one lane-id bit test (five loop-invariant predicates)
@@ -166,8 +173,8 @@ __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t
     ev.first = fe & 3u;
     ev.fast = 0;
     ev.full = 0.0;
-    if (kFull) ev.full = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase);
-    else       ev.fast = fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax);
+    if (kFull) ev.full = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase, corner_table());
+    else       ev.fast = fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, corner_table());
     if (ev.active) {
         ws.cand[c] = b.u64();
         ws.first[c] = (uint8_t)(ev.first | (emax << 2));
@@ -216,6 +223,31 @@ __device__ __forceinline__ void merge_top32_x2(uint32_t &a0, uint32_t b0, uint32
         const bool lower = (lane & j) == 0;
         a0 = exchange(a0, j, lower);
         a1 = exchange(a1, j, lower);
+    }
+}
+
+// Full-evaluation levels: rank = #candidates with a strictly larger float64 score, written into the
+// score field of the keys of the kRows rows in use (candidate c sits in row c / 32, lane c % 32).
+template <int kRows>
+__device__ __forceinline__ void rank_by_count(const WarpScratch &ws, int n_valid, uint32_t lane, uint32_t (&key)[4])
+{
+    int rank[kRows];
+    double mine_s[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int c = r * 32 + (int)lane;
+        rank[r] = 0;
+        mine_s[r] = c < n_valid ? ws.score[c] : 0.0;
+    }
+    for (int j = 0; j < n_valid; ++j) {
+        const double s = ws.score[j];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) rank[r] += (s > mine_s[r]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const int c = r * 32 + (int)lane;
+        if (c < n_valid) key[r] |= (uint32_t)(n_valid - rank[r]) << 9;
     }
 }
 
@@ -331,23 +363,10 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
         if (full_level) {
             // float64 scores: rank = #candidates with a strictly larger score; equal scores are
             // separated by the generation index already in the key (stable sort).
-            int rank[4] = {0, 0, 0, 0};
-            double mine_s[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int c = r * 32 + (int)lane;
-                mine_s[r] = c < n_valid ? ws.score[c] : 0.0;
-            }
-            for (int j = 0; j < n_valid; ++j) {
-                const double s = ws.score[j];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) rank[r] += (s > mine_s[r]) ? 1 : 0;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int c = r * 32 + (int)lane;
-                if (c < n_valid) key[r] |= (uint32_t)(n_valid - rank[r]) << 9;
-            }
+            const int rows = (n_valid + 31) >> 5;
+            if (rows <= 2)      rank_by_count<2>(ws, n_valid, lane, key);
+            else if (rows == 3) rank_by_count<3>(ws, n_valid, lane, key);
+            else                rank_by_count<4>(ws, n_valid, lane, key);
         }
 
         // ---- C: stable top-k ------------------------------------------------------------------------
@@ -384,6 +403,8 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
 
 __device__ __forceinline__ void stage_row_table(uint8_t *smem, const uint16_t *row)
 {
+    uint32_t *corners = corner_table();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) corners[i] = corner_table_entry(i);   // published by the barrier in stage_bulk
     stage_bulk(smem, row, (uint32_t)kRowTableBytes, nullptr, nullptr, 0u);       // TMA bulk copy, stage.cuh
 }
 

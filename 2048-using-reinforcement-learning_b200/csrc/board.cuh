@@ -401,7 +401,7 @@ __device__ __forceinline__ void merge_pairs_flags(Board b, uint32_t nl, uint32_t
     uint32_t hh = eq_flags(b.hi, b.hi >> 4) & nh & 0x01110111u;
     uint32_t vl = eq_flags(b.lo, __funnelshift_r(b.lo, b.hi, 16)) & nl;
     uint32_t vh = eq_flags(b.hi, b.hi >> 16) & nh & 0x00001111u;
-    *pairs = __popc(hl) + __popc(hh) + __popc(vl) + __popc(vh);
+    *pairs = __popc(hl + hh * 2u + vl * 4u + vh * 8u);       // disjoint bit classes: one popc, shifts on the FMA pipe
     if (exponent_sum) {
         // keep the exponent of the first cell of every pair, then add all nibbles up
         uint32_t a = b.lo & (hl * 15u), c = b.hi & (hh * 15u), d = b.lo & (vl * 15u), e = b.hi & (vh * 15u);
@@ -412,11 +412,33 @@ __device__ __forceinline__ void merge_pairs_flags(Board b, uint32_t nl, uint32_t
     }
 }
 
-// BeamSearchAgent._fast_evaluate (agent:280-314): always an exact integer.
-__device__ __forceinline__ int fast_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax)
+// Corner table of the beam kernels (256 x u32, shared memory), indexed by a byte holding two corner
+// exponents: bits 24.. = the larger exponent, bits 0..19 = 2 * its tile value (0 for two empty cells).
+// Both fields grow with the exponent, so the larger entry of the two corner pairs describes the best corner.
+__host__ __device__ __forceinline__ uint32_t corner_table_entry(uint32_t i)
 {
-    uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
-    int corner_score = corner ? (int)(2u << corner) : 0;          // 2 * tile value of the best corner
+    const uint32_t lo = i & 15u, hi = (i >> 4) & 15u, m = lo > hi ? lo : hi;
+    return (m << 24) | (m ? 2u << m : 0u);
+}
+__device__ __forceinline__ uint32_t best_corner(Board b, const uint32_t *corners)
+{
+    // cells 15 and 0 are neighbours in the rotated 64-bit word; cells 3 and 12 after a byte pick
+    const uint32_t c015 = __funnelshift_l(b.hi, b.lo, 6) & 0x3FCu;
+    const uint32_t c312 = (__byte_perm(b.lo, b.hi, 0x0061) >> 2) & 0x3FCu;
+    return max(pair_at(corners, c015), pair_at(corners, c312));
+}
+
+// BeamSearchAgent._fast_evaluate (agent:280-314): always an exact integer.
+__device__ __forceinline__ int fast_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax,
+                                               const uint32_t *corners = nullptr)
+{
+    int corner_score;                                             // 2 * tile value of the best corner
+    if (corners) {
+        corner_score = (int)(best_corner(b, corners) & 0xFFFFFu);
+    } else {
+        uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
+        corner_score = corner ? (int)(2u << corner) : 0;
+    }
     int pairs;
     merge_pairs_flags(b, nl, nh, &pairs, nullptr);
     return n_empty * 10 + (int)emax * 2 + corner_score + pairs * 2;
@@ -428,12 +450,14 @@ __device__ __forceinline__ int fast_eval(Board b, int n_empty, uint32_t emax)
 
 // BeamSearchAgent._evaluate_state (agent:316-373) in float64 with the reference's operation
 // order and no FMA contraction: bit-exact.  phase 0 early, 1 mid, 2 late.
-__device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax, int phase);
+__device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax, int phase,
+                                                  const uint32_t *corners = nullptr);
 __device__ __forceinline__ double full_eval(Board b, int n_empty, uint32_t emax, int phase)
 {
     return full_eval_flags(b, nz_flags(b.lo), nz_flags(b.hi), n_empty, emax, phase);
 }
-__device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax, int phase)
+__device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t nh, int n_empty, uint32_t emax, int phase,
+                                                  const uint32_t *corners)
 {
     const double w_empty  = phase == 0 ? 15.0 : phase == 1 ? 10.0 : 8.0;
     const double w_max    = phase == 0 ? 1.0  : phase == 1 ? 1.5  : 2.0;
@@ -445,7 +469,8 @@ __device__ __forceinline__ double full_eval_flags(Board b, uint32_t nl, uint32_t
     if (emax >= 9)  max_score = __dmul_rn(max_score, 1.2);
     if (emax >= 10) max_score = __dmul_rn(max_score, 1.5);
     if (emax >= 11) max_score = __dmul_rn(max_score, 2.0);
-    uint32_t corner = max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
+    uint32_t corner = corners ? best_corner(b, corners) >> 24
+                              : max(max(b.lo & 15u, (b.lo >> 12) & 15u), max((b.hi >> 16) & 15u, b.hi >> 28));
     double corner_bonus = __dmul_rn(__dmul_rn((double)corner, 2.0), w_corner);
     int pairs, esum;
     merge_pairs_flags(b, nl, nh, &pairs, &esum);

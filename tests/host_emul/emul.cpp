@@ -68,6 +68,7 @@ using namespace g2048;
 static uint16_t g_row[65536];
 static uint8_t g_code[65536];
 static uint32_t g_pairs[kPairEntries];
+static uint32_t g_corners[256];
 static unsigned long long g_overflow;
 
 extern "C" {
@@ -76,6 +77,7 @@ void emul_init(void)
 {
     build_row_tables(g_row, g_code);
     for (int i = 0; i < kPairEntries; ++i) g_pairs[i] = pair_table_entry(i);
+    for (int i = 0; i < 256; ++i) g_corners[i] = corner_table_entry(i);
 }
 uint32_t emul_row(uint32_t r) { return g_row[r & 0xFFFF]; }
 uint32_t emul_code(uint32_t r) { return g_code[r & 0xFFFF]; }
@@ -110,6 +112,17 @@ uint32_t emul_max_exponent(uint64_t b) { return max_exponent(Board(b)); }
 uint64_t emul_place_tile(uint64_t b, uint32_t pw, uint32_t vw) { Board x(b); place_tile(x, pw, vw); return x.u64(); }
 int emul_fast_eval(uint64_t b) { Board x(b); return fast_eval(x, count_empty(x), max_exponent(x)); }
 double emul_full_eval(uint64_t b, int phase) { Board x(b); return full_eval(x, count_empty(x), max_exponent(x), phase); }
+// the beam kernels' variants: corner term from the 256-entry table, flags handed in
+int emul_fast_eval_lut(uint64_t b)
+{
+    Board x(b);
+    return fast_eval_flags(x, nz_flags(x.lo), nz_flags(x.hi), count_empty(x), max_exponent(x), g_corners);
+}
+double emul_full_eval_lut(uint64_t b, int phase)
+{
+    Board x(b);
+    return full_eval_flags(x, nz_flags(x.lo), nz_flags(x.hi), count_empty(x), max_exponent(x), phase, g_corners);
+}
 double emul_ppo_heuristic(uint64_t b) { return ppo_heuristic(Board(b)); }
 double emul_ppo_top4(uint64_t b) { return ppo_top4_bonus(Board(b)); }
 void emul_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out)

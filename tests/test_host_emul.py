@@ -52,6 +52,8 @@ def emul():
     L.emul_place_tile.argtypes = [u64, u32, u32]; L.emul_place_tile.restype = u64
     L.emul_fast_eval.argtypes = [u64]; L.emul_fast_eval.restype = C.c_int
     L.emul_full_eval.argtypes = [u64, C.c_int]; L.emul_full_eval.restype = C.c_double
+    L.emul_fast_eval_lut.argtypes = [u64]; L.emul_fast_eval_lut.restype = C.c_int
+    L.emul_full_eval_lut.argtypes = [u64, C.c_int]; L.emul_full_eval_lut.restype = C.c_double
     L.emul_ppo_heuristic.argtypes = [u64]; L.emul_ppo_heuristic.restype = C.c_double
     L.emul_ppo_top4.argtypes = [u64]; L.emul_ppo_top4.restype = C.c_double
     L.emul_philox.argtypes = [u32] * 6 + [C.POINTER(u32)]
@@ -139,8 +141,10 @@ def test_evals_bit_exact(emul, orc):
             continue
         p = packing.pack_board(b)
         assert float(emul.emul_fast_eval(p)) == orc.fast_eval(b), b
+        assert float(emul.emul_fast_eval_lut(p)) == orc.fast_eval(b), b
         for ph in range(3):
             assert emul.emul_full_eval(p, ph) == orc.full_eval(b, ph), (b, ph)
+            assert emul.emul_full_eval_lut(p, ph) == orc.full_eval(b, ph), (b, ph)
 
 
 def test_place_tile_every_slot(emul, orc):
