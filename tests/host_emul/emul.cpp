@@ -112,6 +112,25 @@ uint32_t emul_max_exponent(uint64_t b) { return max_exponent(Board(b)); }
 uint64_t emul_place_tile(uint64_t b, uint32_t pw, uint32_t vw) { Board x(b); place_tile(x, pw, vw); return x.u64(); }
 int emul_fast_eval(uint64_t b) { Board x(b); return fast_eval(x, count_empty(x), max_exponent(x)); }
 double emul_full_eval(uint64_t b, int phase) { Board x(b); return full_eval(x, count_empty(x), max_exponent(x), phase); }
+// the fused rollout's table-driven pieces against their arithmetic twins
+uint32_t emul_edge_sum(uint64_t b, int use_pairs)
+{
+    Board x(b);
+    const uint32_t total = tile_sum_half(x.lo, LSB4) + tile_sum_half(x.hi, LSB4);
+    if (use_pairs) return edge_sum_pairs(x, total, g_pairs);
+    return total - (tile_sum_half(x.lo, 0x01100000u) + tile_sum_half(x.hi, 0x00000110u))
+                 + (tile_sum_half(x.lo, 0x00001001u) + tile_sum_half(x.hi, 0x10010000u));
+}
+uint32_t emul_move_score_pairs(uint64_t b, uint32_t action)     // bits 28.. = rows with a saturated merge
+{
+    return merge_score_pairs<false>(to_line(Board(b), action), g_code, g_pairs);
+}
+void emul_ordered_lines(uint64_t b, int use_flags, int *line)
+{
+    Board x(b);
+    if (use_flags) ordered_pairs_flags(x, nz_flags(x.lo), nz_flags(x.hi), line);
+    else ordered_pairs(x, line);
+}
 // the beam kernels' variants: corner term from the 256-entry table, flags handed in
 int emul_fast_eval_lut(uint64_t b)
 {

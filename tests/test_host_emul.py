@@ -53,6 +53,9 @@ def emul():
     L.emul_fast_eval.argtypes = [u64]; L.emul_fast_eval.restype = C.c_int
     L.emul_full_eval.argtypes = [u64, C.c_int]; L.emul_full_eval.restype = C.c_double
     L.emul_fast_eval_lut.argtypes = [u64]; L.emul_fast_eval_lut.restype = C.c_int
+    L.emul_edge_sum.argtypes = [u64, C.c_int]; L.emul_edge_sum.restype = C.c_uint32
+    L.emul_move_score_pairs.argtypes = [u64, C.c_uint32]; L.emul_move_score_pairs.restype = C.c_uint32
+    L.emul_ordered_lines.argtypes = [u64, C.c_int, C.POINTER(C.c_int)]; L.emul_ordered_lines.restype = None
     L.emul_full_eval_lut.argtypes = [u64, C.c_int]; L.emul_full_eval_lut.restype = C.c_double
     L.emul_ppo_heuristic.argtypes = [u64]; L.emul_ppo_heuristic.restype = C.c_double
     L.emul_ppo_top4.argtypes = [u64]; L.emul_ppo_top4.restype = C.c_double
@@ -145,6 +148,33 @@ def test_evals_bit_exact(emul, orc):
         for ph in range(3):
             assert emul.emul_full_eval(p, ph) == orc.full_eval(b, ph), (b, ph)
             assert emul.emul_full_eval_lut(p, ph) == orc.full_eval(b, ph), (b, ph)
+
+
+def test_rollout_tables_match_arithmetic(emul, orc):
+    """The fused rollout's shared-memory pair tables (edge sum, merge score incl. the saturation flag)
+    and its one-popc-per-line ordered-pair count against the arithmetic forms the per-step path uses,
+    and against the reference formulas evaluated directly."""
+    for b in boards_for_test(orc):
+        p = packing.pack_board(b)
+        g = b.reshape(4, 4).astype(np.int64)
+        edge = int(g[0].sum() + g[3].sum() + g[:, 0].sum() + g[:, 3].sum())          # env:254-257
+        assert emul.emul_edge_sum(p, 1) == emul.emul_edge_sum(p, 0) == edge, b
+        a, f = (C.c_int * 4)(), (C.c_int * 4)()
+        emul.emul_ordered_lines(p, 0, a); emul.emul_ordered_lines(p, 1, f)
+        want = []
+        for i in range(4):                                                          # env:267-275
+            row = sum(1 for j in range(1, 4) if g[i, j] > 0 and g[i, j - 1] > 0 and g[i, j] >= g[i, j - 1])
+            col = sum(1 for j in range(1, 4) if g[j, i] > 0 and g[j - 1, i] > 0 and g[j, i] >= g[j - 1, i])
+            want.append(row + col)
+        assert list(a) == list(f) == want, b
+        for action in range(4):
+            s = emul.emul_move_score_pairs(p, action)
+            lines = [[v for v in r if v] for r in (g if action in (0, 2) else g.T)]      # tiles slide together first
+            sat = any(r[j] == r[j + 1] == 32768 for r in lines for j in range(len(r) - 1))
+            assert (s & 0x0FFFFFFF) == emul.emul_move_score(p, action), (b, action)
+            assert (s >> 28 != 0) == sat, (b, action)
+    full = packing.pack_board(np.full(16, 32768, np.int32))
+    assert emul.emul_move_score_pairs(full, 0) >> 28 == 4           # every row merges 32768 + 32768
 
 
 def test_place_tile_every_slot(emul, orc):
