@@ -43,8 +43,19 @@ __device__ __forceinline__ uint32_t nz_flags(uint32_t x)
 // bit 4i set  <=>  nibble i of x is zero
 __device__ __forceinline__ uint32_t zero_flags(uint32_t x) { return ~nz_flags(x) & LSB4; }
 
-// (a & mask) | (b & ~mask): one LOP3
-__device__ __forceinline__ uint32_t bitselect(uint32_t mask, uint32_t a, uint32_t b) { return (a & mask) | (b & ~mask); }
+// (a & mask) | (b & ~mask) as ONE LOP3 (truth table 0xE2 with the mask as the middle, immediate
+// operand).  Written in C the compiler re-associates nested selects into and/or chains with one
+// distinct mask per term, which costs three LOP3 where two (transpose) or one (nibble swap) do.
+__device__ __forceinline__ uint32_t bitselect(uint32_t mask, uint32_t a, uint32_t b)
+{
+#ifdef G2048_HOST_EMUL
+    return (a & mask) | (b & ~mask);
+#else
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(d) : "r"(a), "r"(mask), "r"(b));
+    return d;
+#endif
+}
 
 // ---- geometry -------------------------------------------------------------
 // 4x4 nibble transpose: swap inside 2x2 blocks (per half), then swap the two
