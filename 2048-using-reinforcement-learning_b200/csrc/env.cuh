@@ -155,25 +155,36 @@ __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t actio
     saturated |= gained;                                                    // bits 28.. : see rollout_saturated()
     s.score += (int32_t)p.score_delta;
     p.valid = next != prev;
-    uint32_t zl = zero_flags(next.lo), zh = zero_flags(next.hi);
-    int empty_after = __popc(zl) + __popc(zh);
-    // spawn computed unconditionally and masked by `valid` (env:191-192); a valid move always
-    // leaves an empty cell
-    Board spawned = next;
-    Spawned sp = place_tile_flags(spawned, zl, zh, max(empty_after, 1), w.pos, w.val);
-    uint32_t flag = sp.tile >> (sp.exponent - 1u);                          // bit 0 of the new tile's nibble
+    uint32_t nzl = nz_flags(next.lo), nzh = nz_flags(next.hi);             // occupancy before the spawn
+    const uint32_t zl = nzl ^ LSB4, zh = nzh ^ LSB4;
+    const int cl = __popc(zl);
+    int empty_after = cl + __popc(zh);
+    // Spawn (env:59-67) computed unconditionally and masked by `valid` (env:191-192; a valid move
+    // always leaves an empty cell).  Same selection as place_tile(): k-th empty cell in row-major
+    // order, found through the per-nibble prefix count; the lowest set bit of the comparison word
+    // is isolated with v & -v instead of ffs, which also yields the occupancy flag of the new tile,
+    // and the tile itself is flag * exponent (FMA pipe).
+    const uint32_t k = __umulhi(w.pos, (uint32_t)max(empty_after, 1));
+    const bool in_hi = k >= (uint32_t)cl;
+    const uint32_t kk = in_hi ? k - (uint32_t)cl : k;
+    const uint32_t z = in_hi ? zh : zl;
+    const uint32_t v = (z * LSB4 + (7u - kk) * LSB4) & MSB4;             // bit 3 of nibble j set <=> #empty(0..j) > kk
+    const uint32_t flag = (v & (0u - v)) >> 3;                             // bit 0 of the first such nibble (0 on a full board)
+    const uint32_t exponent = w.val < 3865470567u ? 1u : 2u;
+    const uint32_t flag_lo = in_hi ? 0u : flag, flag_hi = in_hi ? flag : 0u;
     uint32_t spawn_value = 0u, spawn_exp = 0u;
     if (p.valid) {
-        next = spawned;
+        next.lo |= flag_lo * exponent;
+        next.hi |= flag_hi * exponent;
+        nzl |= flag_lo;
+        nzh |= flag_hi;
         s.spawn_ctr += 1u;
-        zl &= sp.in_hi ? ~0u : ~flag;
-        zh &= sp.in_hi ? ~flag : ~0u;
         empty_after -= 1;
-        spawn_exp = sp.exponent;
-        spawn_value = 1u << sp.exponent;
+        spawn_exp = exponent;
+        spawn_value = 2u * exponent;                                       // 2^1 = 2*1, 2^2 = 2*2
     }
     p.total = t.total + spawn_value;
-    p.cur = next; p.nzl = zl ^ LSB4; p.nzh = zh ^ LSB4;
+    p.cur = next; p.nzl = nzl; p.nzh = nzh;
     p.empty_before = t.n_empty; p.empty_after = empty_after;
     p.highest_before = kTrackMax ? s.highest : 0u;
     p.prev_max = kTrackMax ? t.bmax : 0u;
