@@ -150,8 +150,10 @@ __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t
     ev.active = c < n_valid;
     Board b = ev.active ? Board(ws.cand[c]) : Board(0u, 0u);
     const uint32_t fe = ev.active ? ws.first[c] : 0u;
-    uint32_t zl = zero_flags(b.lo), zh = zero_flags(b.hi);
-    int n_empty = __popc(zl) + __popc(zh);
+    uint32_t nzl = nz_flags(b.lo), nzh = nz_flags(b.hi);
+    const uint32_t zl = nzl ^ LSB4, zh = nzh ^ LSB4;
+    const int cl = __popc(zl);
+    int n_empty = cl + __popc(zh);
     const bool draws = ev.active && n_empty > 0;                // agent:262-263: no draw on a full board
     const uint32_t bal = __ballot_sync(FULL, draws);
     const uint32_t ordinal = spawn_base + (uint32_t)__popc(bal & lane_lt);
@@ -159,13 +161,12 @@ __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t
     const SpawnWords w = HasSpawnRing<Scratch>::value ? ring_words(ws, ordinal)
                                                       : spawn_words(P.K, game, call, DOM_BEAM, ordinal);
     spawn_base += (uint32_t)__popc(bal);
-    Board spawned = b;
-    const Spawned sp = place_tile_flags(spawned, zl, zh, max(n_empty, 1), w.pos, w.val);
-    const uint32_t flag = sp.tile >> (sp.exponent - 1u);
+    const SpawnPick sp = pick_spawn(zl, zh, cl, n_empty, w.pos, w.val);
     if (draws) {
-        b = spawned;
-        zl &= sp.in_hi ? ~0u : ~flag;
-        zh &= sp.in_hi ? ~flag : ~0u;
+        b.lo |= sp.flag_lo * sp.exponent;
+        b.hi |= sp.flag_hi * sp.exponent;
+        nzl |= sp.flag_lo;
+        nzh |= sp.flag_hi;
         n_empty -= 1;
     }
     const uint32_t pmax = fe >> 2;                              // parent's largest exponent
@@ -173,8 +174,8 @@ __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t
     ev.first = fe & 3u;
     ev.fast = 0;
     ev.full = 0.0;
-    if (kFull) ev.full = full_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, phase, corner_table());
-    else       ev.fast = fast_eval_flags(b, zl ^ LSB4, zh ^ LSB4, n_empty, emax, corner_table());
+    if (kFull) ev.full = full_eval_flags(b, nzl, nzh, n_empty, emax, phase, corner_table());
+    else       ev.fast = fast_eval_flags(b, nzl, nzh, n_empty, emax, corner_table());
     if (ev.active) {
         ws.cand[c] = b.u64();
         ws.first[c] = (uint8_t)(ev.first | (emax << 2));

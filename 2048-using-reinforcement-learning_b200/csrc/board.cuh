@@ -388,6 +388,27 @@ __device__ __forceinline__ Spawned place_tile_flags(Board &b, uint32_t zl, uint3
     return sp;
 }
 
+// The same spawn for callers that keep OCCUPANCY flags (bit 0 of every non-empty nibble) and
+// want them updated: the lowest set bit of the comparison word is isolated with v & -v instead of
+// ffs, which directly gives the new tile's occupancy flag; the tile is flag * exponent (FMA pipe).
+// zl/zh = zero flags, cl = popc(zl), n = number of empty cells (a full board gives flag 0).
+struct SpawnPick { uint32_t flag_lo, flag_hi, exponent; };
+__device__ __forceinline__ SpawnPick pick_spawn(uint32_t zl, uint32_t zh, int cl, int n, uint32_t pos_word,
+                                                uint32_t val_word)
+{
+    const uint32_t k = __umulhi(pos_word, (uint32_t)max(n, 1));
+    const bool in_hi = k >= (uint32_t)cl;
+    const uint32_t kk = in_hi ? k - (uint32_t)cl : k;
+    const uint32_t z = in_hi ? zh : zl;
+    const uint32_t v = (z * LSB4 + (7u - kk) * LSB4) & MSB4;              // bit 3 of nibble j set <=> #empty(0..j) > kk
+    const uint32_t flag = (v & (0u - v)) >> 3;                              // bit 0 of the first such nibble
+    SpawnPick sp;
+    sp.flag_lo = in_hi ? 0u : flag;
+    sp.flag_hi = in_hi ? flag : 0u;
+    sp.exponent = val_word < 3865470567u ? 1u : 2u;
+    return sp;
+}
+
 // ---- heuristics -----------------------------------------------------------------------
 // Sum over a set of cells of 2^e (0 for an empty cell); `cells` has bit 4i set for cell i.
 __device__ __forceinline__ uint32_t tile_sum_half(uint32_t x, uint32_t cells)

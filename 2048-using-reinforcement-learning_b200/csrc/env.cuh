@@ -159,19 +159,10 @@ __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t actio
     const uint32_t zl = nzl ^ LSB4, zh = nzh ^ LSB4;
     const int cl = __popc(zl);
     int empty_after = cl + __popc(zh);
-    // Spawn (env:59-67) computed unconditionally and masked by `valid` (env:191-192; a valid move
-    // always leaves an empty cell).  Same selection as place_tile(): k-th empty cell in row-major
-    // order, found through the per-nibble prefix count; the lowest set bit of the comparison word
-    // is isolated with v & -v instead of ffs, which also yields the occupancy flag of the new tile,
-    // and the tile itself is flag * exponent (FMA pipe).
-    const uint32_t k = __umulhi(w.pos, (uint32_t)max(empty_after, 1));
-    const bool in_hi = k >= (uint32_t)cl;
-    const uint32_t kk = in_hi ? k - (uint32_t)cl : k;
-    const uint32_t z = in_hi ? zh : zl;
-    const uint32_t v = (z * LSB4 + (7u - kk) * LSB4) & MSB4;             // bit 3 of nibble j set <=> #empty(0..j) > kk
-    const uint32_t flag = (v & (0u - v)) >> 3;                             // bit 0 of the first such nibble (0 on a full board)
-    const uint32_t exponent = w.val < 3865470567u ? 1u : 2u;
-    const uint32_t flag_lo = in_hi ? 0u : flag, flag_hi = in_hi ? flag : 0u;
+    // spawn (env:59-67) computed unconditionally and masked by `valid` (env:191-192; a valid move
+    // always leaves an empty cell)
+    const SpawnPick sp = pick_spawn(zl, zh, cl, empty_after, w.pos, w.val);
+    const uint32_t exponent = sp.exponent, flag_lo = sp.flag_lo, flag_hi = sp.flag_hi;
     uint32_t spawn_value = 0u, spawn_exp = 0u;
     if (p.valid) {
         next.lo |= flag_lo * exponent;
