@@ -429,13 +429,18 @@ __device__ __forceinline__ void merge_pairs(Board b, int *pairs, int *exponent_s
 // nl / nh: occupancy flags (bit 0 of every non-empty nibble) of b.lo / b.hi
 __device__ __forceinline__ void merge_pairs_flags(Board b, uint32_t nl, uint32_t nh, int *pairs, int *exponent_sum)
 {
-    uint32_t hl = eq_flags(b.lo, b.lo >> 4) & nl & 0x01110111u;
-    uint32_t hh = eq_flags(b.hi, b.hi >> 4) & nh & 0x01110111u;
-    uint32_t vl = eq_flags(b.lo, __funnelshift_r(b.lo, b.hi, 16)) & nl;
-    uint32_t vh = eq_flags(b.hi, b.hi >> 16) & nh & 0x00001111u;
-    *pairs = __popc(hl + hh * 2u + vl * 4u + vh * 8u);       // disjoint bit classes: one popc, shifts on the FMA pipe
+    // a == b per nibble, exactly, on bit 3: adding 7 to the low three bits of a ^ b carries into bit 3
+    // iff they are non-zero (one LOP3 less per word than smearing, and the add can go to the FMA pipe)
+    auto eq8 = [](uint32_t a, uint32_t c) { uint32_t x = a ^ c; return ~(((x & 0x77777777u) + 0x77777777u) | x) & MSB4; };
+    const uint32_t nl8 = nl * 8u, nh8 = nh * 8u;                            // occupancy on bit 3
+    uint32_t hl = eq8(b.lo, b.lo >> 4) & nl8 & 0x08880888u;
+    uint32_t hh = eq8(b.hi, b.hi >> 4) & nh8 & 0x08880888u;
+    uint32_t vl = eq8(b.lo, __funnelshift_r(b.lo, b.hi, 16)) & nl8;
+    uint32_t vh = eq8(b.hi, b.hi >> 16) & nh8 & 0x00008888u;
+    *pairs = (__popc(hl) + __popc(hh)) + (__popc(vl) + __popc(vh));
     if (exponent_sum) {
         // keep the exponent of the first cell of every pair, then add all nibbles up
+        hl >>= 3; hh >>= 3; vl >>= 3; vh >>= 3;
         uint32_t a = b.lo & (hl * 15u), c = b.hi & (hh * 15u), d = b.lo & (vl * 15u), e = b.hi & (vh * 15u);
         // nibble sums: split even/odd nibbles into bytes, bytes never overflow (<= 4 * 15)
         uint32_t ev = (a & 0x0F0F0F0Fu) + (c & 0x0F0F0F0Fu) + (d & 0x0F0F0F0Fu) + (e & 0x0F0F0F0Fu);
