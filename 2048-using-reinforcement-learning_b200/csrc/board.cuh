@@ -25,13 +25,7 @@ __device__ __forceinline__ bool operator!=(const Board &a, const Board &b) { ret
 constexpr uint32_t LSB4 = 0x11111111u;   // bit 0 of every nibble
 constexpr uint32_t MSB4 = 0x88888888u;   // bit 3 of every nibble
 
-// x >> k on the FMA pipe (IMAD.HI by 2^(32-k)): the kernels are bound by the ALU pipe, which
-// executes LOP3/SHF/PRMT; moving some constant right shifts over balances the two pipes.
-#ifdef G2048_SHR_ON_FMA
-template <int k> __device__ __forceinline__ uint32_t shr(uint32_t x) { return __umulhi(x, 1u << (32 - k)); }
-#else
 template <int k> __device__ __forceinline__ uint32_t shr(uint32_t x) { return x >> k; }
-#endif
 
 // bit 4i set  <=>  nibble i of x is non-zero
 __device__ __forceinline__ uint32_t nz_flags(uint32_t x)
@@ -162,17 +156,6 @@ __device__ __forceinline__ float pow2_sum(uint32_t x, uint32_t cells, float acc)
         if ((cells >> (4 * i)) & 1u) acc = fmaf(pow2_field(x, i), 0x1p127f, acc);
     return acc;
 }
-// decode_score() on the FMA pipe: each code nibble c scores 2 << c (0 for c == 0).
-__device__ __forceinline__ uint32_t decode_score_fma(uint32_t codes)
-{
-    return 2u * (uint32_t)pow2_sum(codes, LSB4, 0.0f);
-}
-// some code nibble is 15  <=>  a merge produced 2^16 (nibble saturation)
-__device__ __forceinline__ bool codes_saturated(uint32_t codes)
-{
-    return ((((codes & 0x77777777u) + LSB4) & codes) & MSB4) != 0u;
-}
-
 // ---- pair tables of the fused rollout (512 x u32, shared memory) ------------------------------
 // Entry b < 256: sum of the two tile values whose exponents are the nibbles of byte b (0 = empty).
 // Entry 256 + c: score of the (up to two) merges a code byte c describes (2 << nibble each), plus
@@ -268,8 +251,6 @@ __device__ __forceinline__ uint32_t env_legal_mask(Board b)
 // is_game_over (env:279-288): no empty cell and no equal neighbours
 __device__ __forceinline__ bool env_game_over(Board b) { return env_legal_mask(b) == 0u; }
 // Out-of-line copy for hot loops: a full board is rare, and a call cannot be if-converted
-// into the per-step instruction stream the way the inline test is.
-static __device__ __noinline__ bool env_game_over_rare(uint32_t lo, uint32_t hi) { return env_legal_mask(Board(lo, hi)) == 0u; }
 
 // ---- counting ----------------------------------------------------------------
 __device__ __forceinline__ int count_empty(Board b) { return __popc(zero_flags(b.lo)) + __popc(zero_flags(b.hi)); }
@@ -365,27 +346,6 @@ __device__ __forceinline__ int place_tile(Board &b, uint32_t pos_word, uint32_t 
     b.lo |= in_hi ? 0u : tile;
     b.hi |= in_hi ? tile : 0u;
     return n;
-}
-
-// Same, with the zero flags of the board already known (zl/zh = zero_flags of lo/hi, n > 0
-// empties in total).  Returns the bit the new tile set in its half and whether that is `hi`.
-struct Spawned { uint32_t tile; bool in_hi; uint32_t exponent; };
-__device__ __forceinline__ Spawned place_tile_flags(Board &b, uint32_t zl, uint32_t zh, int n, uint32_t pos_word,
-                                                    uint32_t val_word)
-{
-    int cl = __popc(zl);
-    uint32_t k = __umulhi(pos_word, (uint32_t)n);
-    Spawned sp;
-    sp.in_hi = k >= (uint32_t)cl;
-    uint32_t kk = sp.in_hi ? k - (uint32_t)cl : k;
-    uint32_t z = sp.in_hi ? zh : zl;
-    uint32_t s = z * LSB4 + (7u - kk) * LSB4;         // bit 3 of nibble j set <=> #empty(0..j) > kk
-    uint32_t bit = __ffs((int)(s & MSB4)) - 1;        // 4j+3 of the first such nibble
-    sp.exponent = val_word < 3865470567u ? 1u : 2u;
-    sp.tile = sp.exponent << ((bit - 3u) & 31u);
-    b.lo |= sp.in_hi ? 0u : sp.tile;
-    b.hi |= sp.in_hi ? sp.tile : 0u;
-    return sp;
 }
 
 // The same spawn for callers that keep OCCUPANCY flags (bit 0 of every non-empty nibble) and
