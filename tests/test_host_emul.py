@@ -245,7 +245,7 @@ def test_step_kats_from_reference(emul, golden):
 
 def test_tracked_rollout_step_matches_oracle(emul, orc):
     """env_step_tracked (the fused-rollout fast path: carried empties / tile total / max exponent,
-    FMA-pipe score decode) against the oracle, reward sums included."""
+    pair-table merge score and edge sum, closed-form reset) against the oracle, reward sums included."""
     n, steps = 64, 1500
     ob = np.zeros((n, 16), np.int32); osc = np.zeros(n, np.int64); ohi = np.zeros(n, np.int32)
     octr = np.zeros(n, np.uint32); ors = np.zeros(n, np.float64); oep = np.zeros(n, np.int32)
