@@ -103,6 +103,7 @@ class BatchedBeamSearch:
         if self.device.type != "cuda":
             raise _lib.G2048Error("BatchedBeamSearch needs a CUDA device (no CPU fallback)")
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)            # "cuda" -> "cuda:<current>": tensors report an index
         _lib.use_device(self.index)
         self.beam_width, self.search_depth = int(beam_width), int(search_depth)
         self.early, self.mid = int(early_game_threshold), int(mid_game_threshold)
@@ -125,8 +126,17 @@ class BatchedBeamSearch:
         Returns dict(action uint8[G], prob float32[G], best_score float64[G], nodes int32[G])."""
         t = self.torch
         g = boards.numel()
+        # the C ABI takes raw device pointers: refuse anything it would misread
+        if boards.device != self.device or boards.dtype not in (t.int64, t.uint64):
+            raise ValueError(f"boards must be an int64 tensor on {self.device}, got {boards.dtype} on {boards.device}")
+        if legal is not None and (legal.device != self.device or legal.dtype != t.uint8 or legal.numel() != g):
+            raise ValueError("legal must be a uint8 tensor with one mask per board, on the same device")
+        if t.is_tensor(call) and (call.device != self.device or call.dtype not in (t.int32, t.uint32) or call.numel() != g):
+            raise ValueError("call must be an int or an int32 tensor with one entry per board, on the same device")
         if out is None:
             out = self.new_outputs(g)
+        elif any(out[k].numel() != g or out[k].device != self.device for k in ("action", "prob", "best_score", "nodes")):
+            raise ValueError("out must come from new_outputs(G) with G = boards.numel()")
         call_ptr, call0 = (call.contiguous().data_ptr(), 0) if t.is_tensor(call) else (0, int(call))
         _lib.check(_lib.use_device(self.index).g2048_beam_search(
             boards.contiguous().data_ptr(), 0 if legal is None else legal.contiguous().data_ptr(), call_ptr, call0,

@@ -157,6 +157,7 @@ class BatchedGame2048Env:
         if self.device.type != "cuda":
             raise _lib.G2048Error("BatchedGame2048Env needs a CUDA device (no CPU fallback)")
         self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)            # "cuda" -> "cuda:<current>": tensors report an index
         self.lib = _lib.use_device(self.index)
         self.n = int(num_envs)
         self.seed = int(seed) & (2**64 - 1)
@@ -217,10 +218,15 @@ class BatchedGame2048Env:
         envs whose game this step ended (`done` still flags them; `episodes` counts them).
         """
         t = self.torch
+        if actions.device != self.device or actions.numel() != self.n:
+            raise ValueError(f"actions must hold one action per env ({self.n}) on {self.device}")
         if actions.dtype != t.uint8:
             actions = actions.to(t.uint8)
         if not actions.is_contiguous():
             actions = actions.contiguous()
+        if inject is not None and (inject.device != self.device or inject.dtype not in (t.int32, t.uint32)
+                                   or inject.numel() != 2 * self.n):
+            raise ValueError("inject must be an int32/uint32[N, 2] tensor of raw spawn words on the same device")
         inj = 0 if inject is None else inject.contiguous().data_ptr()
         p = self._ptrs
         if auto_reset:

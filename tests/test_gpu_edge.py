@@ -148,3 +148,26 @@ def test_wide_beams_vs_oracle(orc, W, D, n):
             assert list(out["milestone"][i]) == list(r.milestone_move)
     a1, _ = G.BeamSearchAgent(beam_width=W, search_depth=D, seed=SEED).get_action(vals[0])
     assert 0 <= a1 <= 3
+
+
+def test_batched_wrappers_refuse_tensors_the_abi_would_misread():
+    """The C ABI takes raw device pointers, so the PyTorch wrappers check device, dtype and length
+    before handing them over; `device="cuda"` (no index) is accepted."""
+    import torch
+    env = G.BatchedGame2048Env(64, "cuda", seed=1)
+    env.reset()
+    env.step(torch.zeros(64, dtype=torch.uint8, device="cuda"))
+    env.step(torch.zeros(64, dtype=torch.int64, device="cuda"))          # other integer dtypes are converted
+    search = G.BatchedBeamSearch(5, 5, "cuda", seed=1)
+    out = search.get_actions(env.boards)
+    assert out["action"].numel() == 64
+    for bad in (lambda: env.step(torch.zeros(63, dtype=torch.uint8, device="cuda")),
+                lambda: env.step(torch.zeros(64, dtype=torch.uint8)),
+                lambda: env.step(torch.zeros(64, dtype=torch.uint8, device="cuda"),
+                                 inject=torch.zeros(64, dtype=torch.int32, device="cuda")),
+                lambda: search.get_actions(env.boards.to(torch.int32)),
+                lambda: search.get_actions(env.boards.cpu()),
+                lambda: search.get_actions(env.boards, legal=torch.zeros(3, dtype=torch.uint8, device="cuda")),
+                lambda: search.get_actions(env.boards, out=search.new_outputs(5))):
+        with pytest.raises(ValueError):
+            bad()
