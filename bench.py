@@ -346,8 +346,11 @@ def run_ours(args):
     from oracle import pyoracle as O
     threads = O.max_threads()
     cpu_n, cpu_steps, cpu_roots = 16384, 1500, 16384         # ~15-25 core-seconds in total
-    cpu_value = cpu_env_sample(O, cpu_n, cpu_steps, threads)
-    cpu_beam = cpu_beam_sample(O, cpu_roots, threads)
+    if world == 1:                                           # the CPU arm is timed at N=1 only
+        cpu_value = cpu_env_sample(O, cpu_n, cpu_steps, threads)
+        cpu_beam = cpu_beam_sample(O, cpu_roots, threads)
+    else:
+        cpu_value = cpu_beam = None
 
     peak, peak_src = measured_peaks()
     achieved = BYTES_PER_STEP * (n * env_steps) / (kernel_ms * 1e-3) / 1e9       # per launch, one rank
@@ -386,7 +389,8 @@ def run_ours(args):
                                "peak_source": INT32_PEAKS["source"]},
                   "measured_issue_peak": INT32_PEAKS["alu_plus_fma_warp_inst_per_s"]},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{cpu_n} envs x {cpu_steps} steps, oracle/orc2048.c on {threads} threads"},
+                         "sample": f"{cpu_n} envs x {cpu_steps} steps, oracle/orc2048.c on {threads} threads"
+                                   if world == 1 else "not timed at N > 1 (see the N=1 line)"},
         "per_step_api": {"value": per_step_api_value, "unit": UNIT,
                          "note": "g2048_env_step, one launch per env step, device-resident tensors",
                          "cuda_graph": {"value": per_step_graph_value, "unit": UNIT,
@@ -400,7 +404,8 @@ def run_ours(args):
                               "frac": beam_achieved / peak, "traffic": NCU_BEAM["dram_bytes_per_launch"],
                               "kernel": "beam_search_kernel", "ncu": NCU_BEAM},
                  "cpu_baseline": {"value": cpu_beam, "unit": "nodes/s", "cores": threads, "kind": "port",
-                                  "sample": f"{cpu_roots} synthetic roots, oracle/orc2048.c on {threads} threads"}},
+                                  "sample": f"{cpu_roots} synthetic roots, oracle/orc2048.c on {threads} threads"
+                                            if world == 1 else "not timed at N > 1 (see the N=1 line)"}},
         "highest_tile_histogram": {str(1 << e): int(c) for e, c in enumerate(hist.tolist()) if c},
     }
     print(json.dumps(line))
