@@ -211,4 +211,47 @@ __device__ __forceinline__ bool full_board_game_over(Board b)
     return (z & MSB4) == 0u;                                                // no equal neighbours anywhere
 }
 
+// The fused rollout's step loop for one env (env_rollout_kernel; the host emulation runs the same
+// code).  Software-pipelined: step_move(t) and step_reward(t-1) share a basic block.  Actions: one
+// Philox block of the action stream holds 64 two-bit actions (16 per word), so the loop nest is
+// block -> word -> step and a step pays one AND and one shift for its action.  A finished game is
+// reset right after the step that ended it.  Returns whether some merge saturated a nibble.
+template <bool kTrackMax>
+__device__ __forceinline__ bool rollout_steps(TrackedEnv &e, int32_t steps, uint32_t t0, const PhiloxKey &K,
+                                              uint32_t game, const uint16_t *row, const uint8_t *code,
+                                              const uint32_t *pairs, double &rsum, int32_t &episodes)
+{
+    if (steps <= 0) return false;
+    uint32_t t = t0;
+    const uint32_t end = t0 + (uint32_t)steps;
+    uint32_t saturated = 0u;
+    bool full, have = false;
+    PendingReward pend;
+    while (t < end) {
+        const Philox4 act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, K);
+        const uint32_t block_end = min(end, (t | 63u) + 1u);
+        while (t < block_end) {
+            const uint32_t sel = (t >> 4) & 3u;
+            uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
+            word >>= 2u * (t & 15u);
+            const uint32_t word_end = min(block_end, (t | 15u) + 1u);
+            if (!have) {                                     // first step of the launch: nothing to overlap with yet
+                pend = step_move<kTrackMax>(e, word & 3u, row, code, pairs, K, game, saturated, full);
+                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, K, game); }
+                word >>= 2; ++t; have = true;
+            }
+            for (; t < word_end; ++t) {
+                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, pairs, K, game, saturated, full);
+                word >>= 2;
+                rsum = __dadd_rn(rsum, step_reward(pend, pairs));      // float64 sum stays in step order
+                pend = cur;
+                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, K, game); }
+            }
+        }
+    }
+    rsum = __dadd_rn(rsum, step_reward(pend, pairs));
+    if (!kTrackMax) e.s.highest = max_exponent(e.s.board);
+    return rollout_saturated(saturated);
+}
+
 }  // namespace g2048

@@ -167,47 +167,6 @@ struct RolloutArgs {
 #endif
 constexpr int kRolloutThreads = G2048_ROLLOUT_THREADS;
 
-// Software-pipelined step loop: step_move(t) and step_reward(t-1) share a basic block.
-// Actions: one Philox block of the action stream holds 64 two-bit actions (16 per word), so the
-// loop nest is block -> word -> step and a step pays one AND and one shift for its action.
-template <bool kTrackMax>
-__device__ __forceinline__ void rollout_steps(TrackedEnv &e, const RolloutArgs &a, uint32_t game, const uint16_t *row,
-                                              const uint8_t *code, const uint32_t *pairs, double &rsum,
-                                              int32_t &episodes)
-{
-    if (a.steps <= 0) return;
-    uint32_t t = a.t0;
-    const uint32_t end = a.t0 + (uint32_t)a.steps;
-    uint32_t saturated = 0u;
-    bool full, have = false;
-    PendingReward pend;
-    while (t < end) {
-        const Philox4 act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, a.K);
-        const uint32_t block_end = min(end, (t | 63u) + 1u);
-        while (t < block_end) {
-            const uint32_t sel = (t >> 4) & 3u;
-            uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
-            word >>= 2u * (t & 15u);
-            const uint32_t word_end = min(block_end, (t | 15u) + 1u);
-            if (!have) {                                     // first step of the launch: nothing to overlap with yet
-                pend = step_move<kTrackMax>(e, word & 3u, row, code, pairs, a.K, game, saturated, full);
-                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, a.K, game); }
-                word >>= 2; ++t; have = true;
-            }
-            for (; t < word_end; ++t) {
-                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, pairs, a.K, game, saturated, full);
-                word >>= 2;
-                rsum = __dadd_rn(rsum, step_reward(pend, pairs));      // float64 sum stays in step order
-                pend = cur;
-                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, a.K, game); }
-            }
-        }
-    }
-    rsum = __dadd_rn(rsum, step_reward(pend, pairs));
-    if (rollout_saturated(saturated)) atomicAdd(a.overflow, 1ull);
-    if (!kTrackMax) e.s.highest = max_exponent(e.s.board);
-}
-
 __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(RolloutArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -229,8 +188,10 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(Rollout
         // highest > board max only if the caller poked it (env:229): such warps take the
         // variant that maintains both per step; everybody else skips that bookkeeping.
         const bool poked = __any_sync(__activemask(), e.s.highest > e.bmax);
-        if (poked) rollout_steps<true>(e, a, game, row, code, pairs, rsum, episodes);
-        else       rollout_steps<false>(e, a, game, row, code, pairs, rsum, episodes);
+        bool saturated;
+        if (poked) saturated = rollout_steps<true>(e, a.steps, a.t0, a.K, game, row, code, pairs, rsum, episodes);
+        else       saturated = rollout_steps<false>(e, a.steps, a.t0, a.K, game, row, code, pairs, rsum, episodes);
+        if (saturated) atomicAdd(a.overflow, 1ull);
         a.boards[i] = e.s.board.u64();
         a.score[i] = e.s.score;
         a.highest[i] = (uint8_t)e.s.highest;

@@ -180,6 +180,18 @@ static void rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, u
     TrackedEnv t; t.s.board = Board(e->board); t.s.score = e->score; t.s.highest = e->highest; t.s.spawn_ctr = e->spawn_ctr;
     track(t);
     const PhiloxKey K = make_philox_key(seed);
+    // the kernel's own step loop (env.cuh): action words, software pipeline, reset points
+    if (rollout_steps<kTrackMax>(t, steps, t0, K, game, g_row, g_code, g_pairs, *reward_sum, *episodes)) g_overflow += 1;
+    e->board = t.s.board.u64(); e->score = t.s.score; e->highest = t.s.highest; e->spawn_ctr = t.s.spawn_ctr;
+}
+// the same transitions one step at a time with the action recomputed per step and both game-over
+// tests compared: an independent walk through what rollout_steps() does in its loop nest
+template <bool kTrackMax>
+static void rollout_stepwise(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uint32_t game, double *reward_sum, int *episodes)
+{
+    TrackedEnv t; t.s.board = Board(e->board); t.s.score = e->score; t.s.highest = e->highest; t.s.spawn_ctr = e->spawn_ctr;
+    track(t);
+    const PhiloxKey K = make_philox_key(seed);
     uint32_t saturated = 0;
     for (int i = 0; i < steps; ++i) {
         bool full;
@@ -198,6 +210,11 @@ void emul_rollout_tracked(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uin
 {
     if (track_max) rollout_tracked<true>(e, steps, t0, seed, game, reward_sum, episodes);
     else rollout_tracked<false>(e, steps, t0, seed, game, reward_sum, episodes);
+}
+void emul_rollout_stepwise(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, uint32_t game, double *reward_sum, int *episodes, int track_max)
+{
+    if (track_max) rollout_stepwise<true>(e, steps, t0, seed, game, reward_sum, episodes);
+    else rollout_stepwise<false>(e, steps, t0, seed, game, reward_sum, episodes);
 }
 unsigned long long emul_overflow(void) { return g_overflow; }
 

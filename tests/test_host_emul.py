@@ -64,6 +64,7 @@ def emul():
     L.emul_env_reset.argtypes = [C.POINTER(EmulEnv), u64, u32]
     L.emul_env_step.argtypes = [C.POINTER(EmulEnv), u32, C.POINTER(u32), u64, u32, C.POINTER(EmulStep)]
     L.emul_rollout_tracked.argtypes = [C.POINTER(EmulEnv), C.c_int, u32, u64, u32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    L.emul_rollout_stepwise.argtypes = L.emul_rollout_tracked.argtypes
     L.emul_row.argtypes = [u32]; L.emul_row.restype = u32
     L.emul_code.argtypes = [u32]; L.emul_code.restype = u32
     L.emul_overflow.restype = C.c_ulonglong
@@ -263,7 +264,35 @@ def test_tracked_rollout_step_matches_oracle(emul, orc):
         emul.emul_rollout_tracked(C.byref(e), steps, 3, SEED, 700 + i, C.byref(rs), C.byref(ep), i & 1)
         assert e.board == packing.pack_board(ob[i]) and e.score == osc[i] and e.spawn_ctr == octr[i]
         assert rs.value == ors[i] and ep.value == oep[i] and (1 << e.highest) == ohi[i]
+        # the one-step-at-a-time walk (action recomputed per step, both game-over tests) agrees too
+        e2 = EmulEnv(packing.pack_board(start[i]), 0, int(start_hi[i]).bit_length() - 1, 2)
+        rs2 = C.c_double(0.0); ep2 = C.c_int(0)
+        emul.emul_rollout_stepwise(C.byref(e2), steps, 3, SEED, 700 + i, C.byref(rs2), C.byref(ep2), i & 1)
+        assert (e2.board, e2.score, e2.spawn_ctr, e2.highest, rs2.value, ep2.value) == \
+               (e.board, e.score, e.spawn_ctr, e.highest, rs.value, ep.value)
     assert oep.sum() > 0
+
+
+def test_rollout_loop_nest_offsets(emul, orc):
+    """rollout_steps() (the kernel's loop: 64-action Philox blocks, 16-action words, software
+    pipeline) started at every kind of offset and length against the oracle."""
+    cases = [(0, 1), (1, 1), (15, 2), (16, 1), (63, 2), (64, 17), (5, 59), (62, 131), (1000, 64), (4095, 300)]
+    for ci, (t0, steps) in enumerate(cases):
+        n = 6
+        ob = np.zeros((n, 16), np.int32); osc = np.zeros(n, np.int64); ohi = np.zeros(n, np.int32)
+        octr = np.zeros(n, np.uint32); ors = np.zeros(n, np.float64); oep = np.zeros(n, np.int32)
+        for i in range(n):
+            env = orc.Env(SEED, 900 + 10 * ci + i, ctor_reset=False)
+            env.reset()
+            ob[i] = env.board; ohi[i] = env.s.highest_tile; octr[i] = env.s.spawn_ctr
+        start = ob.copy()
+        orc.rollout(ob, osc, ohi, octr, ors, oep, steps, t0, SEED, 900 + 10 * ci)
+        for i in range(n):
+            e = EmulEnv(packing.pack_board(start[i]), 0, int(start[i].max()).bit_length() - 1, 2)
+            rs = C.c_double(0.0); ep = C.c_int(0)
+            emul.emul_rollout_tracked(C.byref(e), steps, t0, SEED, 900 + 10 * ci + i, C.byref(rs), C.byref(ep), 0)
+            assert e.board == packing.pack_board(ob[i]) and e.score == osc[i] and e.spawn_ctr == octr[i], (t0, steps)
+            assert rs.value == ors[i] and ep.value == oep[i], (t0, steps)
 
 
 def test_ppo_features_bit_exact(emul, orc):
