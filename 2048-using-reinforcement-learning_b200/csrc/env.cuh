@@ -93,18 +93,22 @@ __device__ __forceinline__ void track(TrackedEnv &t)
 }
 
 // env_reset() + track() for the fused rollout.  Same two spawns; a fresh board is known without
-// looking at it (14 empty cells, two tiles of exponent 1 or 2), the k-th empty cell of an empty
-// board is cell k, and one Philox block serves both spawns when the spawn counter is even.
-__device__ __forceinline__ void reset_tracked(TrackedEnv &t, const PhiloxKey &K, uint32_t game)
+// looking at it (14 empty cells, two tiles of exponent 1 or 2) and the k-th empty cell of an empty
+// board is cell k.  The reset draws spawns i and i+1; it also hands back the words of spawn i+2
+// (`next0`) and, when i is even, of spawn i+3 (`next1`), which sit in the second block it computes:
+// the caller's spawn-word schedule (rollout_steps) continues from them.
+__device__ __forceinline__ void reset_tracked(TrackedEnv &t, const PhiloxKey &K, uint32_t game, SpawnWords &next0,
+                                              SpawnWords &next1)
 {
     EnvState &s = t.s;
     const uint32_t i = s.spawn_ctr;
     const Philox4 p = philox4x32_10(i >> 1, 0u, game, DOM_ENV, K);
-    uint32_t pos0 = p.w[0], val0 = p.w[1], pos1 = p.w[2], val1 = p.w[3];
-    if (i & 1u) {
-        const Philox4 q = philox4x32_10((i >> 1) + 1u, 0u, game, DOM_ENV, K);
-        pos0 = p.w[2]; val0 = p.w[3]; pos1 = q.w[0]; val1 = q.w[1];
-    }
+    const Philox4 q = philox4x32_10((i >> 1) + 1u, 0u, game, DOM_ENV, K);
+    const bool odd = (i & 1u) != 0u;
+    const uint32_t pos0 = odd ? p.w[2] : p.w[0], val0 = odd ? p.w[3] : p.w[1];
+    const uint32_t pos1 = odd ? q.w[0] : p.w[2], val1 = odd ? q.w[1] : p.w[3];
+    next0.pos = odd ? q.w[2] : q.w[0]; next0.val = odd ? q.w[3] : q.w[1];
+    next1.pos = q.w[2]; next1.val = q.w[3];
     const uint32_t e0 = val0 < 3865470567u ? 1u : 2u, e1 = val1 < 3865470567u ? 1u : 2u;
     const uint32_t c0 = pos0 >> 28;                                  // (pos * 16) >> 32
     const uint32_t k1 = __umulhi(pos1, 15u);
@@ -137,17 +141,15 @@ struct PendingReward {
     bool valid;
 };
 
+// `w`: the words of spawn number s.spawn_ctr of the env stream (used iff the move is valid).
 template <bool kTrackMax>
 __device__ __forceinline__ PendingReward step_move(TrackedEnv &t, uint32_t action, const uint16_t *row,
-                                                   const uint8_t *code, const uint32_t *pairs, const PhiloxKey &K,
-                                                   uint32_t game, uint32_t &saturated, bool &full)
+                                                   const uint8_t *code, const uint32_t *pairs, const SpawnWords &w,
+                                                   uint32_t &saturated, bool &full)
 {
     PendingReward p;
     EnvState &s = t.s;
     const Board prev = s.board;
-    // the spawn words depend only on the counter: issue the Philox block first so that it
-    // overlaps the table lookups (it runs on the FMA pipe, the move on the ALU pipe)
-    const SpawnWords w = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr);
     const Board line = to_line(prev, action);
     Board next = from_line(move_left<true>(line, row), action);
     const uint32_t gained = merge_score_pairs<true>(line, code, pairs);      // action is always 0..3 here
@@ -212,21 +214,53 @@ __device__ __forceinline__ bool full_board_game_over(Board b)
 }
 
 // The fused rollout's step loop for one env (env_rollout_kernel; the host emulation runs the same
-// code).  Software-pipelined: step_move(t) and step_reward(t-1) share a basic block.  Actions: one
-// Philox block of the action stream holds 64 two-bit actions (16 per word), so the loop nest is
-// block -> word -> step and a step pays one AND and one shift for its action.  A finished game is
-// reset right after the step that ended it.  Returns whether some merge saturated a nibble.
+// code).  A finished game is reset right after the step that ended it.  Returns whether some merge
+// saturated a nibble.
+//  * Software-pipelined: step_move(t) and step_reward(t-1) share a basic block.
+//  * Actions: one Philox block of the action stream holds 64 two-bit actions (16 per word), so the
+//    loop nest is block -> word -> step and a step pays one AND and one shift for its action.
+//  * Spawn words: a Philox block of the env stream serves two spawns, and a step uses at most one,
+//    so blocks are fetched on a fixed schedule that is the same for every lane of a warp: one block
+//    per PAIR of steps (t even, t+1).  With c = spawn counter at the pair's start the block is
+//    (c+1) >> 1: for even c it holds spawns c, c+1; for odd c it holds c+1, c+2 and spawn c is the
+//    word pair `cache` left over from the block before.  Whatever the two steps consume (0, 1 or 2
+//    spawns), the counter they leave is covered again: if it is odd, `cache` is set to its spawn.
 template <bool kTrackMax>
 __device__ __forceinline__ bool rollout_steps(TrackedEnv &e, int32_t steps, uint32_t t0, const PhiloxKey &K,
                                               uint32_t game, const uint16_t *row, const uint8_t *code,
                                               const uint32_t *pairs, double &rsum, int32_t &episodes)
 {
     if (steps <= 0) return false;
-    uint32_t t = t0;
     const uint32_t end = t0 + (uint32_t)steps;
     uint32_t saturated = 0u;
-    bool full, have = false;
-    PendingReward pend;
+    bool full;
+    // the cache of an odd counter at entry: second word pair of block c >> 1
+    const Philox4 entry = philox4x32_10(e.s.spawn_ctr >> 1, 0u, game, DOM_ENV, K);
+    SpawnWords cache = {entry.w[2], entry.w[3]}, q0, q1, q2;
+    // q0, q1, q2 := the spawns c, c+1, c+2 as far as block (c+1) >> 1 and the cache give them
+    auto fetch = [&]() {
+        const uint32_t c = e.s.spawn_ctr;
+        const Philox4 p = philox4x32_10((c + 1u) >> 1, 0u, game, DOM_ENV, K);
+        const bool odd = (c & 1u) != 0u;
+        q0.pos = odd ? cache.pos : p.w[0]; q0.val = odd ? cache.val : p.w[1];
+        q1.pos = odd ? p.w[0] : p.w[2];    q1.val = odd ? p.w[1] : p.w[3];
+        q2.pos = p.w[2];                   q2.val = p.w[3];
+    };
+    // game over -> reset; the stream continues with the words the reset hands back.  They are filed
+    // as "the spawn after one more" (q1) and "after two more" (q2) and the step is counted as having
+    // consumed one (`a`), which is where a step that follows in the same pair and the cache rule look
+    // for them.  (A reset normally follows a valid move; a caller may also hand in a dead board.)
+    bool a;
+    auto reset_if_over = [&]() {
+        if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, K, game, q1, q2); a = true; }
+    };
+    // first step of the launch: no pending reward to overlap with yet
+    fetch();
+    PendingReward pend = step_move<kTrackMax>(e, random_action(K, game, t0), row, code, pairs, q0, saturated, full);
+    a = pend.valid;
+    reset_if_over();
+    cache = a ? q1 : q0;
+    uint32_t t = t0 + 1u;
     while (t < end) {
         const Philox4 act = philox4x32_10(t >> 6, 0u, game, DOM_ACTION, K);
         const uint32_t block_end = min(end, (t | 63u) + 1u);
@@ -235,17 +269,30 @@ __device__ __forceinline__ bool rollout_steps(TrackedEnv &e, int32_t steps, uint
             uint32_t word = sel == 0 ? act.w[0] : sel == 1 ? act.w[1] : sel == 2 ? act.w[2] : act.w[3];
             word >>= 2u * (t & 15u);
             const uint32_t word_end = min(block_end, (t | 15u) + 1u);
-            if (!have) {                                     // first step of the launch: nothing to overlap with yet
-                pend = step_move<kTrackMax>(e, word & 3u, row, code, pairs, K, game, saturated, full);
-                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, K, game); }
-                word >>= 2; ++t; have = true;
-            }
-            for (; t < word_end; ++t) {
-                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, pairs, K, game, saturated, full);
-                word >>= 2;
+            while (t < word_end) {
+                fetch();
+                PendingReward cur = step_move<kTrackMax>(e, word & 3u, row, code, pairs, q0, saturated, full);
                 rsum = __dadd_rn(rsum, step_reward(pend, pairs));      // float64 sum stays in step order
                 pend = cur;
-                if (full && full_board_game_over(e.s.board)) { ++episodes; reset_tracked(e, K, game); }
+                a = cur.valid;
+                reset_if_over();
+                if ((t & 1u) || t + 1u == word_end) {                  // lone step: before an even t, or the last one
+                    cache = a ? q1 : q0;
+                    word >>= 2; ++t;
+                    continue;
+                }
+                const SpawnWords wb = a ? q1 : q0;                      // second step of the pair
+                cur = step_move<kTrackMax>(e, (word >> 2) & 3u, row, code, pairs, wb, saturated, full);
+                rsum = __dadd_rn(rsum, step_reward(pend, pairs));
+                pend = cur;
+                const bool b = cur.valid;
+                cache = a ? (b ? q2 : q1) : (b ? q1 : q0);             // spawn number (c + consumed)
+                if (full && full_board_game_over(e.s.board)) {         // reset after the second step: its
+                    SpawnWords unused;                                 // next spawn is the new cache
+                    ++episodes;
+                    reset_tracked(e, K, game, cache, unused);
+                }
+                word >>= 4; t += 2;
             }
         }
     }

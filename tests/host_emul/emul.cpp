@@ -195,11 +195,12 @@ static void rollout_stepwise(EmulEnv *e, int steps, uint32_t t0, uint64_t seed, 
     uint32_t saturated = 0;
     for (int i = 0; i < steps; ++i) {
         bool full;
-        PendingReward p = step_move<kTrackMax>(t, random_action(K, game, t0 + i), g_row, g_code, g_pairs, K, game, saturated, full);
+        const SpawnWords w = spawn_words(K, game, 0u, DOM_ENV, t.s.spawn_ctr);       // one block per step, no schedule
+        PendingReward p = step_move<kTrackMax>(t, random_action(K, game, t0 + i), g_row, g_code, g_pairs, w, saturated, full);
         *reward_sum += step_reward(p, g_pairs);
         bool done = full && full_board_game_over(t.s.board);
         if (full && done != env_game_over(t.s.board)) __builtin_trap();   // the two game-over tests must agree
-        if (done) { ++*episodes; reset_tracked(t, K, game); }
+        if (done) { SpawnWords n0, n1; ++*episodes; reset_tracked(t, K, game, n0, n1); }
     }
     g_overflow += rollout_saturated(saturated) ? 1u : 0u;
     if (!kTrackMax) t.s.highest = max_exponent(t.s.board);

@@ -295,6 +295,25 @@ def test_rollout_loop_nest_offsets(emul, orc):
             assert rs.value == ors[i] and ep.value == oep[i], (t0, steps)
 
 
+def test_rollout_from_dead_and_full_boards(emul, orc):
+    """A caller may hand the rollout a board that is already dead (the first step is then an invalid
+    move followed by the reset) or full but alive; both against the oracle, odd and even counters."""
+    dead = np.array([2, 4, 2, 4, 4, 2, 4, 2, 2, 4, 2, 4, 4, 2, 4, 2], np.int32)
+    alive = dead.copy(); alive[15] = 4                       # one vertical pair to merge
+    for bi, board in enumerate((dead, alive)):
+        for ctr in (0, 1, 6, 7):
+            for t0, steps in ((0, 1), (0, 2), (1, 2), (2, 3), (7, 40)):
+                ob = board[None].copy(); osc = np.array([12], np.int64); ohi = np.array([4], np.int32)
+                octr = np.array([ctr], np.uint32); ors = np.zeros(1); oep = np.zeros(1, np.int32)
+                orc.rollout(ob, osc, ohi, octr, ors, oep, steps, t0, SEED, 77 + bi)
+                e = EmulEnv(packing.pack_board(board), 12, 2, ctr)
+                rs = C.c_double(0.0); ep = C.c_int(0)
+                emul.emul_rollout_tracked(C.byref(e), steps, t0, SEED, 77 + bi, C.byref(rs), C.byref(ep), 0)
+                assert e.board == packing.pack_board(ob[0]) and e.score == osc[0] and e.spawn_ctr == octr[0], (bi, ctr, t0, steps)
+                assert rs.value == ors[0] and ep.value == oep[0], (bi, ctr, t0, steps)
+    assert oep[0] >= 0
+
+
 def test_ppo_features_bit_exact(emul, orc):
     for b in boards_for_test(orc):
         if b.max() == 0:
