@@ -41,10 +41,10 @@ BEAM_W, BEAM_D, BEAM_ROOTS = 20, 40, 10000
 SLEEP_CYCLES = 1_000_000     # torch.cuda._sleep before each timed launch (see run_ours)
 # From the committed ncu capture of the same command (profiles/ncu_summary_r01.md): executed warp
 # instructions per warp-step of env_rollout_kernel, its DRAM traffic per launch, and pipe utilisation.
-NCU_ROLLOUT = {"warp_inst_per_warp_step": 345.7, "dram_bytes_per_launch": 2141952, "alu_pipe_pct_of_peak": 65.3,
-               "issue_active_pct": 67.6, "fma_pipe_pct_of_peak": 14.5, "source": "profiles/ncu_summary_r01.md",
+NCU_ROLLOUT = {"warp_inst_per_warp_step": 336.5, "dram_bytes_per_launch": 2157824, "alu_pipe_pct_of_peak": 67.4,
+               "issue_active_pct": 69.6, "fma_pipe_pct_of_peak": 15.4, "source": "profiles/ncu_summary_r01.md",
                # ALU-pipe instructions per warp-step = pct_of_peak x 0.5 inst/clk/SMSP x SMSP cycles per warp-step
-               "alu_warp_inst_per_warp_step": 189.4}
+               "alu_warp_inst_per_warp_step": 186.3}
 # Measured pipe peaks of this pool's B200 (profiles/int32_peak.cu -> profiles/int32_peak_r01.json): a pure
 # LOP3/SHF/PRMT stream sustains 5.79e11 warp-inst/s (0.5 per clock per scheduler), an ALU+IMAD mix 1.13e12.
 INT32_PEAKS = {"alu_pipe_warp_inst_per_s": 5.79e11, "alu_plus_fma_warp_inst_per_s": 1.13e12,
