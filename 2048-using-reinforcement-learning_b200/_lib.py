@@ -46,6 +46,7 @@ _SIGNATURES = {
     "g2048_last_error": ([], C.c_char_p),
     "g2048_overflow_count": ([C.POINTER(_u64), _vp], C.c_int),
     "g2048_launch_count": ([], _u64),
+    "g2048_set_tuning": ([C.c_int, C.c_int], C.c_int),
     "g2048_pack": ([_vp, _vp, _i64, _vp], C.c_int),
     "g2048_unpack": ([_vp, _vp, _i64, _vp], C.c_int),
     "g2048_observe": ([_vp, _vp, _i64, _vp], C.c_int),

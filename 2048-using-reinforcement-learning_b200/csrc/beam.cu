@@ -444,6 +444,46 @@ __global__ void __launch_bounds__(kBeamThreads, 1) beam_search_kernel(BeamArgs a
     }
 }
 
+}  // namespace g2048
+#include "team.cuh"
+namespace g2048 {
+
+// Scratch of team `quad` of the block: it aliases the WarpScratch slots of the team's four warps.
+__device__ __forceinline__ TeamScratch &team_scratch(uint8_t *smem, int quad)
+{
+    return *reinterpret_cast<TeamScratch *>(smem + kRowTableBytes + (size_t)quad * kTeamWarps * sizeof(WarpScratch));
+}
+
+// Small batches (fewer roots than the GPU has warp slots for): one TEAM of four warps per root, so a
+// single get_action takes ~1/4 of the one-warp latency.  blockDim.x is a multiple of 128.
+__global__ void __launch_bounds__(kBeamThreads, 1) beam_search_team_kernel(BeamArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int quad = threadIdx.x >> 7;
+    TeamScratch &ts = team_scratch(smem, quad);
+    const int bar = 1 + quad;
+    const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
+    for (;;) {
+        if (leader) ts.next_item = atomicAdd(a.work, 1u);
+        team_barrier(bar);
+        const unsigned int i = ts.next_item;
+        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
+        if ((int64_t)i >= a.n) break;
+        Board root(a.roots[i]);
+        int legal = a.legal ? (int)a.legal[i] : -1;
+        uint32_t call = a.call ? a.call[i] : a.call0;
+        BeamResult r = beam_search_team(root, legal, a.P, a.game0 + (uint32_t)i, call, row, ts, bar);
+        if (leader) {
+            a.action[i] = (uint8_t)r.action;
+            if (a.prob) a.prob[i] = r.prob;
+            if (a.best) a.best[i] = r.best;
+            if (a.nodes) a.nodes[i] = r.nodes;
+        }
+    }
+}
+
 // ---- wide beams (33 <= beam_width <= 128) ---------------------------------------------------------
 // Same algorithm with the beam and up to 512 candidates per level in shared memory and the stable
 // top-k done by counting (rank = #candidates ahead; score as float64 on every level, ties by
@@ -600,7 +640,19 @@ struct GameState {
     long long nodes;
     int32_t score, moves, valid, invalid;
     uint32_t highest, spawn_ctr, index;      // index = position in the caller's output arrays
+    int32_t streak;                          // consecutive invalid moves so far
     int32_t ms[8];
+};
+
+// Device-side counters of one g2048_play_games call (per-launch scratch, zeroed before the kernels).
+struct GameCounters {
+    unsigned int work;            // queue head of the one-warp kernel
+    unsigned int finished;        // games written or handed to the stall breaker
+    unsigned int tail_count;      // games handed to the team kernel
+    unsigned int team_work;       // queue head of the team kernel
+    unsigned int pending_count;   // stalled games handed to the stall breaker
+    unsigned int finish_work;     // queue head of the stall breaker
+    unsigned int pad[2];
 };
 
 struct GamesArgs {
@@ -608,9 +660,10 @@ struct GamesArgs {
     int32_t *score; uint8_t *highest; int32_t *moves; int32_t *valid; int32_t *invalid;
     int32_t *milestone; int64_t *nodes; uint64_t *final_board;
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
-    unsigned int *work;            // queue head of this launch
-    GameState *pending;            // stalled games handed to finish_games_kernel (may be nullptr)
-    unsigned int *pending_count;
+    GameCounters *ctr;
+    GameState *pending;            // stalled games handed to finish_games_kernel (nullptr: play them in place)
+    GameState *tail;               // live games handed to team_games_kernel once few are left (nullptr: never)
+    unsigned int tail_threshold;   // ... i.e. once n - finished <= tail_threshold
 };
 
 __device__ __forceinline__ void write_game(const GamesArgs &a, const GameState &g)
@@ -628,6 +681,39 @@ __device__ __forceinline__ void write_game(const GamesArgs &a, const GameState &
     if (a.final_board) a.final_board[i] = g.board;
 }
 
+// Game2048Env() -> __init__ calls reset (env:27); state = env.reset() (evaluate_beam_search.py:30)
+__device__ __forceinline__ void start_game(GameState &gs, EnvState &s, const PhiloxKey &K, uint32_t game, uint32_t index)
+{
+    s.spawn_ctr = 0u;
+    env_reset(s, K, game);
+    env_reset(s, K, game);
+    gs.index = index; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0; gs.streak = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) gs.ms[m] = -1;
+}
+__device__ __forceinline__ void load_env(const GameState &gs, EnvState &s)
+{
+    s.board = Board(gs.board); s.score = gs.score; s.highest = gs.highest; s.spawn_ctr = gs.spawn_ctr;
+}
+__device__ __forceinline__ void store_env(GameState &gs, const EnvState &s)
+{
+    gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
+}
+// env.step(action) and the bookkeeping of evaluate_beam_search.py:56-86; returns done.
+__device__ __forceinline__ bool play_move(GameState &gs, EnvState &s, const BeamResult &r, const GamesArgs &a,
+                                          const uint16_t *row, uint32_t game)
+{
+    gs.nodes += r.nodes;
+    const StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
+    // evaluate_beam_search.py:59-64 records the move index BEFORE `moves += 1` (:86)
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+        if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
+    if (st.valid) { ++gs.valid; gs.streak = 0; } else { ++gs.invalid; ++gs.streak; }
+    ++gs.moves;
+    return st.done;
+}
+
 // Consecutive invalid moves after which a game is handed to the stall breaker.  The reference's
 // agent keeps choosing its fake-valid DOWN on some boards for thousands of moves
 // (report.md: games reaching the move limit); one warp would grind through them one call at a time.
@@ -636,8 +722,20 @@ __device__ __forceinline__ void write_game(const GamesArgs &a, const GameState &
 #endif
 constexpr int kStallStreak = G2048_STALL_STREAK;
 
-// Whole games (evaluate_beam_search.py:16-98): one warp plays one game from Game2048Env() to
-// game over, fetching the next game id from a global queue so long games do not strand SMs.
+// A game leaves a play loop finished (done / move cap), stalled (-> stall breaker) or, in the
+// one-warp kernel, because few games are left (-> team kernel).  One thread calls this.
+__device__ __forceinline__ void retire_game(const GamesArgs &a, const GameState &gs, bool done, bool to_tail)
+{
+    if (done || gs.moves >= a.max_moves) { write_game(a, gs); atomicAdd(&a.ctr->finished, 1u); }
+    else if (to_tail) a.tail[atomicAdd(&a.ctr->tail_count, 1u)] = gs;
+    else { a.pending[atomicAdd(&a.ctr->pending_count, 1u)] = gs; atomicAdd(&a.ctr->finished, 1u); }
+}
+
+// Whole games (evaluate_beam_search.py:16-98), throughput form: one warp plays one game, fetching
+// the next game id from a global queue so long games do not strand SMs.  Once the games that are
+// still alive would all fit the team kernel (one team of four warps each), every warp hands its
+// game over after its current move and leaves: from there on the chain of moves of the longest
+// game, not the ALU pipe, bounds the run.
 __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -646,40 +744,70 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
     const uint32_t lane = threadIdx.x & 31u;
+    const volatile unsigned int *finished = &a.ctr->finished;
     for (;;) {
         unsigned int g = 0;
-        if (lane == 0) g = atomicAdd(a.work, 1u);
+        if (lane == 0) g = atomicAdd(&a.ctr->work, 1u);
         g = __shfl_sync(FULL, g, 0);
         if ((int64_t)g >= a.n) break;
         const uint32_t game = a.game0 + g;
         EnvState s;
-        s.spawn_ctr = 0u;
-        env_reset(s, a.P.K, game);      // Game2048Env() -> __init__ calls reset (env:27)
-        env_reset(s, a.P.K, game);      // state = env.reset() (evaluate_beam_search.py:30)
         GameState gs;
-        gs.index = g; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) gs.ms[m] = -1;
-        bool done = false;
-        int streak = 0;
-        while (!done && gs.moves < a.max_moves && streak < kStallStreak) {
-            BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
-            gs.nodes += r.nodes;
-            StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
-            done = st.done;
-            // evaluate_beam_search.py:59-64 records the move index BEFORE `moves += 1` (:86)
-#pragma unroll
-            for (int m = 0; m < 8; ++m)
-                if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
-            if (st.valid) { ++gs.valid; streak = 0; } else { ++gs.invalid; streak = a.pending ? streak + 1 : 0; }
-            ++gs.moves;
+        start_game(gs, s, a.P.K, game, g);
+        bool done = false, to_tail = false;
+        while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
+            if (a.tail) {                                  // warp-uniform: lane 0 reads, everyone follows
+                unsigned int f = 0;
+                if (lane == 0) f = *finished;
+                f = __shfl_sync(FULL, f, 0);
+                to_tail = (unsigned int)a.n - f <= a.tail_threshold;
+                if (to_tail) break;
+            }
+            const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
+            done = play_move(gs, s, r, a, row, game);
         }
-        gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
-        if (lane == 0) {
-            if (!done && gs.moves < a.max_moves) a.pending[atomicAdd(a.pending_count, 1u)] = gs;   // stalled: resume later
-            else write_game(a, gs);
-        }
+        store_env(gs, s);
+        if (lane == 0) retire_game(a, gs, done, to_tail);
         __syncwarp();
+    }
+}
+
+// Whole games, latency form: one TEAM of four warps plays one game (beam_search_team).  Games come
+// from `in` (hand-overs of play_games_kernel, *in_count of them) or, with in == nullptr, are the
+// fresh games 0..n-1.  The first item of a team is fixed (team-major over the grid, so that few
+// games spread over all SMs); further ones come from the queue.
+__global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a, const GameState *in)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int quad = threadIdx.x >> 7;
+    TeamScratch &ts = team_scratch(smem, quad);
+    const int bar = 1 + quad;
+    const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
+    const unsigned int total = in ? a.ctr->tail_count : (unsigned int)a.n;
+    const unsigned int teams = gridDim.x * (blockDim.x >> 7);
+    unsigned int p = (unsigned int)quad * gridDim.x + blockIdx.x;
+    for (;;) {
+        if (p >= total) break;
+        EnvState s;
+        GameState gs;
+        if (in) { gs = in[p]; load_env(gs, s); }
+        else start_game(gs, s, a.P.K, a.game0 + p, p);
+        const uint32_t game = a.game0 + gs.index;
+        bool done = false;
+        while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
+            const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
+            done = play_move(gs, s, r, a, row, game);
+        }
+        store_env(gs, s);
+        if (leader) {
+            retire_game(a, gs, done, false);
+            ts.next_item = teams + atomicAdd(&a.ctr->team_work, 1u);
+        }
+        team_barrier(bar);
+        p = ts.next_item;
+        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
     }
 }
 
@@ -695,31 +823,19 @@ __global__ void __launch_bounds__(kWideWarps * 32, 1) play_games_wide_kernel(Gam
     const uint32_t lane = threadIdx.x & 31u;
     for (;;) {
         unsigned int g = 0;
-        if (lane == 0) g = atomicAdd(a.work, 1u);
+        if (lane == 0) g = atomicAdd(&a.ctr->work, 1u);
         g = __shfl_sync(FULL, g, 0);
         if ((int64_t)g >= a.n) break;
         const uint32_t game = a.game0 + g;
         EnvState s;
-        s.spawn_ctr = 0u;
-        env_reset(s, a.P.K, game);
-        env_reset(s, a.P.K, game);
         GameState gs;
-        gs.index = g; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) gs.ms[m] = -1;
+        start_game(gs, s, a.P.K, game, g);
         bool done = false;
         while (!done && gs.moves < a.max_moves) {
-            BeamResult r = beam_search_wide_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
-            gs.nodes += r.nodes;
-            StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
-            done = st.done;
-#pragma unroll
-            for (int m = 0; m < 8; ++m)
-                if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
-            if (st.valid) ++gs.valid; else ++gs.invalid;
-            ++gs.moves;
+            const BeamResult r = beam_search_wide_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
+            done = play_move(gs, s, r, a, row, game);
         }
-        gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
+        store_env(gs, s);
         if (lane == 0) write_game(a, gs);
         __syncwarp();
     }
@@ -732,13 +848,16 @@ __global__ void __launch_bounds__(kWideWarps * 32, 1) play_games_wide_kernel(Gam
 // after it are discarded.  Exact, and up to kSpecWarps times faster through a stall.
 // kSpecWarps = 8 (three games per block) when many games may be stalled, = 24 (one game per
 // block) when the launch is small enough that a whole SM per stalled game is available.
+// After a valid move the next call most likely is valid too: that one call is searched by the
+// group's first four warps as a team (latency form); the width doubles again with every round
+// that finds no valid move.
 struct SpecSlot { uint32_t action; int32_t nodes; };
 
 template <int kSpecWarps>
-__global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs a, unsigned int *queue)
+__global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs a)
 {
     constexpr int kSpecGroups = kBeamWarps / kSpecWarps;
-    static_assert(kSpecGroups * kSpecWarps == kBeamWarps, "groups must tile the block");
+    static_assert(kSpecGroups * kSpecWarps == kBeamWarps && kSpecWarps % kTeamWarps == 0, "groups must tile the block");
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SpecSlot slots[kSpecGroups][2][kSpecWarps];
     __shared__ unsigned int next_game[kSpecGroups];
@@ -748,10 +867,12 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
     const uint32_t lane = threadIdx.x & 31u;
     const int group = warp / kSpecWarps, w = warp % kSpecWarps;
-    const unsigned int total = *a.pending_count;
-    auto group_barrier = [&]() { asm volatile("barrier.sync %0, %1;" ::"r"(1 + group), "r"(kSpecWarps * 32) : "memory"); };
+    const int quad = warp >> 2;                            // the group's team = its first four warps
+    TeamScratch &ts = team_scratch(smem, quad);
+    const unsigned int total = a.ctr->pending_count;
+    auto group_barrier = [&]() { asm volatile("barrier.sync %0, %1;" ::"r"(8 + group), "r"(kSpecWarps * 32) : "memory"); };
     for (;;) {
-        if (w == 0 && lane == 0) next_game[group] = atomicAdd(queue, 1u);
+        if (w == 0 && lane == 0) next_game[group] = atomicAdd(&a.ctr->finish_work, 1u);
         group_barrier();
         const unsigned int p = next_game[group];
         group_barrier();                                   // everyone has read it before the next round rewrites it
@@ -759,17 +880,19 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
         GameState gs = a.pending[p];                       // every warp of the group keeps an identical copy
         const uint32_t game = a.game0 + gs.index;
         EnvState s;
-        s.board = Board(gs.board); s.score = gs.score; s.highest = gs.highest; s.spawn_ctr = gs.spawn_ctr;
+        load_env(gs, s);
         bool done = false;
         int buf = 0;
-        // speculation width: the game arrives inside a stall (full width); after a valid move the next
-        // call most likely is valid too, so only one warp searches (no contention, no wasted searches)
-        // and the width doubles again with every round that finds no valid move
-        int width = kSpecWarps;
+        int width = kSpecWarps;                            // the game arrives inside a stall
         while (!done && gs.moves < a.max_moves) {
             const int allowed = min(width, a.max_moves - gs.moves);
-            if (w < allowed) {
-                BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(gs.moves + w), row, ws);
+            if (allowed == 1) {
+                if (w < kTeamWarps) {
+                    const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, 1 + quad);
+                    if (w == 0 && lane == 0) { slots[group][buf][0].action = r.action; slots[group][buf][0].nodes = r.nodes; }
+                }
+            } else if (w < allowed) {
+                const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(gs.moves + w), row, ws);
                 if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
             }
             group_barrier();
@@ -783,32 +906,29 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
             gs.invalid += n_invalid;
             gs.moves += n_invalid;                          // invalid moves: nothing else changes (env:188-192)
             if (first_valid >= 0) {
-                StepResult st = env_step<true, false, false>(s, slots[group][buf][first_valid].action, row, a.code, a.P.K,
-                                                             game, nullptr, a.overflow);
-                done = st.done;
-#pragma unroll
-                for (int m = 0; m < 8; ++m)
-                    if (gs.ms[m] < 0 && s.highest >= (uint32_t)(6 + m)) gs.ms[m] = gs.moves;
-                ++gs.valid;
-                ++gs.moves;
+                BeamResult r;
+                r.action = slots[group][buf][first_valid].action;
+                r.nodes = 0;
+                done = play_move(gs, s, r, a, row, game);
                 width = 1;
             } else {
                 width = min(kSpecWarps, 2 * width);
             }
             buf ^= 1;
         }
-        gs.board = s.board.u64(); gs.score = s.score; gs.highest = s.highest; gs.spawn_ctr = s.spawn_ctr;
+        store_env(gs, s);
         if (w == 0 && lane == 0) write_game(a, gs);
     }
 }
 
 static int g_attr_done[kMaxDevices];
+static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1};
 
-// Each launch gets its own queue head so launches on different streams never share one.
-static unsigned int *next_work_counter(DeviceState *st)
+int set_tuning(int key, int value)
 {
-    unsigned int slot = __atomic_fetch_add(&st->next_counter, 1u, __ATOMIC_RELAXED) % kWorkCounters;
-    return st->work_counter + slot;
+    if (key < 0 || key >= G2048_TUNE_COUNT) return set_error(G2048_EINVAL, "g2048_set_tuning: unknown key %d", key);
+    g_tuning[key] = value;
+    return G2048_OK;
 }
 
 static int ensure_attrs()
@@ -817,15 +937,33 @@ static int ensure_attrs()
     G2048_CUDA(cudaGetDevice(&dev));
     if (!g_attr_done[dev]) {
         G2048_CUDA(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(beam_search_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(beam_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         g_attr_done[dev] = 1;
     }
     return G2048_OK;
 }
+
+// Per-launch device scratch from the stream-ordered allocator: launches on different streams (or
+// baked into different CUDA graphs) never share a queue head, and the memory goes back to the
+// pool when the launch's kernels are done -- on every return path.
+struct LaunchScratch {
+    void *ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    int alloc(size_t bytes, size_t zero_bytes, cudaStream_t s)
+    {
+        stream = s;
+        G2048_CUDA(cudaMallocAsync(&ptr, bytes, s));
+        G2048_CUDA(cudaMemsetAsync(ptr, 0, zero_bytes, s));
+        return G2048_OK;
+    }
+    ~LaunchScratch() { if (ptr) cudaFreeAsync(ptr, stream); }
+};
 
 int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *legal, const uint32_t *call,
                        uint32_t call0, uint8_t *action, float *prob, double *best_score, int32_t *nodes,
@@ -834,10 +972,12 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
 {
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
+    LaunchScratch scratch;
+    rc = scratch.alloc(sizeof(unsigned int), sizeof(unsigned int), stream);
+    if (rc != G2048_OK) return rc;
     BeamArgs a{roots, legal, call, call0, action, prob, best_score, nodes, n,
                BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
-               game0, st->row, next_work_counter(st)};
-    G2048_CUDA(cudaMemsetAsync(a.work, 0, sizeof(unsigned int), stream));
+               game0, st->row, static_cast<unsigned int *>(scratch.ptr)};
     if (beam_width > 32) {                                          // wide beams: shared-memory beam, counting top-k
         int wgrid = (int)(n < st->sm_count ? n : st->sm_count);
         int64_t wwarps = (n + wgrid - 1) / wgrid;
@@ -846,8 +986,17 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
         count_launch();
         return check_cuda(cudaGetLastError(), "beam_search_wide_kernel");
     }
-    // one block per SM; a small batch gets fewer warps per block so that it is spread over all SMs
-    int grid = (int)(n < st->sm_count ? n : st->sm_count);
+    const int teams_per_block = kBeamWarps / kTeamWarps;
+    const int mode = g_tuning[G2048_TUNE_SEARCH_MODE];
+    const bool team = mode == 2 || (mode == 0 && n <= (int64_t)st->sm_count * teams_per_block);
+    int grid = (int)(n < st->sm_count ? n : st->sm_count);          // one block per SM; a small batch is spread over all SMs
+    if (team) {                                                     // fewer roots than team slots: latency form
+        int64_t per_block = (n + grid - 1) / grid;
+        int threads = kTeamThreads * (int)(per_block < teams_per_block ? per_block : teams_per_block);
+        beam_search_team_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "beam_search_team_kernel");
+    }
     int64_t warps = (n + grid - 1) / grid;
     int threads = 32 * (int)(warps < kBeamWarps ? warps : kBeamWarps);
     beam_search_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a);
@@ -862,51 +1011,60 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
 {
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
-    if (beam_width > 32) {                                          // wide beams: compatibility path, no stall breaker
-        unsigned int *wwork = next_work_counter(st);
-        G2048_CUDA(cudaMemsetAsync(wwork, 0, sizeof(unsigned int), stream));
-        GamesArgs wa{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
-                     max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
-                     st->row, st->code, st->overflow, wwork, nullptr, nullptr};
-        int wgrid = (int)(n < st->sm_count ? n : st->sm_count);
-        int64_t wwarps = (n + wgrid - 1) / wgrid;
+    const bool wide = beam_width > 32;
+    const int teams_per_block = kBeamWarps / kTeamWarps;
+    const int64_t team_slots = (int64_t)st->sm_count * teams_per_block;
+    // few games: teams from the first move; many: one warp per game until the live ones fit the teams
+    const int64_t direct_max = g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] >= 0 ? g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] : 2 * team_slots;
+    const int64_t tail_thr = g_tuning[G2048_TUNE_TAIL_THRESHOLD] >= 0 ? g_tuning[G2048_TUNE_TAIL_THRESHOLD] : team_slots;
+    const bool direct = !wide && n <= direct_max;
+    const int64_t tail_cap = wide || direct ? 0 : (tail_thr < n ? tail_thr : n);
+    // scratch: counters | stalled games (any game may stall) | games handed to the team kernel
+    const size_t pending_off = 256, tail_off = pending_off + (wide ? 0 : (size_t)n * sizeof(GameState));
+    LaunchScratch scratch;
+    rc = scratch.alloc(tail_off + (size_t)tail_cap * sizeof(GameState), sizeof(GameCounters), stream);
+    if (rc != G2048_OK) return rc;
+    uint8_t *base = static_cast<uint8_t *>(scratch.ptr);
+    GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
+                max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
+                st->row, st->code, st->overflow, reinterpret_cast<GameCounters *>(base),
+                wide ? nullptr : reinterpret_cast<GameState *>(base + pending_off),
+                tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_cap};
+    const int grid = (int)(n < st->sm_count ? n : st->sm_count);    // spread small runs over all SMs (see beam search)
+    if (wide) {                                                     // wide beams: compatibility path, no stall breaker
+        int64_t wwarps = (n + grid - 1) / grid;
         int wthreads = 32 * (int)(wwarps < kWideWarps ? wwarps : kWideWarps);
-        play_games_wide_kernel<<<wgrid, wthreads, kWideSmemBytes, stream>>>(wa);
+        play_games_wide_kernel<<<grid, wthreads, kWideSmemBytes, stream>>>(a);
         count_launch();
         return check_cuda(cudaGetLastError(), "play_games_wide_kernel");
     }
-    // per-launch scratch for stalled games from the stream-ordered allocator: concurrent launches on
-    // different streams never share it, and it is released when this launch's kernels are done
-    GameState *pending = nullptr;
-    G2048_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&pending), (size_t)n * sizeof(GameState), stream));
-    unsigned int *work = next_work_counter(st);
-    unsigned int *pending_count = next_work_counter(st);
-    unsigned int *queue = next_work_counter(st);
-    G2048_CUDA(cudaMemsetAsync(work, 0, sizeof(unsigned int), stream));
-    G2048_CUDA(cudaMemsetAsync(pending_count, 0, sizeof(unsigned int), stream));
-    G2048_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), stream));
-    GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
-                max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
-                st->row, st->code, st->overflow, work, pending, pending_count};
-    int grid = (int)(n < st->sm_count ? n : st->sm_count);          // spread small runs over all SMs (see beam search)
-    int64_t warps = (n + grid - 1) / grid;
-    int threads = 32 * (int)(warps < kBeamWarps ? warps : kBeamWarps);
-    play_games_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a);
-    count_launch();
-    G2048_CUDA(cudaGetLastError());
+    if (direct) {
+        int64_t per_block = (n + grid - 1) / grid;
+        int threads = kTeamThreads * (int)(per_block < teams_per_block ? per_block : teams_per_block);
+        team_games_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a, nullptr);
+        count_launch();
+        G2048_CUDA(cudaGetLastError());
+    } else {
+        play_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a);
+        count_launch();
+        G2048_CUDA(cudaGetLastError());
+        if (tail_cap) {                                             // how many were handed over is only known on the device
+            team_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
+            count_launch();
+            G2048_CUDA(cudaGetLastError());
+        }
+    }
     // stalled games: kSpecWarps warps each (how many there are is only known on the device, so the
     // grid is sized for the worst case and surplus groups leave at once)
     if (n <= 2048) {            // ~5 % of games stall: up to ~100 of them, one SM each
-        int grid2 = (int)(n < st->sm_count ? n : st->sm_count);
-        finish_games_kernel<kBeamWarps><<<grid2, kBeamThreads, kBeamSmemBytes, stream>>>(a, queue);
+        finish_games_kernel<kBeamWarps><<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
     } else {
         int64_t groups = (n + 2) / 3;
         int grid2 = (int)(groups < st->sm_count ? groups : st->sm_count);
-        finish_games_kernel<8><<<grid2, kBeamThreads, kBeamSmemBytes, stream>>>(a, queue);
+        finish_games_kernel<8><<<grid2, kBeamThreads, kBeamSmemBytes, stream>>>(a);
     }
     count_launch();
-    G2048_CUDA(cudaGetLastError());
-    return check_cuda(cudaFreeAsync(pending, stream), "cudaFreeAsync");
+    return check_cuda(cudaGetLastError(), "finish_games_kernel");
 }
 
 }  // namespace g2048

@@ -9,7 +9,6 @@ namespace g2048 {
 
 constexpr int kMaxDevices = 32;
 constexpr int kRowEntries = 65536;
-constexpr int kWorkCounters = 256;          // work-queue heads handed out round-robin to launches
 constexpr size_t kRowTableBytes = kRowEntries * sizeof(uint16_t);    // 128 KiB
 constexpr size_t kCodeTableBytes = kRowEntries * sizeof(uint8_t);    //  64 KiB
 
@@ -18,8 +17,6 @@ struct DeviceState {
     uint16_t *row = nullptr;                 // LEFT-move result per 16-bit row
     uint8_t *code = nullptr;                 // merge codes per 16-bit row
     unsigned long long *overflow = nullptr;  // sticky nibble-saturation counter
-    unsigned int *work_counter = nullptr;    // ring of kWorkCounters queue heads (one per launch in flight)
-    unsigned int next_counter = 0;
     int sm_count = 0;
 };
 
@@ -37,6 +34,7 @@ void count_launch(int n = 1);
     } while (0)
 
 // Launch helpers implemented in beam.cu
+int set_tuning(int key, int value);
 int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *legal, const uint32_t *call,
                        uint32_t call0, uint8_t *action, float *prob, double *best_score, int32_t *nodes,
                        int64_t n, int beam_width, int search_depth, int early_thr, int mid_thr,

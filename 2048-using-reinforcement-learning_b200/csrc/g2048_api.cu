@@ -498,6 +498,7 @@ extern "C" {
 int g2048_abi_version(void) { return G2048_ABI_VERSION; }
 const char *g2048_last_error(void) { return g_error; }
 uint64_t g2048_launch_count(void) { return g_launches.load(); }
+int g2048_set_tuning(int key, int value) { return set_tuning(key, value); }
 
 int g2048_init(int device)
 {
@@ -515,11 +516,9 @@ int g2048_init(int device)
     G2048_CUDA(cudaMalloc(&st.row, kRowTableBytes));
     G2048_CUDA(cudaMalloc(&st.code, kCodeTableBytes));
     G2048_CUDA(cudaMalloc(&st.overflow, sizeof(unsigned long long)));
-    G2048_CUDA(cudaMalloc(&st.work_counter, sizeof(unsigned int) * kWorkCounters));
     G2048_CUDA(cudaMemcpy(st.row, row.data(), kRowTableBytes, cudaMemcpyHostToDevice));
     G2048_CUDA(cudaMemcpy(st.code, code.data(), kCodeTableBytes, cudaMemcpyHostToDevice));
     G2048_CUDA(cudaMemset(st.overflow, 0, sizeof(unsigned long long)));
-    G2048_CUDA(cudaMemset(st.work_counter, 0, sizeof(unsigned int) * kWorkCounters));
     G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
     const int smem = (int)(kRowTableBytes + kCodeTableBytes);
     G2048_CUDA(cudaFuncSetAttribute(env_step_kernel<true, kEnvSharedThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

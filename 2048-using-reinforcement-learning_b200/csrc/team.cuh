@@ -1,0 +1,200 @@
+// team.cuh -- BeamSearchAgent.get_action (agents/beam_search_agent.py:71-181) by a TEAM of four
+// warps, one child per thread.  Included by beam.cu after the one-warp search.
+//
+// The one-warp search (beam_search_warp) is the throughput form: 24 independent roots per SM keep
+// the ALU pipe busy, but a single warp runs a level's ~1,100 instructions as one dependent chain
+// (IPC ~0.3, ~60 us per move at width 20 / depth 40).  Whole games are sequential chains of moves,
+// so once fewer games are alive than warps fit on the GPU the chain, not the pipe, sets the time.
+// Here warp a of the team owns ACTION a and lane r owns the beam entry of RANK r: every thread
+// makes one child (a warp-uniform direction: no selects), spawns and evaluates it, and the stable
+// top-k is a counting rank over the level's <= 128 keys in shared memory (broadcast 16-byte
+// loads, no shuffle network).  Three named barriers per level replace ~45 dependent shuffles.
+//   generation order (agent:142-167) = (rank, action)  ->  position and spawn ordinal of a child
+//   come from the four validity / draw ballots: popc over lower ranks + the lower actions of its
+//   own parent.  Results are bit-identical to the one-warp search (same tests).
+#pragma once
+
+namespace g2048 {
+
+constexpr int kTeamWarps = 4;
+constexpr int kTeamThreads = kTeamWarps * 32;
+constexpr uint32_t kTeamRing = 512;                  // spawn ordinals held per team (power of two)
+
+struct __align__(16) TeamScratch {
+    uint4 rng[kTeamRing / 2];       // spawn words of ordinals [ring_end - 512, ring_end): one Philox block per entry
+    double score[kTeamThreads];     // float64 scores of a full-evaluation level, generation order
+    uint32_t key[kTeamThreads];     // sort keys by thread (action * 32 + parent rank); 0 = no child
+    uint64_t beam[32];              // parents of the level, rank order
+    uint32_t ballots[8];            // [a]: valid children of action a (bit = parent rank); [4 + a]: those that draw
+    uint8_t meta[32];               // first action | largest exponent << 2 of beam[i]
+    double out_best;                // score of the best candidate of the last level
+    uint32_t out_first;             // its first action
+    uint32_t next_item;             // work-queue hand-off of the kernels built on the team
+};
+static_assert(sizeof(TeamScratch) <= kTeamWarps * sizeof(WarpScratch), "a team reuses the scratch of its four warps");
+
+__device__ __forceinline__ void team_barrier(int id)
+{
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "n"(kTeamThreads) : "memory");
+}
+
+// BeamSearchAgent._make_move (agent:194-258) for a warp-uniform direction (DOWN with its rotation
+// bug): same results as agent_children(), one direction per call.
+__device__ __forceinline__ Board agent_child_uniform(Board b, uint32_t action, const uint16_t *row)
+{
+    switch (action) {
+    case 0: return move_left<true>(b, row);
+    case 1: return transpose(move_left<true>(transpose(b), row));
+    case 2: return flip_rows(move_left<true>(flip_rows(b), row));
+    default: return transpose(flip_row_order(move_left<true>(flip_rows(transpose(b)), row)));
+    }
+}
+
+// All 128 threads of the team call this with the same root / parameters; `bar` is the team's
+// named barrier.  Returns the same BeamResult on every thread.
+__device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_given, const BeamParams &P, uint32_t game,
+                                                       uint32_t call, const uint16_t *row, TeamScratch &ts, int bar)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tw = (threadIdx.x >> 5) & 3u;                        // warp in the team = action it expands
+    const uint32_t tid = tw * 32u + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    BeamResult res;
+    res.nodes = 0;
+    res.best = 0.0;
+
+    // agent:82-93 -- legality and the two fast exits (every warp computes them, no exchange needed)
+    const Board root_child = agent_child_any(root, lane & 3u, row);
+    const uint32_t agent_mask = __ballot_sync(FULL, root_child != root) & 15u;
+    const uint32_t vm = legal_given >= 0 ? ((uint32_t)legal_given & 15u) : agent_mask;
+    if (vm == 0u) { res.action = 0u; res.prob = 0.5f; return res; }
+    if ((vm & (vm - 1u)) == 0u) { res.action = (uint32_t)__ffs((int)vm) - 1u; res.prob = 1.0f; return res; }
+
+    // agent:96-106
+    const uint32_t root_emax = max_exponent(root);
+    const int root_max = tile_value(root_emax);
+    const int phase = root_max < P.early_thr ? 0 : root_max < P.mid_thr ? 1 : 2;
+    const int n0 = count_empty(root);
+    const int depth = max(1, n0 <= 4 ? min(P.depth + 5, 25) : n0 >= 10 ? min(P.depth - 5, 10) : P.depth);
+
+    int nb = 1;                  // parents of the level (level 0: the root)
+    uint32_t spawn_base = 0u;    // spawns drawn so far in this call
+    uint32_t ring_end = 0u;      // ts.rng holds the spawn words of ordinals [ring_end - 512, ring_end)
+    const uint32_t *corners = corner_table();
+
+    for (int d = 0; d < depth; ++d) {
+        // a level draws at most 128 spawns; one pass (a Philox block per thread) adds 256 ordinals and
+        // overwrites ordinals below ring_end - 256, all consumed (spawn_base > ring_end - 128)
+        if (ring_end - spawn_base < 128u) {
+            const Philox4 p = philox4x32_10((ring_end >> 1) + tid, call, game, DOM_BEAM, P.K);
+            ts.rng[((ring_end & (kTeamRing - 1u)) >> 1) + tid] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
+            ring_end += 256u;
+        }
+        // ---- A: my child (agent:112-123 for the root, agent:142-167 below it) ------------------------
+        Board parent = root;
+        uint32_t pmeta = tw | (root_emax << 2);
+        bool has_parent = lane == 0u && ((vm >> tw) & 1u);
+        if (d > 0) {
+            has_parent = (int)lane < nb;
+            parent = Board(ts.beam[lane]);
+            pmeta = ts.meta[lane];
+        }
+        Board b = agent_child_uniform(parent, tw, row);
+        const bool valid = has_parent && b != parent;
+        uint32_t nzl = nz_flags(b.lo), nzh = nz_flags(b.hi);
+        const uint32_t zl = nzl ^ LSB4, zh = nzh ^ LSB4;
+        const int cl = __popc(zl);
+        int n_empty = cl + __popc(zh);
+        const bool draws = valid && n_empty > 0;                        // agent:262-263: no draw on a full board
+        const uint32_t vb = __ballot_sync(FULL, valid), db = __ballot_sync(FULL, draws);
+        if (lane == 0u) { ts.ballots[tw] = vb; ts.ballots[4u + tw] = db; }
+        team_barrier(bar);                                              // (1) ballots (and the ring) are visible
+        const uint4 V = *reinterpret_cast<const uint4 *>(&ts.ballots[0]);
+        const uint4 D = *reinterpret_cast<const uint4 *>(&ts.ballots[4]);
+        const int n_valid = (__popc(V.x) + __popc(V.y)) + (__popc(V.z) + __popc(V.w));
+        if (n_valid == 0) {
+            team_barrier(bar);                                          // everyone has read the ballots before a next call rewrites them
+            if (d > 0) break;                                           // agent:170-171 keeps the old beam
+            // agent:126-128: random.choice among the caller's valid moves, one draw
+            const Philox4 p = philox4x32_10(0u, call, game, DOM_BEAM, P.K);
+            const int pick = (int)__umulhi(p.w[0], (uint32_t)__popc(vm));
+            uint32_t m = vm;
+            for (int i = 0; i < pick; ++i) m &= m - 1u;
+            res.action = (uint32_t)__ffs((int)m) - 1u;
+            res.prob = 0.5f;
+            return res;
+        }
+        res.nodes += n_valid;
+        // children of lower ranks come first, then the lower actions of my own parent
+        const uint32_t own = (tw > 0u ? (V.x >> lane) & 1u : 0u) + (tw > 1u ? (V.y >> lane) & 1u : 0u) +
+                             (tw > 2u ? (V.z >> lane) & 1u : 0u);
+        const uint32_t pos = (uint32_t)((__popc(V.x & lt_mask) + __popc(V.y & lt_mask)) +
+                                        (__popc(V.z & lt_mask) + __popc(V.w & lt_mask))) + own;
+        const uint32_t down = (tw > 0u ? (D.x >> lane) & 1u : 0u) + (tw > 1u ? (D.y >> lane) & 1u : 0u) +
+                              (tw > 2u ? (D.z >> lane) & 1u : 0u);
+        const uint32_t ordinal = spawn_base + (uint32_t)((__popc(D.x & lt_mask) + __popc(D.y & lt_mask)) +
+                                                         (__popc(D.z & lt_mask) + __popc(D.w & lt_mask))) + down;
+        spawn_base += (uint32_t)((__popc(D.x) + __popc(D.y)) + (__popc(D.z) + __popc(D.w)));
+
+        // ---- B: spawn + evaluate (agent:155-161) ---------------------------------------------------------
+        const uint2 w = reinterpret_cast<const uint2 *>(ts.rng)[ordinal & (kTeamRing - 1u)];
+        const SpawnPick sp = pick_spawn(zl, zh, cl, n_empty, w.x, w.y);
+        if (draws) {
+            b.lo |= sp.flag_lo * sp.exponent;
+            b.hi |= sp.flag_hi * sp.exponent;
+            nzl |= sp.flag_lo;
+            nzh |= sp.flag_hi;
+            n_empty -= 1;
+        }
+        const uint32_t pmax = pmeta >> 2;                               // parent's largest exponent
+        const uint32_t emax = pmax + ((pmax < 15u && has_exponent(b, pmax + 1u)) ? 1u : 0u);
+        const uint32_t first = pmeta & 3u;
+        const uint32_t tail = ((127u - pos) << 2) | first;
+        const bool full_level = d >= 1 && d <= 3;                       // agent:139,158-161
+        uint32_t key = 0u;
+        double full = 0.0;
+        if (full_level) {
+            // float64 scores: rank = #candidates with a strictly larger score; equal scores are
+            // separated by the generation index in the key (Python's stable sort)
+            full = full_eval_flags(b, nzl, nzh, n_empty, emax, phase, corners);
+            if (valid) ts.score[pos] = full;
+            team_barrier(bar);
+            int larger = 0;
+            for (int j = 0; j < n_valid; ++j) larger += ts.score[j] > full ? 1 : 0;
+            if (valid) key = ((uint32_t)(n_valid - larger) << 9) | tail;
+        } else {
+            const int fast = fast_eval_flags(b, nzl, nzh, n_empty, emax, corners);
+            if (valid) key = ((uint32_t)fast << 9) | tail;
+        }
+        ts.key[tid] = key;
+        team_barrier(bar);                                              // (2) all keys of the level are visible
+
+        // ---- C: stable top-k by counting (agent:131-132,174-175) -----------------------------------------
+        const int holders = d == 0 ? 1 : nb;                            // lanes of each warp that held a parent
+        uint32_t rank = 0u;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const uint4 *k4 = reinterpret_cast<const uint4 *>(&ts.key[32 * a]);
+            for (int l = 0; l < holders; l += 4) {
+                const uint4 k = k4[l >> 2];
+                rank += (k.x > key ? 1u : 0u) + (k.y > key ? 1u : 0u) + (k.z > key ? 1u : 0u) + (k.w > key ? 1u : 0u);
+            }
+        }
+        nb = min(P.width, n_valid);
+        if (valid && (int)rank < nb) {
+            ts.beam[rank] = b.u64();
+            ts.meta[rank] = (uint8_t)(first | (emax << 2));
+            if (rank == 0u) {
+                ts.out_first = first;
+                ts.out_best = full_level ? full : (double)(key >> 9);
+            }
+        }
+        team_barrier(bar);                                              // (3) the next level's parents are in place
+    }
+    res.action = ts.out_first;                                          // agent:178
+    res.best = ts.out_best;
+    res.prob = 1.0f;
+    return res;
+}
+
+}  // namespace g2048

@@ -211,6 +211,18 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
                           int32_t *score, uint8_t *highest_exp, int32_t *moves, int32_t *valid, int32_t *invalid,
                           int32_t *milestone, int64_t *nodes, uint64_t *final_board, int64_t *stats);
 
+/* Scheduling knobs of the beam-search launchers (results never depend on them; tests and
+ * profiles/ use them to force a path).  Process-wide.
+ *   G2048_TUNE_SEARCH_MODE      g2048_beam_search: 0 = auto (one team of four warps per root while the
+ *                               roots fit the GPU's team slots, else one warp per root), 1 = always one
+ *                               warp per root, 2 = always teams
+ *   G2048_TUNE_TEAM_DIRECT_MAX  g2048_play_games: up to this many games are played by teams from the
+ *                               first move (-1 = default: twice the team slots of the device)
+ *   G2048_TUNE_TAIL_THRESHOLD   g2048_play_games with more games: one warp per game until this many are
+ *                               left alive, then teams (-1 = default: the team slots; 0 = never) */
+enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2, G2048_TUNE_COUNT = 3 };
+int g2048_set_tuning(int key, int value);
+
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
 uint64_t g2048_launch_count(void);
 

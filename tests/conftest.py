@@ -32,6 +32,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_games():
+    """Whole reference games at the BASELINE widths, move by move (oracle/make_golden_games.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_games.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def orc():
     from oracle import pyoracle
     pyoracle.lib()

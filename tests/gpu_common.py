@@ -13,6 +13,31 @@ def lib():
     return _lib.use_device(0)
 
 
+TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD = 0, 1, 2
+_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1}
+
+
+class tuning:
+    """with tuning({key: value}): force a scheduling path of the beam-search launchers (g2048_set_tuning)."""
+
+    def __init__(self, values):
+        self.values = values
+
+    def __enter__(self):
+        for k, v in self.values.items():
+            _lib.check(lib().g2048_set_tuning(k, v))
+
+    def __exit__(self, *exc):
+        for k in self.values:
+            _lib.check(lib().g2048_set_tuning(k, _TUNE_DEFAULTS[k]))
+
+
+# scheduling paths of g2048_play_games: teams from the first move / one warp per game only /
+# one warp per game until `tail` games are left, then teams
+PLAY_PATHS = {"team": {TUNE_TEAM_DIRECT_MAX: 1 << 30}, "warp": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 0},
+              "warp+tail": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 40}}
+
+
 def host_reset(n, seed, game0=0, spawn_ctr=None):
     b = np.zeros(n, np.uint64); s = np.zeros(n, np.int32); h = np.zeros(n, np.uint8)
     c = np.zeros(n, np.uint32) if spawn_ctr is None else spawn_ctr

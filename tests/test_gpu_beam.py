@@ -10,33 +10,40 @@ from tests import gpu_common as X   # noqa: E402
 SEED = 0x0B200B200B200
 
 
-def test_golden_get_action(golden):
+@pytest.mark.parametrize("mode", [1, 2], ids=["warp", "team"])
+def test_golden_get_action(golden, mode):
     seed = golden["seed"]
-    for c in golden["beam"]:
-        b = np.array([G.pack_board(c["board"])], np.uint64)
-        legal = None
-        if c["valid_moves"] is not None:
-            legal = np.array([sum(int(v) << k for k, v in enumerate(c["valid_moves"]))], np.uint8)
-        a, p, s, k = X.host_beam(b, c["W"], c["D"], seed, game0=c["game"], call0=c["call"], legal=legal)
-        assert (int(a[0]), float(p[0])) == (c["action"], c["prob"]), c
+    with X.tuning({X.TUNE_SEARCH_MODE: mode}):
+        for c in golden["beam"]:
+            b = np.array([G.pack_board(c["board"])], np.uint64)
+            legal = None
+            if c["valid_moves"] is not None:
+                legal = np.array([sum(int(v) << k for k, v in enumerate(c["valid_moves"]))], np.uint8)
+            a, p, s, k = X.host_beam(b, c["W"], c["D"], seed, game0=c["game"], call0=c["call"], legal=legal)
+            assert (int(a[0]), float(p[0])) == (c["action"], c["prob"]), c
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["warp", "team"])
 @pytest.mark.parametrize("W,D,n", [(15, 20, 1500), (20, 40, 1200), (10, 15, 600), (32, 12, 400), (1, 30, 300),
                                    (7, 3, 300), (20, 1, 200)])
-def test_batched_get_action_vs_oracle(orc, W, D, n):
+def test_batched_get_action_vs_oracle(orc, W, D, n, mode):
+    """One warp per root (throughput form) and one team of four warps per root (latency form)."""
     vals, packed = X.synthetic(orc, n, SEED, 1000 * W)
-    a, p, s, k = X.host_beam(packed, W, D, SEED, game0=1000 * W, call0=5)
+    with X.tuning({X.TUNE_SEARCH_MODE: mode}):
+        a, p, s, k = X.host_beam(packed, W, D, SEED, game0=1000 * W, call0=5)
     oa, op, on, ob = orc.beam_batch(vals, W, D, SEED, 1000 * W, 5)
     assert (a == oa).all(), np.flatnonzero(a != oa)[:10]
     assert (p == op).all() and (k == on).all()
     assert (s == ob).all()                     # float64 best score, bit-exact (fast: integer; full: fp64 order)
 
 
-def test_caller_supplied_valid_moves_and_per_root_calls(orc):
+@pytest.mark.parametrize("mode", [1, 2], ids=["warp", "team"])
+def test_caller_supplied_valid_moves_and_per_root_calls(orc, mode):
     vals, packed = X.synthetic(orc, 600, SEED, 31)
     legal = np.array([orc.env_legal_mask(v) for v in vals], np.uint8)       # env.get_valid_moves(), as train.py passes
     call = (np.arange(600) % 7).astype(np.uint32)
-    a, p, s, k = X.host_beam(packed, 15, 20, SEED, game0=31, legal=legal, call=call)
+    with X.tuning({X.TUNE_SEARCH_MODE: mode}):
+        a, p, s, k = X.host_beam(packed, 15, 20, SEED, game0=31, legal=legal, call=call)
     for i in range(600):
         o = orc.beam_get_action(vals[i], int(legal[i]), 15, 20, SEED, 31 + i, int(call[i]))
         assert (a[i], p[i], k[i]) == (o.action, o.prob, o.nodes), i
@@ -77,9 +84,11 @@ def test_golden_full_games(golden):
         assert list(out["milestone"][0]) == g["milestones"]
 
 
+@pytest.mark.parametrize("path", list(X.PLAY_PATHS))
 @pytest.mark.parametrize("W,D,n,cap", [(4, 6, 96, 10000), (10, 12, 40, 400), (15, 20, 24, 120)])
-def test_play_games_vs_oracle(orc, W, D, n, cap):
-    out = X.host_play(n, W, D, SEED, game0=70, max_moves=cap)
+def test_play_games_vs_oracle(orc, W, D, n, cap, path):
+    with X.tuning(X.PLAY_PATHS[path]):
+        out = X.host_play(n, W, D, SEED, game0=70, max_moves=cap)
     ref = orc.play_games(SEED, 70, n, W, D, max_moves=cap)
     for i in range(n):
         r = ref[i]
@@ -148,11 +157,13 @@ def test_run_evaluation_writes_reference_results(orc, tmp_path):
     assert res["summary"]["games"] == 12 and res["summary"]["max_score"] == max(res["scores"])
 
 
-def test_stall_breaker_path_matches_sequential_oracle(orc):
+@pytest.mark.parametrize("path", list(X.PLAY_PATHS))
+def test_stall_breaker_path_matches_sequential_oracle(orc, path):
     """Games whose agent keeps choosing the fake-valid DOWN are finished by finish_games_kernel
-    (8 speculative get_action calls per round); per-game results must equal the sequential loop."""
+    (speculative get_action calls per round); per-game results must equal the sequential loop."""
     n, W, D, cap = 160, 6, 8, 2500
-    out = X.host_play(n, W, D, SEED, game0=4000, max_moves=cap)
+    with X.tuning(X.PLAY_PATHS[path]):
+        out = X.host_play(n, W, D, SEED, game0=4000, max_moves=cap)
     stalled = (out["moves"] == cap) | (out["invalid"] >= 32)
     assert stalled.sum() >= 3, "choose parameters that exercise the stall path"
     ref = orc.play_games(SEED, 4000, n, W, D, max_moves=cap)
@@ -189,3 +200,85 @@ def test_dropin_modules_play_a_game_like_run_game(orc):
     ref = orc.play_game(SEED, agent._game, 4, 6, max_moves=10000)
     assert (int(info["score"]), int(np.max(state)), moves, valid, invalid) == \
         (ref.score, ref.highest_tile, ref.moves, ref.valid_moves, ref.invalid_moves)
+
+
+# ---- BASELINE.json configs 4 and 5: whole games at widths 15/20 and 20/40 ---------------------------------
+def _check_games(out, ref, n):
+    for i in range(n):
+        r = ref[i]
+        assert (out["score"][i], 1 << int(out["highest"][i]), out["moves"][i], out["valid"][i], out["invalid"][i],
+                out["nodes"][i]) == (r.score, r.highest_tile, r.moves, r.valid_moves, r.invalid_moves, r.nodes), i
+        assert list(out["milestone"][i]) == list(r.milestone_move), i
+
+
+def test_cfg4_hundred_whole_games_15_20_vs_oracle(orc):
+    """cfg 4: BeamSearchAgent(15, 20), 100 games to game over (cap 10,000 as evaluate_beam_search.py:16)."""
+    n = 100
+    out = X.host_play(n, 15, 20, SEED, game0=0, max_moves=10000)
+    ref = orc.play_games(SEED, 0, n, 15, 20, max_moves=10000)
+    _check_games(out, ref, n)
+    assert (out["highest"] >= 10).sum() >= 50 and out["stats"][22] == n      # most games reach 1024
+
+
+def test_cfg5_whole_games_20_40_vs_oracle(orc):
+    """cfg 5 width/depth: 64 games at 20/40 to game over, teams from the first move; the set holds games
+    that stall (>= 32 consecutive invalid moves -> stall breaker) and games that hit the move cap."""
+    n = 64
+    out = X.host_play(n, 20, 40, SEED, game0=0, max_moves=10000)
+    ref = orc.play_games(SEED, 0, n, 20, 40, max_moves=10000)
+    _check_games(out, ref, n)
+    assert (out["invalid"] >= 32).any() and (out["moves"] == 10000).any(), "no stalled game in the set"
+
+
+def test_cfg5_whole_games_20_40_warp_then_team_tail(orc):
+    """The many-games path of cfg 5 (one warp per game, hand-over to teams once few are left) on the same
+    64 games, and the warp-only path on a slice of them: identical results on every path."""
+    n = 64
+    ref = orc.play_games(SEED, 0, n, 20, 40, max_moves=10000)
+    with X.tuning({X.TUNE_TEAM_DIRECT_MAX: 0, X.TUNE_TAIL_THRESHOLD: 24}):
+        out = X.host_play(n, 20, 40, SEED, game0=0, max_moves=10000)
+    _check_games(out, ref, n)
+    with X.tuning(X.PLAY_PATHS["warp"]):
+        out = X.host_play(16, 20, 40, SEED, game0=0, max_moves=10000)
+    _check_games(out, ref, 16)
+
+
+def test_reference_whole_games_at_baseline_widths(golden_games):
+    """The reference's own games at 15/20 and 20/40 (oracle/make_golden_games.py), every scheduling path."""
+    seed = golden_games["seed"]
+    for path, knobs in X.PLAY_PATHS.items():
+        with X.tuning(knobs):
+            for g in golden_games["games"]:
+                out = X.host_play(1, g["W"], g["D"], seed, game0=g["game"], max_moves=g["max_moves"])
+                assert (out["score"][0], 1 << int(out["highest"][0]), out["moves"][0], out["valid"][0], out["invalid"][0]) == \
+                    (g["score"], g["highest_tile"], g["moves"], g["valid"], g["invalid"]), (path, g["game"])
+                assert int(out["final"][0]) == int(g["final"], 16) and list(out["milestone"][0]) == g["milestones"]
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["warp", "team"])
+def test_reference_get_action_calls_harvested_from_play(golden_games, mode):
+    """> 4,000 reference get_action calls on boards from real play, one call per launch (the call index
+    and game id address the beam stream, so each launch reproduces one reference call)."""
+    seed = golden_games["seed"]
+    calls = 0
+    with X.tuning({X.TUNE_SEARCH_MODE: mode}):
+        for g in golden_games["games"]:
+            boards = np.array([int(b, 16) for b in g["boards"]], np.uint64)
+            step = 1 if mode == 2 else 3                      # the one-warp form replays every third call
+            for m in range(0, len(boards), step):
+                a, p, s, k = X.host_beam(boards[m:m + 1], g["W"], g["D"], seed, game0=g["game"], call0=m)
+                assert int(a[0]) == int(g["actions"][m]), (g["game"], m)
+                calls += 1
+    assert calls >= (4000 if mode == 2 else 1300)
+
+
+def test_soak_slice(orc):
+    """A bounded slice of profiles/soak.py (random widths, depths, thresholds, legality, whole games)."""
+    import runpy, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    argv = sys.argv
+    sys.argv = ["soak.py", "12", "20261018"]
+    try:
+        runpy.run_path(os.path.join(root, "profiles", "soak.py"), run_name="__main__")
+    finally:
+        sys.argv = argv

@@ -111,3 +111,33 @@ def test_hybrid_expand(orc, golden):
         assert draws == rec["draws"] and len(outs) == len(rec["outcomes"])
         for (s, r, d), want in zip(outs, rec["outcomes"]):
             assert s.tolist() == want["state"] and r == float.fromhex(want["reward"]) and d == want["done"]
+
+
+def test_reference_whole_games_at_baseline_widths(orc, golden_games):
+    """BASELINE cfg 4 / cfg 5 widths: whole games of the live reference (evaluate_beam_search.py:16-98),
+    incl. stalls of > 32 consecutive invalid moves (fake-valid DOWN) and a 2048 game."""
+    seed = golden_games["seed"]
+    assert {(g["W"], g["D"]) for g in golden_games["games"]} >= {(15, 20), (20, 40)}
+    assert max(g["longest_invalid_streak"] for g in golden_games["games"]) >= 32
+    for g in golden_games["games"]:
+        o = orc.play_game(seed, g["game"], g["W"], g["D"], max_moves=g["max_moves"])
+        assert (o.score, o.highest_tile, o.moves, o.valid_moves, o.invalid_moves) == \
+            (g["score"], g["highest_tile"], g["moves"], g["valid"], g["invalid"])
+        assert list(o.milestone_move) == g["milestones"]
+
+
+def test_reference_get_action_calls_harvested_from_play(orc, golden_games):
+    """Every move of those games is one reference get_action(state) call: > 4,000 calls on boards from
+    real play (<= 4 empties -> depth 25, late phase, dead boards), replayed one by one."""
+    import g2048_b200 as G
+    seed = golden_games["seed"]
+    calls = few_empties = late = 0
+    for g in golden_games["games"]:
+        boards = G.unpack_boards(np.array([int(b, 16) for b in g["boards"]], np.uint64))
+        assert len(boards) == g["moves"] == len(g["actions"])
+        for m, (b, a) in enumerate(zip(boards, g["actions"])):
+            o = orc.beam_get_action(b, None, g["W"], g["D"], seed, g["game"], m)
+            assert o.action == int(a), (g["game"], m)
+            few_empties += int((b == 0).sum() <= 4); late += int(b.max() >= 1024)
+        calls += len(boards)
+    assert calls >= 4000 and few_empties >= 1000 and late >= 500
