@@ -35,7 +35,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 _lib = None
 _ready_devices = set()
-_current_device = None
 
 _vp, _i64, _i32, _u32, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64
 
@@ -62,6 +61,7 @@ _SIGNATURES = {
     "g2048_env_reset_done": ([_vp] * 6 + [_i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_step_autoreset": ([_vp] * 12 + [_i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_step": ([_vp] * 12 + [_i64, _u64, _u32, _vp], C.c_int),
+    "g2048_env_step_fused": ([_vp] * 16 + [_i64, _u64, _u32, _vp], C.c_int),
     "g2048_legal_masks": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
     "g2048_env_rollout": ([_vp] * 6 + [_i64, _i32, _u32, _u64, _u32, _vp], C.c_int),
     "g2048_evaluate": ([_vp, _vp, _vp, _i64, _vp], C.c_int),
@@ -103,16 +103,17 @@ def check(rc: int):
 
 
 def use_device(index: int):
-    """Initialises `index` on first use and makes it current for this thread."""
-    global _current_device
+    """Initialises `index` on first use and makes it the calling thread's current CUDA device.
+
+    The C ABI picks its per-device state from cudaGetDevice(), which is per THREAD and which torch
+    changes behind our back (`torch.cuda.set_device`, `with torch.cuda.device(...)`, stream contexts),
+    so the device is set on every entry instead of trusting a cache; cudaSetDevice is cheap."""
     lib = load()
     if index not in _ready_devices:
         check(lib.g2048_init(index))
         _ready_devices.add(index)
-        _current_device = index
-    elif _current_device != index:
+    else:
         check(lib.g2048_set_device(index))
-        _current_device = index
     return lib
 
 

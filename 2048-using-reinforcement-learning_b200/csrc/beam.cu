@@ -922,7 +922,8 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
 }
 
 static int g_attr_done[kMaxDevices];
-static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1};
+static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, 0};
+int step_tuning(int key) { return g_tuning[key]; }
 
 int set_tuning(int key, int value)
 {

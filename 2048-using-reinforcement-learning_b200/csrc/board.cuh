@@ -196,6 +196,59 @@ __device__ __forceinline__ uint32_t edge_sum_pairs(Board b, uint32_t total, cons
     return total - inner + corners;
 }
 
+// ---- LEFT move without tables ------------------------------------------------------------------
+// The per-step kernel makes ONE move per launch: staging 192 KiB of tables per block cannot pay and
+// reading them through L1/L2 puts two dependent memory round trips (state, then table) on a path
+// that is latency-bound end to end.  This is the same row semantics (env:116-168) as pure SWAR on a
+// half board (two rows), both rows at once:
+//   1. compress: nibble i moves left by s_i = #empty cells left of it, as two masked shifts
+//      (s_i & 1 -> one nibble, s_i & 2 -> two; adjacent tiles share s_i, so nothing collides);
+//   2. merge: e_i = (y_i == y_i+1 != 0) for i = 0..2; the scan takes a pair only if the pair before
+//      it was not taken: m0 = e0, m1 = e1 & ~m0, m2 = e2 & ~m1; the left cell gains one (a merged
+//      exponent of 16 saturates to 15, as in row_tables.h), the right cell empties;
+//   3. close the holes: cells right of a hole move one nibble left.
+// `codes` gets, on the cell that received a merge, the exponent before it (= merged exponent - 1,
+// the code of row_tables.h): one pair-table lookup per byte then gives the score and the saturation flag.
+struct HalfMove { uint32_t rows, codes; };
+__device__ __forceinline__ HalfMove move_left_half(uint32_t x)
+{
+    const uint32_t nz = nz_flags(x), z = nz ^ LSB4;
+    const uint32_t c = (z << 4) & 0xFFF0FFF0u;                                // nibble i: cell i-1 is empty
+    const uint32_t s = c + ((c << 4) & 0xFFF0FFF0u) + ((c << 8) & 0xFF00FF00u);   // empty cells left of i (0..3)
+    const uint32_t m1 = (s & nz) * 15u, m2 = ((s >> 1) & nz) * 15u;           // full-nibble masks of the movers
+    uint32_t y = (x & ~m1) | ((x & m1) >> 4);
+    const uint32_t m2a = (m2 & ~m1) | ((m2 & m1) >> 4);                       // the second mask travels with its cells
+    y = (y & ~m2a) | ((y & m2a) >> 8);
+    // merge scan over the packed row
+    const uint32_t d = y ^ (y >> 4);
+    uint32_t e = zero_flags(d) & nz_flags(y) & 0x01110111u;                    // e_i on nibble i, i = 0..2
+    e &= ~((e & 0x00010001u) << 4);                                           // m1 = e1 & ~m0
+    e &= ~((e & 0x00100010u) << 4);                                           // m2 = e2 & ~m1
+    const uint32_t em = e * 15u;
+    HalfMove r;
+    r.codes = y & em;
+    const uint32_t sat = r.codes & (r.codes >> 1) & (r.codes >> 2) & (r.codes >> 3) & LSB4;   // merging two 32768s
+    y = (y + (e ^ sat)) & ~(em << 4);
+    const uint32_t mv = (((e & 0x00110011u) << 8) | ((e & 0x00010001u) << 12)) * 15u;
+    r.rows = (y & ~mv) | ((y & mv) >> 4);
+    return r;
+}
+// Sum over the 8 bytes of the two code words of pairs[256 + byte]: merge score + saturation flags
+__device__ __forceinline__ uint32_t code_score_pairs(uint32_t codes_lo, uint32_t codes_hi, const uint32_t *pairs)
+{
+    const uint32_t *m = pairs + 256;
+    return ((m[codes_lo & 0xFFu] + m[(codes_lo >> 8) & 0xFFu]) + (m[(codes_lo >> 16) & 0xFFu] + m[codes_lo >> 24])) +
+           ((m[codes_hi & 0xFFu] + m[(codes_hi >> 8) & 0xFFu]) + (m[(codes_hi >> 16) & 0xFFu] + m[codes_hi >> 24]));
+}
+// Sum of the tile values of a board from the pair table (8 lookups)
+__device__ __forceinline__ uint32_t tile_total_pairs(Board b, const uint32_t *pairs)
+{
+    return ((pair_at(pairs, (b.lo << 2) & 0x3FCu) + pair_at(pairs, (b.lo >> 6) & 0x3FCu)) +
+            (pair_at(pairs, (b.lo >> 14) & 0x3FCu) + pair_at(pairs, (b.lo >> 22) & 0x3FCu))) +
+           ((pair_at(pairs, (b.hi << 2) & 0x3FCu) + pair_at(pairs, (b.hi >> 6) & 0x3FCu)) +
+            (pair_at(pairs, (b.hi >> 14) & 0x3FCu) + pair_at(pairs, (b.hi >> 22) & 0x3FCu)));
+}
+
 // Direction wrappers.  `to_line` brings the rows the tiles travel along into LEFT-move
 // position, `from_line` undoes it.  Lane-varying actions use selects, not branches.
 __device__ __forceinline__ Board select(bool p, Board a, Board b) { return Board(p ? a.lo : b.lo, p ? a.hi : b.hi); }

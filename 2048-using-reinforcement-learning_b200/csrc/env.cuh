@@ -72,6 +72,68 @@ __device__ __forceinline__ StepResult env_step(EnvState &s, uint32_t action, con
     return r;
 }
 
+// The same transition for the per-step kernel (env_step_fused_kernel): merge score, tile sums and
+// edge sum come from the 512-entry pair table in shared memory (board.cuh), the move itself either
+// from the row tables through L1/L2 (kSwarMove = false) or table-free (move_left_half).  Bit-exact
+// with env_step(): `shaped_reward_tracked` adds the reference's exact terms as integers.
+// Also returns the legal mask of the new board (get_valid_moves, env:69-95); done = no legal move.
+struct StepResult2 {
+    double reward;
+    uint32_t score_delta, legal;
+    bool valid, done;
+};
+template <bool kSwarMove, bool kReward>
+__device__ __forceinline__ StepResult2 env_step_pairs(EnvState &s, uint32_t action, const uint16_t *row, const uint8_t *code,
+                                                      const uint32_t *pairs, const PhiloxKey &K, uint32_t game,
+                                                      const uint32_t *inject, unsigned long long *overflow)
+{
+    StepResult2 r;
+    const Board prev = s.board;
+    const Board line = to_line(prev, action);
+    Board moved;
+    uint32_t gained;
+    if (kSwarMove) {
+        const HalfMove lo = move_left_half(line.lo), hi = move_left_half(line.hi);
+        moved = Board(lo.rows, hi.rows);
+        gained = code_score_pairs(lo.codes, hi.codes, pairs);
+    } else {
+        moved = move_left<false>(line, row);
+        gained = merge_score_pairs<false>(line, code, pairs);
+    }
+    const bool in_range = action < 4u;                                       // env:99-114 has no else branch
+    Board next = select(in_range, from_line(moved, action), prev);           // env:185
+    gained = in_range ? gained : 0u;
+    r.score_delta = gained & (kPairSaturated - 1u);
+    if (gained >> 28) atomicAdd(overflow, 1ull);                             // 32768+32768: nibble saturated
+    s.score += (int32_t)r.score_delta;
+    r.valid = next != prev;                                                  // env:188
+    uint32_t nzl = nz_flags(next.lo), nzh = nz_flags(next.hi);
+    const uint32_t zl = nzl ^ LSB4, zh = nzh ^ LSB4;
+    const int cl = __popc(zl);
+    int empty_after = cl + __popc(zh);
+    SpawnWords w;
+    if (inject) { w.pos = inject[0]; w.val = inject[1]; }
+    else w = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr);                  // computed for every lane, used by the valid ones
+    const SpawnPick sp = pick_spawn(zl, zh, cl, empty_after, w.pos, w.val);
+    if (r.valid) {                                                           // env:191-192, always >= 1 empty here
+        next.lo |= sp.flag_lo * sp.exponent;
+        next.hi |= sp.flag_hi * sp.exponent;
+        nzl |= sp.flag_lo;
+        nzh |= sp.flag_hi;
+        if (!inject) s.spawn_ctr += 1u;
+        empty_after -= 1;
+    }
+    r.reward = 0.0;
+    if (kReward)                                                             // env:195, uses the OLD highest_tile
+        r.reward = shaped_reward_tracked(r.valid, count_empty(prev), next, empty_after, nzl, nzh, r.score_delta, s.highest,
+                                         max_exponent(prev), tile_total_pairs(next, pairs), pairs);
+    r.legal = env_legal_mask(next);
+    r.done = r.legal == 0u;                                                  // env:198
+    s.highest = max(s.highest, max_exponent(next));                          // env:200-203
+    s.board = next;
+    return r;
+}
+
 // ---- fused-rollout fast path ----------------------------------------------------------------
 // Same transition as env_step(), for callers that keep an env in registers across steps and
 // therefore can carry what a step already knows into the next one: the empty count, the sum

@@ -59,7 +59,6 @@ DeviceState *current_device_state()
 #define G2048_ENV_THREADS 256
 #endif
 constexpr int kEnvThreads = G2048_ENV_THREADS;
-constexpr int kEnvSharedThreads = 512;   // one 192 KiB block per SM
 
 // Both row tables into dynamic shared memory (192 KiB) by TMA bulk copy (stage.cuh).
 __device__ __forceinline__ void stage_tables(uint8_t *smem, const uint16_t *row, const uint8_t *code, bool with_code)
@@ -74,47 +73,89 @@ struct StepArgs {
     int64_t n; PhiloxKey K; uint32_t game0;
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
     int32_t *episodes;             // non-null: reset an env right after the step that ended its game
+    // fused extras (all optional)
+    float *obs;                    // float32[n][16] observation of the board the caller acts on next
+    uint64_t *stepped;             // board after the step, BEFORE an auto-reset (the `next_state` of the transition)
+    int32_t *final_score;          // score / highest exponent after the step, before an auto-reset
+    uint8_t *final_highest;
 };
 
-// Game2048Env.step for n envs, one env per thread, one launch per step.
-template <bool kShared, int kThreads>
-__global__ void __launch_bounds__(kThreads) env_step_kernel(StepArgs a)
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor in the stream drains; `pdl_wait` blocks until that
+// predecessor has completed and its writes are visible.  Everything before it (building the
+// block's lookup tables) overlaps the predecessor's tail; without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Game2048Env.step for n envs, one env per thread, one launch per step, with everything a
+// training loop wants next to it in the same launch: legal mask, done, the reset of a finished
+// game, the policy's observation (agents/ppo_agent.py:184-195) and the pre-reset state.
+// No 192 KiB tables: the move is table-free SWAR (kSwarMove) or reads the tables through L1/L2;
+// scores and tile sums come from a 2 KiB pair table built per block.
+template <bool kSwarMove>
+__global__ void __launch_bounds__(kEnvThreads) env_step_fused_kernel(StepArgs a)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint16_t *row = a.row;
-    const uint8_t *code = a.code;
-    if (kShared) {
-        stage_tables(smem, a.row, a.code, true);
-        row = reinterpret_cast<const uint16_t *>(smem);
-        code = smem + kRowTableBytes;
-    }
+    __shared__ uint32_t pairs[kPairEntries];
+    __shared__ float obs_lut[16];
+    for (int i = threadIdx.x; i < kPairEntries; i += blockDim.x) pairs[i] = pair_table_entry(i);
+    if (threadIdx.x < 16) obs_lut[threadIdx.x] = (float)threadIdx.x / 15.0f;     // log2(tile) / 15.0 in float32
+    __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
     const bool want_reward = a.reward != nullptr || a.reward32 != nullptr;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31u;
+    // warps stay whole (the observation is written through shuffles): warp-aligned base, lane offset
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < a.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
+        const bool live = i < a.n;
         EnvState s;
-        s.board = Board(a.boards[i]);
-        s.score = a.score ? a.score[i] : 0;
-        s.highest = a.highest ? a.highest[i] : 0u;
-        s.spawn_ctr = a.spawn_ctr ? a.spawn_ctr[i] : 0u;
-        const uint32_t action = a.actions[i];
-        uint32_t inj[2];
-        if (a.inject) { inj[0] = a.inject[2 * i]; inj[1] = a.inject[2 * i + 1]; }
-        StepResult r = want_reward
-            ? env_step<kShared, kShared, true>(s, action, row, code, a.K, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow)
-            : env_step<kShared, kShared, false>(s, action, row, code, a.K, a.game0 + (uint32_t)i, a.inject ? inj : nullptr, a.overflow);
-        if (a.episodes && r.done) {                       // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
-            env_reset(s, a.K, a.game0 + (uint32_t)i);
-            a.episodes[i] += 1;
+        s.board = Board(0u, 0u); s.score = 0; s.highest = 0u; s.spawn_ctr = 0u;
+        if (live) {
+            s.board = Board(a.boards[i]);
+            s.score = a.score ? a.score[i] : 0;
+            s.highest = a.highest ? a.highest[i] : 0u;
+            s.spawn_ctr = a.spawn_ctr ? a.spawn_ctr[i] : 0u;
+            const uint32_t action = a.actions[i];
+            uint32_t inj[2];
+            if (a.inject) { inj[0] = a.inject[2 * i]; inj[1] = a.inject[2 * i + 1]; }
+            const uint32_t game = a.game0 + (uint32_t)i;
+            StepResult2 r = want_reward
+                ? env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow)
+                : env_step_pairs<kSwarMove, false>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow);
+            if (a.stepped) a.stepped[i] = s.board.u64();
+            if (a.final_score) a.final_score[i] = s.score;
+            if (a.final_highest) a.final_highest[i] = (uint8_t)s.highest;
+            if (a.episodes && r.done) {                   // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
+                env_reset(s, a.K, game);
+                a.episodes[i] += 1;
+                r.legal = env_legal_mask(s.board);
+            }
+            a.boards[i] = s.board.u64();
+            if (a.score) a.score[i] = s.score;
+            if (a.highest) a.highest[i] = (uint8_t)s.highest;
+            if (a.spawn_ctr) a.spawn_ctr[i] = s.spawn_ctr;
+            if (a.reward) a.reward[i] = r.reward;
+            if (a.reward32) a.reward32[i] = (float)r.reward;
+            if (a.score_delta) a.score_delta[i] = (int32_t)r.score_delta;
+            if (a.valid) a.valid[i] = r.valid;
+            if (a.legal) a.legal[i] = (uint8_t)r.legal;
+            if (a.done) a.done[i] = r.done;
         }
-        a.boards[i] = s.board.u64();
-        if (a.score) a.score[i] = s.score;
-        if (a.highest) a.highest[i] = (uint8_t)s.highest;
-        if (a.spawn_ctr) a.spawn_ctr[i] = s.spawn_ctr;
-        if (a.reward) a.reward[i] = r.reward;
-        if (a.reward32) a.reward32[i] = (float)r.reward;
-        if (a.score_delta) a.score_delta[i] = (int32_t)r.score_delta;
-        if (a.valid) a.valid[i] = r.valid;
-        if (a.legal) a.legal[i] = (uint8_t)env_legal_mask(s.board);
-        if (a.done) a.done[i] = r.done;
+        if (a.obs) {
+            // 32 envs x 16 floats = 2 KiB per warp, written as four fully coalesced 512-byte rows:
+            // store k, lane l writes float4 number 32k + l = cells 4q..4q+3 of env 8k + l/4, q = l%4
+            float4 *out = reinterpret_cast<float4 *>(a.obs + 16 * base);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int src = 8 * k + (int)(lane >> 2);
+                const uint32_t lo = __shfl_sync(0xFFFFFFFFu, s.board.lo, src), hi = __shfl_sync(0xFFFFFFFFu, s.board.hi, src);
+                const uint32_t q = lane & 3u;
+                const uint32_t cells = ((q & 2u) ? hi : lo) >> (16u * (q & 1u));
+                if (base + src < a.n)
+                    out[32 * k + lane] = make_float4(obs_lut[cells & 15u], obs_lut[(cells >> 4) & 15u],
+                                                     obs_lut[(cells >> 8) & 15u], obs_lut[(cells >> 12) & 15u]);
+            }
+        }
     }
 }
 
@@ -182,15 +223,25 @@ __global__ void __launch_bounds__(kRolloutThreads, 1) env_rollout_kernel(Rollout
         e.s.score = a.score[i];
         e.s.highest = a.highest[i];
         e.s.spawn_ctr = a.spawn_ctr[i];
-        track(e);
         double rsum = a.reward_sum ? a.reward_sum[i] : 0.0;
         int32_t episodes = a.episodes ? a.episodes[i] : 0;
+        int32_t steps = a.steps;
+        uint32_t t0 = a.t0;
+        // A tile-less board (only a caller can hand one in: moves keep tiles, resets place two) has no
+        // legal move: env.step reports an invalid move and game over (env:188,198), the harness resets.
+        // The step loop below only tests FULL boards for game over, so this one step is taken here.
+        if (steps > 0 && (e.s.board.lo | e.s.board.hi) == 0u) {
+            rsum = __dadd_rn(rsum, shaped_reward(false, 16, e.s.board, 16, 0u, e.s.highest, 0u));
+            env_reset(e.s, a.K, game);
+            ++episodes; --steps; ++t0;
+        }
+        track(e);
         // highest > board max only if the caller poked it (env:229): such warps take the
         // variant that maintains both per step; everybody else skips that bookkeeping.
         const bool poked = __any_sync(__activemask(), e.s.highest > e.bmax);
         bool saturated;
-        if (poked) saturated = rollout_steps<true>(e, a.steps, a.t0, a.K, game, row, code, pairs, rsum, episodes);
-        else       saturated = rollout_steps<false>(e, a.steps, a.t0, a.K, game, row, code, pairs, rsum, episodes);
+        if (poked) saturated = rollout_steps<true>(e, steps, t0, a.K, game, row, code, pairs, rsum, episodes);
+        else       saturated = rollout_steps<false>(e, steps, t0, a.K, game, row, code, pairs, rsum, episodes);
         if (saturated) atomicAdd(a.overflow, 1ull);
         a.boards[i] = e.s.board.u64();
         a.score[i] = e.s.score;
@@ -482,9 +533,24 @@ static int grid_for(int64_t n, int threads, int sm_count, int blocks_per_sm)
     return (int)(want < cap ? want : cap);
 }
 
-// Large batches amortise staging 192 KiB of tables per block; small ones read the tables
-// through L1/L2 instead.
-static bool use_shared_tables(int64_t n, int sm_count) { return n >= (int64_t)sm_count * 4096; }
+int step_tuning(int key);      // beam.cu: g2048_set_tuning values
+
+// Launch with the programmatic-serialization attribute (see pdl_wait above).
+template <typename Kernel, typename Args>
+static cudaError_t launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t stream, const Args &args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
 
 }  // namespace g2048
 
@@ -521,7 +587,6 @@ int g2048_init(int device)
     G2048_CUDA(cudaMemset(st.overflow, 0, sizeof(unsigned long long)));
     G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
     const int smem = (int)(kRowTableBytes + kCodeTableBytes);
-    G2048_CUDA(cudaFuncSetAttribute(env_step_kernel<true, kEnvSharedThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     G2048_CUDA(cudaFuncSetAttribute(env_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     st.ready = true;
     return G2048_OK;
@@ -638,21 +703,17 @@ int g2048_env_reset_done(uint64_t *boards, int32_t *score, uint8_t *highest_exp,
     G2048_LAUNCHED();
 }
 
-static int env_step_launch(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
-                           int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
-                           double *reward, float *reward32, int32_t *score_delta,
-                           uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
-                           int64_t n, uint64_t seed, uint32_t game0, void *stream)
+static int env_step_launch(StepArgs a, void *stream)
 {
-    G2048_ENTER(boards && actions);
-    StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, make_philox_key(seed), game0, st->row, st->code, st->overflow, episodes};
-    if (use_shared_tables(n, st->sm_count)) {
-        env_step_kernel<true, kEnvSharedThreads><<<st->sm_count, kEnvSharedThreads, kRowTableBytes + kCodeTableBytes, s>>>(a);
-    } else {
-        env_step_kernel<false, kEnvThreads><<<grid_for(n, kEnvThreads, st->sm_count, 16), kEnvThreads, 0, s>>>(a);
-    }
-    G2048_LAUNCHED();
+    const int64_t n = a.n;
+    G2048_ENTER(a.boards && a.actions);
+    a.row = st->row; a.code = st->code; a.overflow = st->overflow;
+    const int grid = grid_for(n, kEnvThreads, st->sm_count, 16);
+    cudaError_t e;
+    if (step_tuning(G2048_TUNE_STEP_TABLES)) e = launch_pdl(env_step_fused_kernel<false>, grid, kEnvThreads, s, a);
+    else                                     e = launch_pdl(env_step_fused_kernel<true>, grid, kEnvThreads, s, a);
+    count_launch();
+    return check_cuda(e, __func__);
 }
 
 int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spawn_inject,
@@ -661,8 +722,10 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
                    uint8_t *valid, uint8_t *legal, uint8_t *done,
                    int64_t n, uint64_t seed, uint32_t game0, void *stream)
 {
-    return env_step_launch(boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta, valid,
-                           legal, done, nullptr, n, seed, game0, stream);
+    StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
+               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, nullptr,
+               nullptr, nullptr, nullptr, nullptr};
+    return env_step_launch(a, stream);
 }
 
 int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
@@ -672,8 +735,24 @@ int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
                              int64_t n, uint64_t seed, uint32_t game0, void *stream)
 {
     if (!episodes || !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_autoreset: episodes and spawn_ctr are required");
-    return env_step_launch(boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta, valid, legal,
-                           done, episodes, n, seed, game0, stream);
+    StepArgs a{boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
+               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, episodes,
+               nullptr, nullptr, nullptr, nullptr};
+    return env_step_launch(a, stream);
+}
+
+int g2048_env_step_fused(uint64_t *boards, const uint8_t *actions,
+                         int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                         double *reward, float *reward32, int32_t *score_delta,
+                         uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
+                         float *obs, uint64_t *stepped_boards, int32_t *final_score, uint8_t *final_highest_exp,
+                         int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    if (episodes && !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_fused: auto-reset (episodes) needs spawn_ctr");
+    StepArgs a{boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
+               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, episodes,
+               obs, stepped_boards, final_score, final_highest_exp};
+    return env_step_launch(a, stream);
 }
 
 int g2048_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal, int64_t n, void *stream)

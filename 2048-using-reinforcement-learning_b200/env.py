@@ -175,12 +175,19 @@ class BatchedGame2048Env:
         self.done = torch.zeros(self.n, dtype=torch.uint8, **z)
         self.reward_sum = torch.zeros(self.n, dtype=torch.float64, **z)
         self.episodes = torch.zeros(self.n, dtype=torch.int32, **z)
+        self.obs = torch.zeros(self.n, 16, dtype=torch.float32, **z)
+        self.stepped = torch.zeros(self.n, dtype=torch.int64, **z)
+        self.final_score = torch.zeros(self.n, dtype=torch.int32, **z)
+        self.final_highest_exp = torch.zeros(self.n, dtype=torch.uint8, **z)
         self.t = 0
         names = ("boards", "score", "highest_exp", "spawn_ctr", "reward", "reward32", "score_delta", "valid", "legal",
-                 "done", "reward_sum", "episodes")
+                 "done", "reward_sum", "episodes", "obs", "stepped", "final_score", "final_highest_exp")
         self._ptrs = {k: getattr(self, k).data_ptr() for k in names}        # state tensors never move
         self._info = {"score": self.score, "valid_move": self.valid, "highest_exp": self.highest_exp,
                       "legal_mask": self.legal, "score_delta": self.score_delta, "reward32": self.reward32}
+        self._fused_info = dict(self._info, obs=self.obs, next_boards=self.stepped, final_score=self.final_score,
+                                final_highest_exp=self.final_highest_exp, episodes=self.episodes)
+        self.reset()                                   # env:27 -- the reference's constructor resets
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -246,6 +253,32 @@ class BatchedGame2048Env:
             _lib.check(rc)
         self.t += 1
         return self.boards, self.reward, self.done, self._info
+
+    def step_fused(self, actions, auto_reset=True, want_reward=True, want_obs=True):
+        """The whole per-step call of a training loop in ONE launch (g2048_env_step_fused): step, float64 /
+        float32 reward, done, the reset of finished games, and for the board the policy acts on next its
+        legal mask and float32[N,16] observation (agents/ppo_agent.py:184-195).
+
+        Returns (obs, reward float64[N], done uint8[N], info); info adds to `step`'s: `next_boards`
+        (state right after the step, before a reset -- the `next_state` of the transition), `final_score`,
+        `final_highest_exp` (what info["score"] / info["highest_tile"] read at `done`) and `episodes`."""
+        t = self.torch
+        if actions.device != self.device or actions.numel() != self.n:
+            raise ValueError(f"actions must hold one action per env ({self.n}) on {self.device}")
+        if actions.dtype != t.uint8:
+            actions = actions.to(t.uint8)
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        p = self._ptrs
+        rc = self._use().g2048_env_step_fused(
+            p["boards"], actions.data_ptr(), p["score"], p["highest_exp"], p["spawn_ctr"],
+            p["reward"] if want_reward else 0, p["reward32"] if want_reward else 0, p["score_delta"], p["valid"],
+            p["legal"], p["done"], p["episodes"] if auto_reset else 0, p["obs"] if want_obs else 0, p["stepped"],
+            p["final_score"], p["final_highest_exp"], self.n, self.seed, self.game0, self._stream())
+        if rc:
+            _lib.check(rc)
+        self.t += 1
+        return self.obs, self.reward, self.done, self._fused_info
 
     def graph(self, fn):
         """Capture `fn()` (any sequence of this env's calls and torch ops on static tensors) into a

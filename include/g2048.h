@@ -127,6 +127,20 @@ int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
                              uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
                              int64_t n, uint64_t seed, uint32_t game0, void *stream);
 
+/* The per-step call of a training loop in ONE launch: g2048_env_step, then
+ *   stepped_boards / final_score / final_highest_exp = the state right after the step (the `next_state`,
+ *                    info["score"], info["highest_tile"] a loop reads at `done`, train.py:74-133),
+ *   the reset of the envs whose game ended (only when `episodes` is given; episodes[i] += 1),
+ *   legal          = get_valid_moves of the board the caller acts on next (after a reset: the fresh one),
+ *   obs            = float32[n][16] PPOAgent.normalize_state of that board (agents/ppo_agent.py:184-195).
+ * Every output is optional; boards, actions are required. */
+int g2048_env_step_fused(uint64_t *boards, const uint8_t *actions,
+                         int32_t *score, uint8_t *highest_exp, uint32_t *spawn_ctr,
+                         double *reward, float *reward32, int32_t *score_delta,
+                         uint8_t *valid, uint8_t *legal, uint8_t *done, int32_t *episodes,
+                         float *obs, uint64_t *stepped_boards, int32_t *final_score, uint8_t *final_highest_exp,
+                         int64_t n, uint64_t seed, uint32_t game0, void *stream);
+
 /* Game2048Env.get_valid_moves (env:69-95) -> env_legal; BeamSearchAgent._check_valid_moves
  * (agent:183-192, DOWN quirk included) -> agent_legal.  Bit a = action a.  Either may be NULL. */
 int g2048_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *agent_legal,
@@ -219,8 +233,11 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *   G2048_TUNE_TEAM_DIRECT_MAX  g2048_play_games: up to this many games are played by teams from the
  *                               first move (-1 = default: twice the team slots of the device)
  *   G2048_TUNE_TAIL_THRESHOLD   g2048_play_games with more games: one warp per game until this many are
- *                               left alive, then teams (-1 = default: the team slots; 0 = never) */
-enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2, G2048_TUNE_COUNT = 3 };
+ *                               left alive, then teams (-1 = default: the team slots; 0 = never)
+ *   G2048_TUNE_STEP_TABLES      g2048_env_step*: 0 = table-free SWAR row move (default), 1 = row tables
+ *                               read through L1/L2 (the round-1 form; kept for A/B measurements) */
+enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2,
+       G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_COUNT = 4 };
 int g2048_set_tuning(int key, int value);
 
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */

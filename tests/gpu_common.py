@@ -13,8 +13,8 @@ def lib():
     return _lib.use_device(0)
 
 
-TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD = 0, 1, 2
-_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1}
+TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD, TUNE_STEP_TABLES = 0, 1, 2, 3
+_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1, TUNE_STEP_TABLES: 0}
 
 
 class tuning:

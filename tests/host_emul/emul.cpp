@@ -107,6 +107,14 @@ uint64_t emul_agent_child(uint64_t b, uint32_t action)
     }
     return env_move<false>(x, action, g_row).u64();
 }
+// table-free LEFT move of a half board (two rows): result rows in the low word, code word in the high one
+uint64_t emul_move_left_half(uint32_t x)
+{
+    const HalfMove m = move_left_half(x);
+    return ((uint64_t)m.codes << 32) | m.rows;
+}
+uint32_t emul_code_score(uint32_t codes_lo, uint32_t codes_hi) { return code_score_pairs(codes_lo, codes_hi, g_pairs); }
+uint32_t emul_tile_total(uint64_t b) { return tile_total_pairs(Board(b), g_pairs); }
 int emul_count_empty(uint64_t b) { return count_empty(Board(b)); }
 uint32_t emul_max_exponent(uint64_t b) { return max_exponent(Board(b)); }
 uint64_t emul_place_tile(uint64_t b, uint32_t pw, uint32_t vw) { Board x(b); place_tile(x, pw, vw); return x.u64(); }
@@ -171,6 +179,18 @@ void emul_env_step(EmulEnv *e, uint32_t action, const uint32_t *inject, uint64_t
                                                 inject, &g_overflow);
     e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
     o->reward = r.reward; o->score_delta = r.score_delta; o->valid = r.valid; o->done = r.done;
+}
+// the per-step kernel's transition (env_step_fused_kernel): pair-table scores, table-free or table move
+void emul_env_step_pairs(EmulEnv *e, uint32_t action, const uint32_t *inject, uint64_t seed, uint32_t game, int swar,
+                         EmulStep *o, uint32_t *legal)
+{
+    EnvState s; s.board = Board(e->board); s.score = e->score; s.highest = e->highest; s.spawn_ctr = e->spawn_ctr;
+    const PhiloxKey K = make_philox_key(seed);
+    StepResult2 r = swar ? env_step_pairs<true, true>(s, action, g_row, g_code, g_pairs, K, game, inject, &g_overflow)
+                         : env_step_pairs<false, true>(s, action, g_row, g_code, g_pairs, K, game, inject, &g_overflow);
+    e->board = s.board.u64(); e->score = s.score; e->highest = s.highest; e->spawn_ctr = s.spawn_ctr;
+    o->reward = r.reward; o->score_delta = r.score_delta; o->valid = r.valid; o->done = r.done;
+    *legal = r.legal;
 }
 // `steps` tracked steps with the random-policy action stream and auto-reset, like env_rollout_kernel
 }  // extern "C"

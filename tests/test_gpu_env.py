@@ -370,3 +370,75 @@ def test_step_autoreset_equals_step_then_reset_done():
     assert torch.equal(a_env.episodes, b_env.episodes) and int(a_env.episodes.sum()) > 0
     assert torch.equal(a_env.spawn_ctr, b_env.spawn_ctr) and torch.equal(a_env.highest_exp, b_env.highest_exp)
     assert torch.equal(a_env.legal, b_env.legal_masks())
+
+
+@pytest.mark.parametrize("tables", [0, 1], ids=["table-free", "row-tables"])
+@pytest.mark.parametrize("n", [1, 31, 77, 1000, 4097])
+def test_step_fused_vs_oracle(orc, n, tables):
+    """g2048_env_step_fused: step + reset of finished games + legal mask + observation + pre-reset state in
+    one launch, at ragged sizes (the observation is written through warp shuffles), with both row-move forms."""
+    import torch
+    steps = 140 if n <= 1000 else 40
+    env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=11)
+    env.reset()
+    envs = [orc.Env(SEED, 11 + i, ctor_reset=False) for i in range(n)]
+    for e in envs:
+        e.reset()
+    sample = sorted(set(range(min(n, 40))) | {n - 1, n // 2})
+    rng = np.random.default_rng(2)
+    episodes = np.zeros(n, np.int64)
+    with X.tuning({X.TUNE_STEP_TABLES: tables}):
+        for t in range(steps):
+            a = rng.integers(0, 4, n).astype(np.uint8)
+            obs, reward, done, info = env.step_fused(torch.from_numpy(a).cuda(), auto_reset=True)
+            torch.cuda.synchronize()
+            boards = env.boards_u64(); obs = obs.cpu().numpy(); reward = reward.cpu().numpy(); done = done.cpu().numpy()
+            nxt = info["next_boards"].cpu().numpy().view(np.uint64); legal = info["legal_mask"].cpu().numpy()
+            fs = info["final_score"].cpu().numpy(); fh = info["final_highest_exp"].cpu().numpy()
+            score = info["score"].cpu().numpy()
+            for i in sample:
+                ob, orw, od, oi = envs[i].step(int(a[i]))
+                assert nxt[i] == G.pack_board(ob) and reward[i] == orw and bool(done[i]) == od, (t, i)
+                assert fs[i] == oi["score"] and (1 << int(fh[i])) == oi["highest_tile"]
+                if od:
+                    ob = envs[i].reset()
+                    episodes[i] += 1
+                    assert score[i] == 0
+                assert boards[i] == G.pack_board(ob) and legal[i] == orc.env_legal_mask(ob)
+                assert (obs[i] == orc.ppo_observe(ob)).all()
+    assert (env.episodes.cpu().numpy()[sample] == episodes[sample]).all()
+    if n >= 1000:
+        assert episodes.sum() > 0
+
+
+def test_step_without_autoreset_matches_fused_outputs(orc):
+    """The round-1 entry points (g2048_env_step / _autoreset) run the same kernel: same results."""
+    import torch
+    n = 333
+    a_env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=5)
+    b_env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=5)
+    rng = np.random.default_rng(4)
+    for t in range(200):
+        act = torch.from_numpy(rng.integers(0, 4, n).astype(np.uint8)).cuda()
+        a_env.step(act, auto_reset=True)
+        b_env.step_fused(act, auto_reset=True)
+        assert torch.equal(a_env.boards, b_env.boards) and torch.equal(a_env.reward, b_env.reward)
+        assert torch.equal(a_env.done, b_env.done) and torch.equal(a_env.legal, b_env.legal)
+
+
+def test_constructor_resets_and_tileless_boards_end_at_once(orc):
+    """Game2048Env.__init__ resets (env:27): a fresh batched env is playable.  A tile-less board handed in by
+    the caller is an invalid move + game over for env.step (env:188,198); the fused rollout does the same."""
+    import torch
+    n, steps = 64, 50
+    env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=3)
+    assert (env.boards_u64() != 0).all()
+    ohi = (1 << env.highest_exp.cpu().numpy().astype(np.int32))       # highest_tile left by the constructor's reset
+    env.set_boards(np.zeros(n, np.uint64))
+    env.rollout(steps)
+    torch.cuda.synchronize()
+    ob = np.zeros((n, 16), np.int32); osc = np.zeros(n, np.int64)
+    octr = np.full(n, 2, np.uint32); ors = np.zeros(n, np.float64); oep = np.zeros(n, np.int32)
+    orc.rollout(ob, osc, ohi, octr, ors, oep, steps, 0, SEED, 3)
+    assert (env.boards_u64() == G.pack_boards(ob)).all() and (env.episodes.cpu().numpy() == oep).all()
+    assert (oep >= 1).all() and np.isnan(ors).all() and np.isnan(env.reward_sum.cpu().numpy()).all()

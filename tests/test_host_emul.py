@@ -48,6 +48,9 @@ def emul():
     L.emul_agent_legal.argtypes = [u64]; L.emul_agent_legal.restype = u32
     L.emul_agent_child.argtypes = [u64, u32]; L.emul_agent_child.restype = u64
     L.emul_count_empty.argtypes = [u64]; L.emul_count_empty.restype = C.c_int
+    L.emul_move_left_half.argtypes = [u32]; L.emul_move_left_half.restype = u64
+    L.emul_code_score.argtypes = [u32, u32]; L.emul_code_score.restype = u32
+    L.emul_tile_total.argtypes = [u64]; L.emul_tile_total.restype = u32
     L.emul_max_exponent.argtypes = [u64]; L.emul_max_exponent.restype = u32
     L.emul_place_tile.argtypes = [u64, u32, u32]; L.emul_place_tile.restype = u64
     L.emul_fast_eval.argtypes = [u64]; L.emul_fast_eval.restype = C.c_int
@@ -63,6 +66,7 @@ def emul():
     L.emul_random_action.argtypes = [u64, u32, u32]; L.emul_random_action.restype = u32
     L.emul_env_reset.argtypes = [C.POINTER(EmulEnv), u64, u32]
     L.emul_env_step.argtypes = [C.POINTER(EmulEnv), u32, C.POINTER(u32), u64, u32, C.POINTER(EmulStep)]
+    L.emul_env_step_pairs.argtypes = [C.POINTER(EmulEnv), u32, C.POINTER(u32), u64, u32, C.c_int, C.POINTER(EmulStep), C.POINTER(u32)]
     L.emul_rollout_tracked.argtypes = [C.POINTER(EmulEnv), C.c_int, u32, u64, u32, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     L.emul_rollout_stepwise.argtypes = L.emul_rollout_tracked.argtypes
     L.emul_row.argtypes = [u32]; L.emul_row.restype = u32
@@ -344,3 +348,66 @@ def test_row_tables_exhaustively_against_oracle(emul, orc):
         assert sum((2 << ((code >> s) & 15)) & ~3 for s in (0, 4)) == score, r
         checked += 1
     assert checked == 65536
+
+
+def test_table_free_row_move_exhaustively(emul):
+    """move_left_half (board.cuh) on all 65,536 rows, in both row slots of a half board and next to a
+    random neighbour row, against the row tables (themselves held to the oracle above): result rows,
+    merge score and saturation flag through the pair table."""
+    rng = np.random.default_rng(11)
+    other = rng.integers(0, 65536, 65536)
+    for r in range(65536):
+        row, code = emul.emul_row(r), emul.emul_code(r)
+        o = int(other[r])
+        orow, ocode = emul.emul_row(o), emul.emul_code(o)
+        score = lambda c: sum((2 << ((c >> s) & 15)) & ~3 for s in (0, 4))          # noqa: E731
+        sat = lambda c: int(((c & 15) == 15) or ((c >> 4) == 15))                      # noqa: E731
+        for x, want_rows, want_score, want_sat in ((r | (o << 16), row | (orow << 16), score(code) + score(ocode), sat(code) + sat(ocode)),
+                                                   (o | (r << 16), orow | (row << 16), score(code) + score(ocode), sat(code) + sat(ocode))):
+            m = emul.emul_move_left_half(x)
+            assert (m & 0xFFFFFFFF) == want_rows, hex(x)
+            got = emul.emul_code_score(m >> 32, 0)
+            assert (got & ((1 << 28) - 1)) == want_score and ((got >> 28) != 0) == (want_sat != 0), hex(x)
+
+
+def test_tile_total_from_pair_table(emul, orc):
+    for b in boards_for_test(orc, 200):
+        if b.max() > 32768:
+            continue
+        assert emul.emul_tile_total(packing.pack_board(b)) == int(b.astype(np.int64).sum())
+
+
+@pytest.mark.parametrize("swar", [1, 0], ids=["table-free", "row-tables"])
+def test_per_step_kernel_transition_bit_exact(emul, orc, golden, swar):
+    """env_step_pairs (what env_step_fused_kernel runs per env): trajectories with rewards, legal masks,
+    out-of-range actions, a poked highest_tile and the reference's step KATs."""
+    for g in range(40, 52):
+        o = orc.Env(SEED, g)
+        o.reset()
+        e = EmulEnv(0, 0, 0, 0)
+        emul.emul_env_reset(C.byref(e), SEED, g)
+        emul.emul_env_reset(C.byref(e), SEED, g)
+        if g % 4 == 1:                                    # highest_tile above the board maximum
+            o.s.highest_tile = 512; e.highest = 9
+        for t in range(400):
+            a = orc.lib().orc_random_action(SEED, g, t) if t % 37 else 7       # 7: not an action -> no-op, invalid
+            ob, orw, od, oi = o.step(a)
+            st = EmulStep(); legal = C.c_uint32(0)
+            emul.emul_env_step_pairs(C.byref(e), a, None, SEED, g, swar, C.byref(st), C.byref(legal))
+            assert e.board == packing.pack_board(ob), (g, t)
+            assert st.reward == orw, (g, t, st.reward, orw)
+            assert bool(st.done) == od and bool(st.valid) == oi["valid_move"] and st.score_delta == oi["score_delta"]
+            assert e.score == oi["score"] and (1 << e.highest) == oi["highest_tile"] and e.spawn_ctr == o.s.spawn_ctr
+            assert legal.value == orc.env_legal_mask(ob)
+            if od:
+                o.reset()
+                emul.emul_env_reset(C.byref(e), SEED, g)
+    for k in golden["step_kats"]:
+        e = EmulEnv(packing.pack_board(k["board"]), 0, int(k["highest_tile"]).bit_length() - 1, 0)
+        inj = (C.c_uint32 * 2)(*k["inject"])
+        st = EmulStep(); legal = C.c_uint32(0)
+        emul.emul_env_step_pairs(C.byref(e), k["action"], inj, golden["seed"], 0, swar, C.byref(st), C.byref(legal))
+        assert e.board == packing.pack_board(k["out"]) and st.reward == float.fromhex(k["reward"]), k
+        assert bool(st.done) == k["done"] and bool(st.valid) == k["valid"] and e.score == k["score"]
+        assert (1 << e.highest) == k["highest_after"] and e.spawn_ctr == 0
+    assert emul.emul_overflow() == 0
