@@ -56,6 +56,8 @@ _SIGNATURES = {
     "g2048_host_hybrid_expand": ([_vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u32], C.c_int),
     "g2048_ppo_features": ([_vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "g2048_host_ppo_features": ([_vp, _vp, _vp, _vp, _i64], C.c_int),
+    "g2048_novelty_set_init": ([_vp, _vp, _i64, _vp], C.c_int),
+    "g2048_ppo_shape_rewards": ([_vp] * 6 + [_i64, _u32, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "g2048_synthetic_boards": ([_vp, _i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_reset": ([_vp, _vp, _vp, _vp, _i64, _u64, _u32, _vp], C.c_int),
     "g2048_env_reset_done": ([_vp] * 6 + [_i64, _u64, _u32, _vp], C.c_int),

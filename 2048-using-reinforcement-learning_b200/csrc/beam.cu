@@ -652,7 +652,8 @@ struct GameCounters {
     unsigned int team_work;       // queue head of the team kernel
     unsigned int pending_count;   // stalled games handed to the stall breaker
     unsigned int finish_work;     // queue head of the stall breaker
-    unsigned int pad[2];
+    unsigned int written;         // games whose results are final (the stall breaker leaves when this reaches n)
+    unsigned int pad;
 };
 
 struct GamesArgs {
@@ -662,6 +663,7 @@ struct GamesArgs {
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
     GameCounters *ctr;
     GameState *pending;            // stalled games handed to finish_games_kernel (nullptr: play them in place)
+    unsigned int *pending_ready;   // pending[i] is complete (the stall breaker runs beside its producers)
     GameState *tail;               // live games handed to team_games_kernel once few are left (nullptr: never)
     unsigned int tail_threshold;   // ... i.e. once n - finished <= tail_threshold
 };
@@ -726,9 +728,19 @@ constexpr int kStallStreak = G2048_STALL_STREAK;
 // one-warp kernel, because few games are left (-> team kernel).  One thread calls this.
 __device__ __forceinline__ void retire_game(const GamesArgs &a, const GameState &gs, bool done, bool to_tail)
 {
-    if (done || gs.moves >= a.max_moves) { write_game(a, gs); atomicAdd(&a.ctr->finished, 1u); }
-    else if (to_tail) a.tail[atomicAdd(&a.ctr->tail_count, 1u)] = gs;
-    else { a.pending[atomicAdd(&a.ctr->pending_count, 1u)] = gs; atomicAdd(&a.ctr->finished, 1u); }
+    if (done || gs.moves >= a.max_moves) {
+        write_game(a, gs);
+        atomicAdd(&a.ctr->finished, 1u);
+        atomicAdd(&a.ctr->written, 1u);
+    } else if (to_tail) {
+        a.tail[atomicAdd(&a.ctr->tail_count, 1u)] = gs;
+    } else {
+        const unsigned int slot = atomicAdd(&a.ctr->pending_count, 1u);
+        a.pending[slot] = gs;
+        __threadfence();                                   // the entry before its flag
+        *reinterpret_cast<volatile unsigned int *>(&a.pending_ready[slot]) = 1u;
+        atomicAdd(&a.ctr->finished, 1u);
+    }
 }
 
 // Whole games (evaluate_beam_search.py:16-98), throughput form: one warp plays one game, fetching
@@ -769,45 +781,6 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         store_env(gs, s);
         if (lane == 0) retire_game(a, gs, done, to_tail);
         __syncwarp();
-    }
-}
-
-// Whole games, latency form: one TEAM of four warps plays one game (beam_search_team).  Games come
-// from `in` (hand-overs of play_games_kernel, *in_count of them) or, with in == nullptr, are the
-// fresh games 0..n-1.  The first item of a team is fixed (team-major over the grid, so that few
-// games spread over all SMs); further ones come from the queue.
-__global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a, const GameState *in)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    stage_row_table(smem, a.row);
-    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
-    const int quad = threadIdx.x >> 7;
-    TeamScratch &ts = team_scratch(smem, quad);
-    const int bar = 1 + quad;
-    const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
-    const unsigned int total = in ? a.ctr->tail_count : (unsigned int)a.n;
-    const unsigned int teams = gridDim.x * (blockDim.x >> 7);
-    unsigned int p = (unsigned int)quad * gridDim.x + blockIdx.x;
-    for (;;) {
-        if (p >= total) break;
-        EnvState s;
-        GameState gs;
-        if (in) { gs = in[p]; load_env(gs, s); }
-        else start_game(gs, s, a.P.K, a.game0 + p, p);
-        const uint32_t game = a.game0 + gs.index;
-        bool done = false;
-        while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
-            const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
-            done = play_move(gs, s, r, a, row, game);
-        }
-        store_env(gs, s);
-        if (leader) {
-            retire_game(a, gs, done, false);
-            ts.next_item = teams + atomicAdd(&a.ctr->team_work, 1u);
-        }
-        team_barrier(bar);
-        p = ts.next_item;
-        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
     }
 }
 
@@ -853,30 +826,45 @@ __global__ void __launch_bounds__(kWideWarps * 32, 1) play_games_wide_kernel(Gam
 // that finds no valid move.
 struct SpecSlot { uint32_t action; int32_t nodes; };
 
+// The whole block calls this.  It returns when every game of the g2048_play_games call is final, so
+// it may run BESIDE the producers of stalled games: entries are claimed as they are published.
 template <int kSpecWarps>
-__global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs a)
+__device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, const uint16_t *row)
 {
     constexpr int kSpecGroups = kBeamWarps / kSpecWarps;
     static_assert(kSpecGroups * kSpecWarps == kBeamWarps && kSpecWarps % kTeamWarps == 0, "groups must tile the block");
-    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ SpecSlot slots[kSpecGroups][2][kSpecWarps];
     __shared__ unsigned int next_game[kSpecGroups];
-    stage_row_table(smem, a.row);
-    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
     const uint32_t lane = threadIdx.x & 31u;
     const int group = warp / kSpecWarps, w = warp % kSpecWarps;
     const int quad = warp >> 2;                            // the group's team = its first four warps
     TeamScratch &ts = team_scratch(smem, quad);
-    const unsigned int total = a.ctr->pending_count;
     auto group_barrier = [&]() { asm volatile("barrier.sync %0, %1;" ::"r"(8 + group), "r"(kSpecWarps * 32) : "memory"); };
+    constexpr unsigned int kNone = 0xFFFFFFFFu;
     for (;;) {
-        if (w == 0 && lane == 0) next_game[group] = atomicAdd(&a.ctr->finish_work, 1u);
+        if (w == 0 && lane == 0) {
+            volatile unsigned int *head = &a.ctr->finish_work, *avail = &a.ctr->pending_count, *written = &a.ctr->written;
+            unsigned int got = kNone;
+            for (;;) {
+                const unsigned int h = *head;
+                if (h < *avail) {
+                    if (atomicCAS(&a.ctr->finish_work, h, h + 1u) != h) continue;
+                    while (*reinterpret_cast<volatile unsigned int *>(&a.pending_ready[h]) == 0u) __nanosleep(200);
+                    __threadfence();
+                    got = h;
+                    break;
+                }
+                if (*written >= (unsigned int)a.n) break;
+                __nanosleep(2000);
+            }
+            next_game[group] = got;
+        }
         group_barrier();
         const unsigned int p = next_game[group];
         group_barrier();                                   // everyone has read it before the next round rewrites it
-        if (p >= total) break;
+        if (p == kNone) break;
         GameState gs = a.pending[p];                       // every warp of the group keeps an identical copy
         const uint32_t game = a.game0 + gs.index;
         EnvState s;
@@ -917,9 +905,76 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
             buf ^= 1;
         }
         store_env(gs, s);
-        if (w == 0 && lane == 0) write_game(a, gs);
+        if (w == 0 && lane == 0) { write_game(a, gs); __threadfence(); atomicAdd(&a.ctr->written, 1u); }
     }
 }
+
+// The stall breaker on its own: after the one-warp kernel when no team kernel follows it.
+template <int kSpecWarps>
+__global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    break_stalls<kSpecWarps>(a, smem, reinterpret_cast<const uint16_t *>(smem));
+}
+
+// Whole games, latency form: one TEAM of four warps plays one game (beam_search_team).  Games come
+// from `in` (hand-overs of play_games_kernel, ctr->tail_count of them) or, with in == nullptr, are
+// the fresh games 0..n-1.  The first item of a team is fixed (team-major over the grid, so that few
+// games spread over all SMs); further ones come from the queue.  A block whose six teams have run
+// out of games turns into a stall breaker (break_stalls) until every game of the call is final: the
+// stalls are broken on the SMs the finished games leave, while the long games are still being played.
+// Always launched with kBeamThreads threads on every SM.
+template <int kSpecWarps>
+__global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a, const GameState *in)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_row_table(smem, a.row);
+    const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
+    const int quad = threadIdx.x >> 7;
+    TeamScratch &ts = team_scratch(smem, quad);
+    const int bar = 1 + quad;
+    const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
+    const unsigned int total = in ? a.ctr->tail_count : (unsigned int)a.n;
+    const unsigned int teams = gridDim.x * (blockDim.x >> 7);
+    unsigned int p = (unsigned int)quad * gridDim.x + blockIdx.x;
+    for (;;) {
+        if (p >= total) break;
+        EnvState s;
+        GameState gs;
+        if (in) { gs = in[p]; load_env(gs, s); }
+        else start_game(gs, s, a.P.K, a.game0 + p, p);
+        const uint32_t game = a.game0 + gs.index;
+        bool done = false;
+        while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
+            const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
+            done = play_move(gs, s, r, a, row, game);
+        }
+        store_env(gs, s);
+        if (leader) {
+            retire_game(a, gs, done, false);
+            ts.next_item = teams + atomicAdd(&a.ctr->team_work, 1u);
+        }
+        team_barrier(bar);
+        p = ts.next_item;
+        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
+    }
+    __syncthreads();                                       // all six teams of the block are out of games
+    break_stalls<kSpecWarps>(a, smem, row);
+}
+
+#ifdef G2048_TEAM_PROFILE
+}  // namespace g2048
+// [0..2] cycles in phases A/B/C of beam_search_team, [3] levels, [4] searches, [5] cycles in searches; resets them
+extern "C" int g2048_debug_team_profile(unsigned long long *out8)
+{
+    unsigned long long zero[8] = {0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out8, g2048::g_team_prof, sizeof zero) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(g2048::g_team_prof, zero, sizeof zero) == cudaSuccess ? 0 : -1;
+}
+namespace g2048 {
+#endif
 
 static int g_attr_done[kMaxDevices];
 static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, 0};
@@ -942,7 +997,8 @@ static int ensure_attrs()
         G2048_CUDA(cudaFuncSetAttribute(beam_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
-        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         g_attr_done[dev] = 1;
@@ -1020,16 +1076,18 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     const int64_t tail_thr = g_tuning[G2048_TUNE_TAIL_THRESHOLD] >= 0 ? g_tuning[G2048_TUNE_TAIL_THRESHOLD] : team_slots;
     const bool direct = !wide && n <= direct_max;
     const int64_t tail_cap = wide || direct ? 0 : (tail_thr < n ? tail_thr : n);
-    // scratch: counters | stalled games (any game may stall) | games handed to the team kernel
-    const size_t pending_off = 256, tail_off = pending_off + (wide ? 0 : (size_t)n * sizeof(GameState));
+    // scratch: counters | ready flags of the stalled games | stalled games (any game may stall) | games for the team kernel
+    const size_t flags_off = 256, flags_bytes = wide ? 0 : (((size_t)n * sizeof(unsigned int) + 255) & ~(size_t)255);
+    const size_t pending_off = flags_off + flags_bytes, tail_off = pending_off + (wide ? 0 : (size_t)n * sizeof(GameState));
     LaunchScratch scratch;
-    rc = scratch.alloc(tail_off + (size_t)tail_cap * sizeof(GameState), sizeof(GameCounters), stream);
+    rc = scratch.alloc(tail_off + (size_t)tail_cap * sizeof(GameState), pending_off, stream);
     if (rc != G2048_OK) return rc;
     uint8_t *base = static_cast<uint8_t *>(scratch.ptr);
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
                 st->row, st->code, st->overflow, reinterpret_cast<GameCounters *>(base),
                 wide ? nullptr : reinterpret_cast<GameState *>(base + pending_off),
+                wide ? nullptr : reinterpret_cast<unsigned int *>(base + flags_off),
                 tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_cap};
     const int grid = (int)(n < st->sm_count ? n : st->sm_count);    // spread small runs over all SMs (see beam search)
     if (wide) {                                                     // wide beams: compatibility path, no stall breaker
@@ -1039,25 +1097,25 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
         count_launch();
         return check_cuda(cudaGetLastError(), "play_games_wide_kernel");
     }
+    // ~5 % of games stall.  Up to 2048 games that is at most ~100 of them: a whole SM (24 speculative calls
+    // per round) each; beyond, three games per SM (8 calls per round each).
+    const bool whole_sm = n <= 2048;
     if (direct) {
-        int64_t per_block = (n + grid - 1) / grid;
-        int threads = kTeamThreads * (int)(per_block < teams_per_block ? per_block : teams_per_block);
-        team_games_kernel<<<grid, threads, kBeamSmemBytes, stream>>>(a, nullptr);
+        if (whole_sm) team_games_kernel<kBeamWarps><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, nullptr);
+        else          team_games_kernel<8><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, nullptr);
         count_launch();
-        G2048_CUDA(cudaGetLastError());
-    } else {
-        play_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a);
-        count_launch();
-        G2048_CUDA(cudaGetLastError());
-        if (tail_cap) {                                             // how many were handed over is only known on the device
-            team_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
-            count_launch();
-            G2048_CUDA(cudaGetLastError());
-        }
+        return check_cuda(cudaGetLastError(), "team_games_kernel");
     }
-    // stalled games: kSpecWarps warps each (how many there are is only known on the device, so the
-    // grid is sized for the worst case and surplus groups leave at once)
-    if (n <= 2048) {            // ~5 % of games stall: up to ~100 of them, one SM each
+    play_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a);
+    count_launch();
+    G2048_CUDA(cudaGetLastError());
+    if (tail_cap) {                                                 // how many were handed over is only known on the device
+        if (whole_sm) team_games_kernel<kBeamWarps><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
+        else          team_games_kernel<8><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "team_games_kernel");
+    }
+    if (whole_sm) {
         finish_games_kernel<kBeamWarps><<<grid, kBeamThreads, kBeamSmemBytes, stream>>>(a);
     } else {
         int64_t groups = (n + 2) / 3;

@@ -460,6 +460,74 @@ __global__ void ppo_features_kernel(const uint64_t *boards, float *obs, double *
     }
 }
 
+// ---- PPOAgent.remember's reward shaping (agents/ppo_agent.py:234-269), SURVEY 8f row 1 -----------------
+// The agent's `seen_states` set as an open-addressing table of packed boards.  One agent remembers the
+// transitions of all n envs in env order, every step; to reproduce that order in parallel a slot carries a
+// CLAIM = (step << 32 | env): claims only shrink (atomicMin) and steps grow, so after the insert pass
+// a slot holds the first step the board was ever seen in and the lowest env that saw it then -- exactly the
+// env whose `state_hash not in self.seen_states` test succeeds in the sequential loop.
+constexpr int kNoveltyProbes = 256;
+__device__ __forceinline__ uint64_t novelty_key(uint64_t board) { return board ? board : ~0ull; }   // 0 marks a free slot
+__device__ __forceinline__ uint64_t novelty_hash(uint64_t k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return k;
+}
+__global__ void novelty_insert_kernel(const uint64_t *next_boards, unsigned long long *keys, unsigned long long *claims,
+                                      uint64_t mask, uint32_t step, int64_t n, unsigned long long *dropped)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = novelty_key(next_boards[i]);
+        uint64_t slot = novelty_hash(key) & mask;
+        bool placed = false;
+        for (int probe = 0; probe < kNoveltyProbes; ++probe, slot = (slot + 1) & mask) {
+            const unsigned long long old = atomicCAS(&keys[slot], 0ull, key);
+            if (old == 0ull || old == key) {
+                atomicMin(&claims[slot], ((unsigned long long)step << 32) | (unsigned long long)(uint32_t)i);
+                placed = true;
+                break;
+            }
+        }
+        if (!placed && dropped) atomicAdd(dropped, 1ull);                  // table (nearly) full: the state is not recorded
+    }
+}
+__global__ void ppo_shape_kernel(const uint64_t *state_boards, const uint64_t *next_boards, const double *reward_in,
+                                 uint8_t *highest_seen, const unsigned long long *keys, const unsigned long long *claims,
+                                 uint64_t mask, uint32_t step, double *reward_out, uint8_t *novel_out, int64_t n)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const Board cur(state_boards[i]), nxt(next_boards[i]);
+        const uint32_t cur_max = max_exponent(cur), nxt_max = max_exponent(nxt);
+        double reward = reward_in[i];
+        uint32_t seen = highest_seen[i];
+        if (nxt_max > seen) {                                              // ppo_agent.py:241-246
+            reward = __dadd_rn(reward, __dmul_rn(5.0, (double)(int)(nxt_max - seen)));
+            highest_seen[i] = (uint8_t)nxt_max;
+        }
+        if (nxt_max < cur_max)                                             // :249-251
+            reward = __dadd_rn(reward, __dmul_rn(-2.0, (double)(int)(cur_max - nxt_max)));
+        reward = __dadd_rn(reward, ppo_top4_bonus(nxt));                   // :254-256
+        bool novel = false;
+        if (keys) {                                                        // :259-262
+            const unsigned long long key = novelty_key(next_boards[i]);
+            uint64_t slot = novelty_hash(key) & mask;
+            for (int probe = 0; probe < kNoveltyProbes; ++probe, slot = (slot + 1) & mask) {
+                const unsigned long long k = keys[slot];
+                if (k == key) { novel = claims[slot] == (((unsigned long long)step << 32) | (unsigned long long)(uint32_t)i); break; }
+                if (k == 0ull) break;
+            }
+        }
+        if (novel) reward = __dadd_rn(reward, 0.2);
+        reward = __dadd_rn(reward, __dmul_rn(0.3, ppo_heuristic(nxt)));    // :265-266
+        reward_out[i] = reward;
+        if (novel_out) novel_out[i] = novel;
+    }
+}
+
 __global__ void synthetic_kernel(uint64_t *boards, int64_t n, PhiloxKey K, uint32_t game0)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -536,8 +604,8 @@ static int grid_for(int64_t n, int threads, int sm_count, int blocks_per_sm)
 int step_tuning(int key);      // beam.cu: g2048_set_tuning values
 
 // Launch with the programmatic-serialization attribute (see pdl_wait above).
-template <typename Kernel, typename Args>
-static cudaError_t launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t stream, const Args &args)
+template <typename... Params, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(Params...), int grid, int threads, cudaStream_t stream, Args... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -549,7 +617,7 @@ static cudaError_t launch_pdl(Kernel kernel, int grid, int threads, cudaStream_t
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args);
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
 }  // namespace g2048
@@ -676,6 +744,38 @@ int g2048_ppo_features(const uint64_t *boards, float *obs, double *heuristic, do
     G2048_ENTER(boards);
     ppo_features_kernel<<<grid_for(n, 256, st->sm_count, 8), 256, 0, s>>>(boards, obs, heuristic, top4_bonus, n);
     G2048_LAUNCHED();
+}
+
+int g2048_novelty_set_init(uint64_t *set_keys, uint64_t *set_claims, int64_t capacity, void *stream)
+{
+    const int64_t n = capacity;
+    G2048_ENTER(set_keys && set_claims && (capacity & (capacity - 1)) == 0);
+    G2048_CUDA(cudaMemsetAsync(set_keys, 0, (size_t)capacity * sizeof(uint64_t), s));
+    return check_cuda(cudaMemsetAsync(set_claims, 0xFF, (size_t)capacity * sizeof(uint64_t), s), __func__);
+}
+
+int g2048_ppo_shape_rewards(const uint64_t *state_boards, const uint64_t *next_boards, const double *reward_in,
+                            uint8_t *highest_seen_exp, uint64_t *set_keys, uint64_t *set_claims, int64_t set_capacity,
+                            uint32_t step, double *reward_out, uint8_t *novel, uint64_t *set_dropped,
+                            int64_t n, void *stream)
+{
+    G2048_ENTER(state_boards && next_boards && reward_in && highest_seen_exp && reward_out &&
+                (!set_keys || (set_claims && set_capacity > 0 && (set_capacity & (set_capacity - 1)) == 0)));
+    const int grid = grid_for(n, 256, st->sm_count, 8);
+    const uint64_t mask = set_keys ? (uint64_t)set_capacity - 1 : 0;
+    if (set_keys) {
+        cudaError_t e = launch_pdl(novelty_insert_kernel, grid, 256, s, next_boards,
+                                   reinterpret_cast<unsigned long long *>(set_keys),
+                                   reinterpret_cast<unsigned long long *>(set_claims), mask, step, n,
+                                   reinterpret_cast<unsigned long long *>(set_dropped));
+        count_launch();
+        G2048_CUDA(e);
+    }
+    cudaError_t e = launch_pdl(ppo_shape_kernel, grid, 256, s, state_boards, next_boards, reward_in, highest_seen_exp,
+                               reinterpret_cast<const unsigned long long *>(set_keys),
+                               reinterpret_cast<const unsigned long long *>(set_claims), mask, step, reward_out, novel, n);
+    count_launch();
+    return check_cuda(e, __func__);
 }
 
 int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t game0, void *stream)

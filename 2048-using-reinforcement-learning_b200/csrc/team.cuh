@@ -22,7 +22,7 @@ constexpr uint32_t kTeamRing = 512;                  // spawn ordinals held per 
 
 struct __align__(16) TeamScratch {
     uint4 rng[kTeamRing / 2];       // spawn words of ordinals [ring_end - 512, ring_end): one Philox block per entry
-    double score[kTeamThreads];     // float64 scores of a full-evaluation level, generation order
+    double score[kTeamThreads + 8]; // float64 scores of a full-evaluation level, generation order (+ padding of a chunk)
     uint32_t key[kTeamThreads];     // sort keys by thread (action * 32 + parent rank); 0 = no child
     uint64_t beam[32];              // parents of the level, rank order
     uint32_t ballots[8];            // [a]: valid children of action a (bit = parent rank); [4 + a]: those that draw
@@ -32,6 +32,21 @@ struct __align__(16) TeamScratch {
     uint32_t next_item;             // work-queue hand-off of the kernels built on the team
 };
 static_assert(sizeof(TeamScratch) <= kTeamWarps * sizeof(WarpScratch), "a team reuses the scratch of its four warps");
+
+// -DG2048_TEAM_PROFILE: cycles per phase of the team search, summed by each team's first thread
+// (profiles/tail.py reads them through g2048_debug_team_profile; never part of the product build)
+#ifdef G2048_TEAM_PROFILE
+__device__ unsigned long long g_team_prof[8];
+#define TEAM_PROF_DECL long long _tp = clock64(), _tp0 = _tp; unsigned long long _pa = 0, _pb = 0, _pc = 0, _pl = 0
+#define TEAM_PROF_MARK(acc) do { const long long _n = clock64(); acc += (unsigned long long)(_n - _tp); _tp = _n; } while (0)
+#define TEAM_PROF_FLUSH() do { if (tid == 0u) { atomicAdd(&g_team_prof[0], _pa); atomicAdd(&g_team_prof[1], _pb); \
+    atomicAdd(&g_team_prof[2], _pc); atomicAdd(&g_team_prof[3], _pl); atomicAdd(&g_team_prof[4], 1ull); \
+    atomicAdd(&g_team_prof[5], (unsigned long long)(clock64() - _tp0)); } } while (0)
+#else
+#define TEAM_PROF_DECL
+#define TEAM_PROF_MARK(acc)
+#define TEAM_PROF_FLUSH()
+#endif
 
 __device__ __forceinline__ void team_barrier(int id)
 {
@@ -48,6 +63,40 @@ __device__ __forceinline__ Board agent_child_uniform(Board b, uint32_t action, c
     case 2: return flip_rows(move_left<true>(flip_rows(b), row));
     default: return transpose(flip_row_order(move_left<true>(flip_rows(transpose(b)), row)));
     }
+}
+
+// #keys of the level larger than `key`: the keys of action a sit at keys[32a .. 32a + holders),
+// unused slots are 0.  kGroups 16-byte groups per action, fully unrolled with four independent
+// accumulators: the loads are broadcasts, the compares independent, so a lone warp issues them
+// back to back instead of walking one dependent chain.
+template <int kGroups>
+__device__ __forceinline__ uint32_t count_larger_keys(const uint32_t *keys, uint32_t key)
+{
+    uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + 32 * a);
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const uint4 k = k4[g];
+            // keys are below 2^31, so the sign of key - k is "k is larger": a subtract and a shift-add
+            // (LEA.HI) per key instead of compare / increment / select
+            r0 += (key - k.x) >> 31; r1 += (key - k.y) >> 31; r2 += (key - k.z) >> 31; r3 += (key - k.w) >> 31;
+        }
+    }
+    return (r0 + r1) + (r2 + r3);
+}
+// #scores among score[0 .. n) larger than `mine`; score[n .. n + 7] must hold -inf (chunks of 8)
+__device__ __forceinline__ int count_larger_scores(const double *score, int n, double mine)
+{
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    for (int j = 0; j < n; j += 8) {
+        const double2 a = *reinterpret_cast<const double2 *>(score + j), b = *reinterpret_cast<const double2 *>(score + j + 2);
+        const double2 c = *reinterpret_cast<const double2 *>(score + j + 4), d = *reinterpret_cast<const double2 *>(score + j + 6);
+        r0 += (a.x > mine ? 1 : 0) + (c.x > mine ? 1 : 0); r1 += (a.y > mine ? 1 : 0) + (c.y > mine ? 1 : 0);
+        r2 += (b.x > mine ? 1 : 0) + (d.x > mine ? 1 : 0); r3 += (b.y > mine ? 1 : 0) + (d.y > mine ? 1 : 0);
+    }
+    return (r0 + r1) + (r2 + r3);
 }
 
 // All 128 threads of the team call this with the same root / parameters; `bar` is the team's
@@ -82,6 +131,7 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
     uint32_t ring_end = 0u;      // ts.rng holds the spawn words of ordinals [ring_end - 512, ring_end)
     const uint32_t *corners = corner_table();
 
+    TEAM_PROF_DECL;
     for (int d = 0; d < depth; ++d) {
         // a level draws at most 128 spawns; one pass (a Philox block per thread) adds 256 ordinals and
         // overwrites ordinals below ring_end - 256, all consumed (spawn_base > ring_end - 128)
@@ -109,6 +159,7 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
         const uint32_t vb = __ballot_sync(FULL, valid), db = __ballot_sync(FULL, draws);
         if (lane == 0u) { ts.ballots[tw] = vb; ts.ballots[4u + tw] = db; }
         team_barrier(bar);                                              // (1) ballots (and the ring) are visible
+        TEAM_PROF_MARK(_pa);
         const uint4 V = *reinterpret_cast<const uint4 *>(&ts.ballots[0]);
         const uint4 D = *reinterpret_cast<const uint4 *>(&ts.ballots[4]);
         const int n_valid = (__popc(V.x) + __popc(V.y)) + (__popc(V.z) + __popc(V.w));
@@ -158,9 +209,9 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
             // separated by the generation index in the key (Python's stable sort)
             full = full_eval_flags(b, nzl, nzh, n_empty, emax, phase, corners);
             if (valid) ts.score[pos] = full;
+            if (tid < 8u) ts.score[n_valid + (int)tid] = -INFINITY;       // padding of the last chunk of 8
             team_barrier(bar);
-            int larger = 0;
-            for (int j = 0; j < n_valid; ++j) larger += ts.score[j] > full ? 1 : 0;
+            const int larger = count_larger_scores(ts.score, n_valid, full);
             if (valid) key = ((uint32_t)(n_valid - larger) << 9) | tail;
         } else {
             const int fast = fast_eval_flags(b, nzl, nzh, n_empty, emax, corners);
@@ -168,18 +219,15 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
         }
         ts.key[tid] = key;
         team_barrier(bar);                                              // (2) all keys of the level are visible
+        TEAM_PROF_MARK(_pb);
 
         // ---- C: stable top-k by counting (agent:131-132,174-175) -----------------------------------------
-        const int holders = d == 0 ? 1 : nb;                            // lanes of each warp that held a parent
-        uint32_t rank = 0u;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const uint4 *k4 = reinterpret_cast<const uint4 *>(&ts.key[32 * a]);
-            for (int l = 0; l < holders; l += 4) {
-                const uint4 k = k4[l >> 2];
-                rank += (k.x > key ? 1u : 0u) + (k.y > key ? 1u : 0u) + (k.z > key ? 1u : 0u) + (k.w > key ? 1u : 0u);
-            }
-        }
+        const int groups = d == 0 ? 1 : (nb + 3) >> 2;                 // 16-byte key groups per action in use
+        uint32_t rank;
+        if (groups <= 4)      rank = count_larger_keys<4>(ts.key, key);
+        else if (groups == 5) rank = count_larger_keys<5>(ts.key, key);
+        else if (groups == 6) rank = count_larger_keys<6>(ts.key, key);
+        else                  rank = count_larger_keys<8>(ts.key, key);
         nb = min(P.width, n_valid);
         if (valid && (int)rank < nb) {
             ts.beam[rank] = b.u64();
@@ -190,7 +238,12 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
             }
         }
         team_barrier(bar);                                              // (3) the next level's parents are in place
+        TEAM_PROF_MARK(_pc);
+#ifdef G2048_TEAM_PROFILE
+        ++_pl;
+#endif
     }
+    TEAM_PROF_FLUSH();
     res.action = ts.out_first;                                          // agent:178
     res.best = ts.out_best;
     res.prob = 1.0f;

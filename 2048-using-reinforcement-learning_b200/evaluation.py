@@ -5,7 +5,8 @@ The returned dict and the `overall_results.json` it writes have the reference's 
 (`scores`, `highest_tiles`, `moves`, `valid_moves`, `invalid_moves`, `milestones`, `best_games`,
 `parameters`), so the reference's `create_visualizations(results, save_dir, k, d)` consumes them
 unchanged.  With torch.distributed initialised, games are sharded over the ranks by global
-game id and gathered on rank 0; the statistics vector is all-reduced (NCCL over NVLink).
+game id; the per-game columns are all-gathered as one int32 tensor and the statistics vector is
+all-reduced (NCCL over NVLink).
 """
 from __future__ import annotations
 
@@ -38,18 +39,28 @@ def best_games(scores, k=5):
 GAME_KEYS = ("score", "highest_exp", "moves", "valid", "invalid", "milestone")
 
 
-def gather_games(host, group=None):
-    """Per-rank per-game arrays (each rank holds the contiguous game-id range of `shard_range`) ->
-    the full arrays in global game order on rank 0; other ranks keep their shard.  No-op without
-    torch.distributed."""
+def gather_games(out, num_games, group=None):
+    """Per-rank per-game device tensors (each rank holds the contiguous game-id range of `shard_range`)
+    -> host arrays in global game order, on every rank.  The 13 per-game columns travel as ONE int32
+    tensor per rank in a tensor all_gather (NCCL over NVLink on GPUs, gloo in the CPU tests): no pickling
+    through the host.  Without torch.distributed it is just the device->host copy."""
+    import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return host
-    gathered = [None] * dist.get_world_size(group)
-    dist.all_gather_object(gathered, host, group=group)
-    if dist.get_rank(group) == 0:
-        return {k: np.concatenate([g[k] for g in gathered]) for k in host}
-    return host
+    cols = torch.cat([out["score"].to(torch.int32).unsqueeze(1), out["highest_exp"].to(torch.int32).unsqueeze(1),
+                      out["moves"].to(torch.int32).unsqueeze(1), out["valid"].to(torch.int32).unsqueeze(1),
+                      out["invalid"].to(torch.int32).unsqueeze(1), out["milestone"].to(torch.int32)], dim=1)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        sizes = [shard_range(num_games, r, world) for r in range(world)]
+        most = max(hi - lo for lo, hi in sizes)
+        padded = torch.zeros(most, cols.shape[1], dtype=torch.int32, device=cols.device)
+        padded[:cols.shape[0]] = cols
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded, group=group)
+        cols = torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+    host = cols.cpu().numpy()
+    return {"score": host[:, 0], "highest_exp": host[:, 1], "moves": host[:, 2], "valid": host[:, 3],
+            "invalid": host[:, 4], "milestone": host[:, 5:13]}
 
 
 def compile_results(score, highest_exp, moves, valid, invalid, milestone, beam_width, search_depth):
@@ -84,8 +95,7 @@ def write_overall_results(results, save_dir):
 def run_evaluation(num_games=1000, beam_width=15, search_depth=20, render_freq=None, save_dir="results",
                    max_moves=10000, seed=None, device=None, timestamp=True):
     """Drop-in for evaluate_beam_search.run_evaluation.  `render_freq` is accepted and ignored
-    (no per-move rendering of batched games).  Returns the results dict (on every rank; the
-    per-game lists are complete on rank 0, other ranks get their own shard)."""
+    (no per-move rendering of batched games).  Returns the results dict (the same on every rank)."""
     import torch
     import torch.distributed as dist
 
@@ -93,7 +103,12 @@ def run_evaluation(num_games=1000, beam_width=15, search_depth=20, render_freq=N
     rank = dist.get_rank() if distributed else 0
     world = dist.get_world_size() if distributed else 1
     if device is None:
-        device = f"cuda:{torch.cuda.current_device()}"
+        # under torch.distributed one process drives one GPU: LOCAL_RANK unless the caller already chose a device
+        local = os.environ.get("LOCAL_RANK")
+        if distributed and local is not None and torch.cuda.current_device() == 0:
+            device = f"cuda:{int(local) % max(torch.cuda.device_count(), 1)}"
+        else:
+            device = f"cuda:{torch.cuda.current_device()}"
     if seed is None:
         seed = _random.getrandbits(64)
         if distributed:                       # every rank must use rank 0's seed
@@ -104,7 +119,7 @@ def run_evaluation(num_games=1000, beam_width=15, search_depth=20, render_freq=N
     search = BatchedBeamSearch(beam_width, search_depth, device, seed=seed)
     out = search.play_games(hi - lo, max_moves=max_moves, game0=lo)
     stats = all_reduce_stats(out["stats"])
-    host = gather_games({k: out[k].cpu().numpy() for k in GAME_KEYS})
+    host = gather_games(out, num_games)
     results = compile_results(host["score"], host["highest_exp"], host["moves"], host["valid"], host["invalid"],
                               host["milestone"], beam_width, search_depth)
     results["parameters"]["num_games"] = num_games

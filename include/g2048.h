@@ -68,6 +68,25 @@ int g2048_observe(const uint64_t *boards, float *obs, int64_t n, void *stream);
  * top4_bonus = 0.1 * sum(log2 of the four largest tiles) (:251-254).  Outputs optional. */
 int g2048_ppo_features(const uint64_t *boards, float *obs, double *heuristic, double *top4_bonus,
                        int64_t n, void *stream);
+/* PPOAgent.remember's reward shaping (agents/ppo_agent.py:234-269) for n transitions (state, next_state,
+ * reward) in one call, float64 in the reference's order:
+ *   + 5 * (log2 max(next) - log2 highest_tile_seen) when next_state holds a new highest tile (:241-246;
+ *     highest_seen_exp[i] = log2 of the running maximum of env i, in/out, start it at 1 = tile 2, :171),
+ *   - 2 * (log2 max(state) - log2 max(next)) when the maximum regressed (:249-251),
+ *   + 0.1 * sum(log2 of the four largest tiles) (:254-256),
+ *   + 0.2 when next_state was not in the agent's seen_states (:259-262), then it is added,
+ *   + 0.3 * evaluate_heuristic(next_state) (:265-266).
+ * seen_states is ONE set for the whole batch, an open-addressing table the caller owns (set_keys /
+ * set_claims, uint64[set_capacity], capacity a power of two, prepared by g2048_novelty_set_init; pass NULL
+ * to leave the novelty term out).  The result equals calling remember() for env 0, 1, ..., n-1 in order:
+ * of several envs reaching the same new board in one call the lowest env gets the bonus.  `step` must grow
+ * with every call on the same table.  novel[i] (optional) = the bonus was given; *set_dropped (optional,
+ * device counter) counts states that found no slot within 256 probes (size the table for < 70 % load). */
+int g2048_novelty_set_init(uint64_t *set_keys, uint64_t *set_claims, int64_t set_capacity, void *stream);
+int g2048_ppo_shape_rewards(const uint64_t *state_boards, const uint64_t *next_boards, const double *reward_in,
+                            uint8_t *highest_seen_exp, uint64_t *set_keys, uint64_t *set_claims, int64_t set_capacity,
+                            uint32_t step, double *reward_out, uint8_t *novel, uint64_t *set_dropped,
+                            int64_t n, void *stream);
 /* Synthetic mid-game boards: cell empty w.p. ~0.3 else 2^U{1..11} (bench workloads). */
 int g2048_synthetic_boards(uint64_t *boards, int64_t n, uint64_t seed, uint32_t game0, void *stream);
 

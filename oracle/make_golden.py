@@ -242,6 +242,29 @@ def main():
                       "top4_bonus": float(0.1 * sum(np.log2(t) for t in top if t > 0)).hex()})
     G["ppo"] = feats
 
+    # ---- PPOAgent.remember's stored reward (agents/ppo_agent.py:234-269) along one random-policy game sequence
+    class Memory:
+        def add(self, state, action, prob, reward, next_state, done):
+            self.reward = reward
+    import contextlib, io
+    ag_ppo = object.__new__(PPO)
+    ag_ppo.highest_tile_seen = 2; ag_ppo.highest_tile_history = []; ag_ppo.seen_states = set()
+    ag_ppo.novelty_factor = 0.2; ag_ppo.heuristic_weight = 0.3; ag_ppo.memory = Memory()
+    shim.select(P.DOM_ENV, 4242, 0, 0)
+    env = game.Game2048Env()
+    state = env.reset()
+    rem = []
+    for t in range(400):
+        a = P.random_action(SEED, 4242, t)
+        nxt, r, d, info = env.step(a)
+        known = hash(nxt.tobytes()) in ag_ppo.seen_states
+        with contextlib.redirect_stdout(io.StringIO()):
+            ag_ppo.remember(state.copy(), a, 0.0, r, nxt.copy(), d)
+        rem.append({"state": L(state), "next": L(nxt), "reward": float(r).hex(), "novel": not known,
+                    "stored": float(ag_ppo.memory.reward).hex(), "highest_seen": int(ag_ppo.highest_tile_seen)})
+        state = env.reset() if d else nxt
+    G["ppo_remember"] = rem
+
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(G, f, separators=(",", ":"))

@@ -462,6 +462,27 @@ double orc_ppo_top4_bonus(const int32_t b[16])
     return 0.1 * sum;
 }
 
+/* ppo_agent.py:234-269 PPOAgent.remember: the reward it stores.  `highest_tile_seen` is the agent's
+ * running maximum (in/out, starts at 2, :171); `novel` says whether hash(next_state.tobytes()) was absent
+ * from agent.seen_states (:257-260; the caller keeps the set).  float64, the reference's order. */
+double orc_ppo_shape_reward(const int32_t state[16], const int32_t next_state[16], double reward,
+                            int32_t *highest_tile_seen, int novel)
+{
+    int32_t cur = 0, nxt = 0;
+    for (int i = 0; i < 16; ++i) { if (state[i] > cur) cur = state[i]; if (next_state[i] > nxt) nxt = next_state[i]; }
+    if (nxt > *highest_tile_seen) {                                        /* :241-246 */
+        double tile_bonus = 5.0 * ((double)ilog2(nxt) - (double)ilog2(*highest_tile_seen));
+        *highest_tile_seen = nxt;
+        reward += tile_bonus;
+    }
+    if (nxt < cur)                                                         /* :249-251 (nxt > 0 on this path) */
+        reward += -2.0 * ((double)ilog2(cur) - (double)ilog2(nxt));
+    reward += orc_ppo_top4_bonus(next_state);                              /* :254-256 */
+    if (novel) reward += 0.2;                                              /* :259-262, novelty_factor :175 */
+    reward += 0.3 * orc_ppo_heuristic(next_state);                         /* :265-266, heuristic_weight :181 */
+    return reward;
+}
+
 typedef struct { int32_t board[16]; int first; double score; } cand_t;
 
 /* sorted(..., key=score, reverse=True)[:k]  -- Python's sort is stable, so equal

@@ -86,6 +86,9 @@ int orc_phase(int32_t max_tile, int32_t early_thr, int32_t mid_thr);  /* :271-27
 void orc_ppo_observe(const int32_t board[16], float obs[16]);      /* :184-195 */
 double orc_ppo_heuristic(const int32_t board[16]);                 /* :271-333 */
 double orc_ppo_top4_bonus(const int32_t board[16]);                /* :251-254 */
+/* :234-269 the reward PPOAgent.remember stores; highest_tile_seen in/out, novel = state not yet in seen_states */
+double orc_ppo_shape_reward(const int32_t state[16], const int32_t next_state[16], double reward,
+                            int32_t *highest_tile_seen, int novel);
 
 typedef struct {
     int32_t action;        /* chosen action                                */

@@ -83,6 +83,8 @@ def lib():
         L.orc_ppo_top4_bonus.argtypes = [i32p]
         L.orc_ppo_top4_bonus.restype = C.c_double
         L.orc_ppo_observe.argtypes = [i32p, C.POINTER(C.c_float)]
+        L.orc_ppo_shape_reward.argtypes = [i32p, i32p, C.c_double, i32p, C.c_int]
+        L.orc_ppo_shape_reward.restype = C.c_double
         L.orc_phase.argtypes = [C.c_int32] * 3
         L.orc_phase.restype = C.c_int
         L.orc_beam_get_action.argtypes = [i32p, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32,
@@ -175,6 +177,13 @@ def ppo_heuristic(board):
 
 def ppo_top4_bonus(board):
     return lib().orc_ppo_top4_bonus(_b(board))
+
+
+def ppo_shape_reward(state, next_state, reward, highest_tile_seen, novel):
+    """-> (shaped reward, new highest_tile_seen), agents/ppo_agent.py:234-269"""
+    h = C.c_int32(int(highest_tile_seen))
+    r = lib().orc_ppo_shape_reward(_b(state), _b(next_state), float(reward), C.byref(h), int(bool(novel)))
+    return r, h.value
 
 
 def ppo_observe(board):

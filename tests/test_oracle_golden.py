@@ -141,3 +141,11 @@ def test_reference_get_action_calls_harvested_from_play(orc, golden_games):
             few_empties += int((b == 0).sum() <= 4); late += int(b.max() >= 1024)
         calls += len(boards)
     assert calls >= 4000 and few_empties >= 1000 and late >= 500
+
+
+def test_ppo_remember_sequence(orc, golden):
+    highest = 2
+    for rec in golden["ppo_remember"]:
+        want, highest = orc.ppo_shape_reward(rec["state"], rec["next"], float.fromhex(rec["reward"]), highest, rec["novel"])
+        assert want == float.fromhex(rec["stored"]) and highest == rec["highest_seen"], rec
+    assert any(r["novel"] for r in golden["ppo_remember"]) and not all(r["novel"] for r in golden["ppo_remember"])

@@ -131,3 +131,36 @@ def test_hybrid_simulate_move_vs_reference(orc):
             assert len(outs) == len(want) and shim.draw - 4 == draws
             for (s1, r1, d1), (s2, r2, d2) in zip(outs, want):
                 assert (np.asarray(s1).flatten() == s2).all() and float(r1) == r2 and bool(d1) == d2
+
+
+def test_ppo_remember_reward_shaping_vs_reference(orc):
+    """PPOAgent.remember (agents/ppo_agent.py:234-269) on transitions of real play: new-highest-tile bonus,
+    top-4 bonus, novelty (the agent's own seen_states set), heuristic; plus regressions of the maximum."""
+    import contextlib, io
+    PPO = R.load_ppo_agent_class()
+
+    class Memory:
+        def add(self, state, action, prob, reward, next_state, done):
+            self.reward = reward
+
+    ppo = object.__new__(PPO)
+    ppo.highest_tile_seen = 2; ppo.highest_tile_history = []; ppo.seen_states = set()
+    ppo.novelty_factor = 0.2; ppo.heuristic_weight = 0.3; ppo.memory = Memory()
+    seen, highest = set(), 2
+    env = orc.Env(SEED, 77)
+    state = env.reset()
+    rng = np.random.default_rng(8)
+    for t in range(1500):
+        a = int(rng.integers(0, 4))
+        nxt, r, done, _ = env.step(a)
+        if t % 97 == 96:                                   # a transition whose maximum regresses (arbitrary inputs)
+            state = np.where(state == state.max(), state.max() * 2, state).astype(np.int32)
+        with contextlib.redirect_stdout(io.StringIO()):    # the reference prints on a new highest tile
+            ppo.remember(state.copy(), a, 0.0, np.float64(r), nxt.copy(), done)
+        key = nxt.tobytes()
+        want, highest = orc.ppo_shape_reward(state, nxt, r, highest, key not in seen)
+        seen.add(key)
+        assert float(ppo.memory.reward) == want, t
+        assert highest == ppo.highest_tile_seen
+        state = env.reset() if done else nxt
+    assert highest >= 64

@@ -68,9 +68,11 @@ def _gather_main(rank, world, port, total, out):
     lo, hi = G.shard_range(total, rank, world)
     g = np.arange(lo, hi)
     ms = -np.ones((hi - lo, 8), np.int32); ms[:, 0] = g
-    host = gather_games({"score": (g * 3).astype(np.int32), "highest_exp": (g % 9 + 3).astype(np.uint8),
-                         "moves": (g + 100).astype(np.int32), "valid": g.astype(np.int32), "invalid": (g % 5).astype(np.int32),
-                         "milestone": ms})
+    t = torch.from_numpy
+    host = gather_games({"score": t((g * 3).astype(np.int32)), "highest_exp": t((g % 9 + 3).astype(np.uint8)),
+                         "moves": t((g + 100).astype(np.int32)), "valid": t(g.astype(np.int32)),
+                         "invalid": t((g % 5).astype(np.int32)), "milestone": t(ms)}, total)
+    assert len(host["score"]) == total                       # complete on every rank
     if rank == 0:
         res = compile_results(host["score"], host["highest_exp"], host["moves"], host["valid"], host["invalid"],
                               host["milestone"], 20, 40)
