@@ -920,8 +920,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
 
 // Whole games, latency form: one TEAM of four warps plays one game (beam_search_team).  Games come
 // from `in` (hand-overs of play_games_kernel, ctr->tail_count of them) or, with in == nullptr, are
-// the fresh games 0..n-1.  The first item of a team is fixed (team-major over the grid, so that few
-// games spread over all SMs); further ones come from the queue.  A block whose six teams have run
+// the fresh games 0..n-1.  A block whose six teams have run
 // out of games turns into a stall breaker (break_stalls) until every game of the call is final: the
 // stalls are broken on the SMs the finished games leave, while the long games are still being played.
 // Always launched with kBeamThreads threads on every SM.
@@ -936,9 +935,16 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
     const int bar = 1 + quad;
     const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
     const unsigned int total = in ? a.ctr->tail_count : (unsigned int)a.n;
-    const unsigned int teams = gridDim.x * (blockDim.x >> 7);
-    unsigned int p = (unsigned int)quad * gridDim.x + blockIdx.x;
+    // Every game comes from the queue, so whichever blocks are resident can play all of them (a block
+    // that is not scheduled yet holds nothing back, and the blocks that wait in break_stalls below
+    // wait only for work that resident blocks do).  Team q of a block asks a little later than team
+    // q - 1: when there are fewer games than teams, they spread over all SMs instead of filling a few.
+    if (leader) __nanosleep(4000u * (unsigned int)quad);
     for (;;) {
+        if (leader) ts.next_item = atomicAdd(&a.ctr->team_work, 1u);
+        team_barrier(bar);
+        const unsigned int p = ts.next_item;
+        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
         if (p >= total) break;
         EnvState s;
         GameState gs;
@@ -951,13 +957,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
             done = play_move(gs, s, r, a, row, game);
         }
         store_env(gs, s);
-        if (leader) {
-            retire_game(a, gs, done, false);
-            ts.next_item = teams + atomicAdd(&a.ctr->team_work, 1u);
-        }
-        team_barrier(bar);
-        p = ts.next_item;
-        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
+        if (leader) retire_game(a, gs, done, false);
     }
     __syncthreads();                                       // all six teams of the block are out of games
     break_stalls<kSpecWarps>(a, smem, row);
