@@ -641,6 +641,7 @@ struct GameState {
     int32_t score, moves, valid, invalid;
     uint32_t highest, spawn_ctr, index;      // index = position in the caller's output arrays
     int32_t streak;                          // consecutive invalid moves so far
+    int32_t reserved;                        // pending entry of a MIGRATED game: its pusher reserved an idle group for it
     int32_t ms[8];
 };
 
@@ -653,7 +654,7 @@ struct GameCounters {
     unsigned int pending_count;   // stalled games handed to the stall breaker
     unsigned int finish_work;     // queue head of the stall breaker
     unsigned int written;         // games whose results are final (the stall breaker leaves when this reaches n)
-    unsigned int pad;
+    int idle_groups;              // stall-breaker groups waiting for work that no migrating game has reserved yet
 };
 
 struct GamesArgs {
@@ -689,7 +690,7 @@ __device__ __forceinline__ void start_game(GameState &gs, EnvState &s, const Phi
     s.spawn_ctr = 0u;
     env_reset(s, K, game);
     env_reset(s, K, game);
-    gs.index = index; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0; gs.streak = 0;
+    gs.index = index; gs.nodes = 0; gs.moves = 0; gs.valid = 0; gs.invalid = 0; gs.streak = 0; gs.reserved = 0;
 #pragma unroll
     for (int m = 0; m < 8; ++m) gs.ms[m] = -1;
 }
@@ -726,20 +727,22 @@ constexpr int kStallStreak = G2048_STALL_STREAK;
 
 // A game leaves a play loop finished (done / move cap), stalled (-> stall breaker) or, in the
 // one-warp kernel, because few games are left (-> team kernel).  One thread calls this.
-__device__ __forceinline__ void retire_game(const GamesArgs &a, const GameState &gs, bool done, bool to_tail)
+enum RetireTo { kRetirePending = 0, kRetireTail = 1, kRetireMigrate = 2 };
+__device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, bool done, int to)
 {
     if (done || gs.moves >= a.max_moves) {
         write_game(a, gs);
         atomicAdd(&a.ctr->finished, 1u);
         atomicAdd(&a.ctr->written, 1u);
-    } else if (to_tail) {
+    } else if (to == kRetireTail) {
         a.tail[atomicAdd(&a.ctr->tail_count, 1u)] = gs;
     } else {
+        gs.reserved = to == kRetireMigrate ? 1 : 0;
         const unsigned int slot = atomicAdd(&a.ctr->pending_count, 1u);
         a.pending[slot] = gs;
         __threadfence();                                   // the entry before its flag
         *reinterpret_cast<volatile unsigned int *>(&a.pending_ready[slot]) = 1u;
-        atomicAdd(&a.ctr->finished, 1u);
+        if (to == kRetirePending) atomicAdd(&a.ctr->finished, 1u);
     }
 }
 
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
             done = play_move(gs, s, r, a, row, game);
         }
         store_env(gs, s);
-        if (lane == 0) retire_game(a, gs, done, to_tail);
+        if (lane == 0) retire_game(a, gs, done, to_tail ? kRetireTail : kRetirePending);
         __syncwarp();
     }
 }
@@ -847,17 +850,24 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         if (w == 0 && lane == 0) {
             volatile unsigned int *head = &a.ctr->finish_work, *avail = &a.ctr->pending_count, *written = &a.ctr->written;
             unsigned int got = kNone;
+            bool counted_idle = false;                     // this group is in ctr->idle_groups
             for (;;) {
                 const unsigned int h = *head;
                 if (h < *avail) {
                     if (atomicCAS(&a.ctr->finish_work, h, h + 1u) != h) continue;
                     while (*reinterpret_cast<volatile unsigned int *>(&a.pending_ready[h]) == 0u) __nanosleep(200);
                     __threadfence();
+                    // a migrated game's pusher took one idle group off the count for it; keep the count
+                    // right whoever ends up with the entry
+                    const int reserved = reinterpret_cast<volatile GameState *>(&a.pending[h])->reserved;
+                    if (counted_idle && !reserved) atomicSub(&a.ctr->idle_groups, 1);
+                    if (!counted_idle && reserved) atomicAdd(&a.ctr->idle_groups, 1);
                     got = h;
                     break;
                 }
                 if (*written >= (unsigned int)a.n) break;
-                __nanosleep(2000);
+                if (!counted_idle) { atomicAdd(&a.ctr->idle_groups, 1); counted_idle = true; }
+                __nanosleep(1000);
             }
             next_game[group] = got;
         }
@@ -865,13 +875,14 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         const unsigned int p = next_game[group];
         group_barrier();                                   // everyone has read it before the next round rewrites it
         if (p == kNone) break;
+        if (w == 0 && lane == 0) GAMES_PROF_ADD(6, 1);
         GameState gs = a.pending[p];                       // every warp of the group keeps an identical copy
         const uint32_t game = a.game0 + gs.index;
         EnvState s;
         load_env(gs, s);
         bool done = false;
         int buf = 0;
-        int width = kSpecWarps;                            // the game arrives inside a stall
+        int width = gs.streak >= kStallStreak ? kSpecWarps : 1;   // a stalled game, or a migrated one in normal play
         while (!done && gs.moves < a.max_moves) {
             const int allowed = min(width, a.max_moves - gs.moves);
             if (allowed == 1) {
@@ -884,6 +895,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                 if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
             }
             group_barrier();
+            if (w == 0 && lane == 0) GAMES_PROF_ADD(7, 1);
             const uint32_t legal = env_legal_mask(s.board);
             int first_valid = -1;
             for (int j = 0; j < allowed; ++j) {
@@ -935,32 +947,63 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
     const int bar = 1 + quad;
     const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
     const unsigned int total = in ? a.ctr->tail_count : (unsigned int)a.n;
+    __shared__ int active_teams;                           // teams of this block that are playing a game
+    if (threadIdx.x == 0) active_teams = 0;
+    __syncthreads();
     // Every game comes from the queue, so whichever blocks are resident can play all of them (a block
     // that is not scheduled yet holds nothing back, and the blocks that wait in break_stalls below
     // wait only for work that resident blocks do).  Team q of a block asks a little later than team
     // q - 1: when there are fewer games than teams, they spread over all SMs instead of filling a few.
+    if (threadIdx.x == 0) GAMES_PROF_MIN(0);
     if (leader) __nanosleep(4000u * (unsigned int)quad);
     for (;;) {
         if (leader) ts.next_item = atomicAdd(&a.ctr->team_work, 1u);
         team_barrier(bar);
         const unsigned int p = ts.next_item;
         team_barrier(bar);                                 // everyone has read it before the next round rewrites it
-        if (p >= total) break;
+        if (p >= total) { if (leader) GAMES_PROF_MIN(1); break; }
         EnvState s;
         GameState gs;
         if (in) { gs = in[p]; load_env(gs, s); }
         else start_game(gs, s, a.P.K, a.game0 + p, p);
         const uint32_t game = a.game0 + gs.index;
-        bool done = false;
+        bool done = false, migrate = false;
+        if (leader) atomicAdd(&active_teams, 1);
         while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
+            // Once the queue is dry, SMs that still hold several games run them slower (six teams share four
+            // schedulers) than an SM holding one; blocks that have turned stall breaker and found nothing
+            // to do count themselves in idle_groups.  Every fourth move the team checks: a game that shares
+            // its SM moves to such a group (which plays it with a team of its own, break_stalls).
+            if (a.pending && (gs.moves & 3) == 3) {
+                if (leader) {
+                    unsigned int go = 0u;
+                    if (*reinterpret_cast<volatile int *>(&active_teams) > 1 &&
+                        *reinterpret_cast<volatile unsigned int *>(&a.ctr->team_work) >= total &&
+                        *reinterpret_cast<volatile int *>(&a.ctr->idle_groups) > 0) {
+                        if (atomicSub(&a.ctr->idle_groups, 1) > 0) go = 1u;            // reserved one idle group
+                        else atomicAdd(&a.ctr->idle_groups, 1);
+                    }
+                    ts.next_item = go;
+                }
+                team_barrier(bar);
+                migrate = ts.next_item != 0u;
+                team_barrier(bar);
+                if (migrate) break;
+            }
             const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
             done = play_move(gs, s, r, a, row, game);
         }
         store_env(gs, s);
-        if (leader) retire_game(a, gs, done, false);
+        if (leader) {
+            atomicSub(&active_teams, 1);
+            retire_game(a, gs, done, migrate ? kRetireMigrate : kRetirePending);
+            GAMES_PROF_MAX(2);
+        }
     }
     __syncthreads();                                       // all six teams of the block are out of games
+    if (threadIdx.x == 0) { GAMES_PROF_MIN(3); GAMES_PROF_MAX(4); }
     break_stalls<kSpecWarps>(a, smem, row);
+    if (threadIdx.x == 0) GAMES_PROF_MAX(5);
 }
 
 #ifdef G2048_TEAM_PROFILE
@@ -972,6 +1015,14 @@ extern "C" int g2048_debug_team_profile(unsigned long long *out8)
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     if (cudaMemcpyFromSymbol(out8, g2048::g_team_prof, sizeof zero) != cudaSuccess) return -1;
     return cudaMemcpyToSymbol(g2048::g_team_prof, zero, sizeof zero) == cudaSuccess ? 0 : -1;
+}
+// timeline of the last team_games_kernel launches (see g_games_prof); resets it (min slots to ~0)
+extern "C" int g2048_debug_games_profile(unsigned long long *out8)
+{
+    unsigned long long init[8] = {~0ull, ~0ull, 0, ~0ull, 0, 0, 0, 0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out8, g2048::g_games_prof, sizeof init) != cudaSuccess) return -1;
+    return cudaMemcpyToSymbol(g2048::g_games_prof, init, sizeof init) == cudaSuccess ? 0 : -1;
 }
 namespace g2048 {
 #endif

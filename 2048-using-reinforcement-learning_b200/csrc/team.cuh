@@ -37,6 +37,19 @@ static_assert(sizeof(TeamScratch) <= kTeamWarps * sizeof(WarpScratch), "a team r
 // (profiles/tail.py reads them through g2048_debug_team_profile; never part of the product build)
 #ifdef G2048_TEAM_PROFILE
 __device__ unsigned long long g_team_prof[8];
+// timeline of a team_games_kernel launch (globaltimer, ns): [0] first block started, [1] queue first found
+// empty, [2] last game retired by a team, [3] first / [4] last block turning stall breaker, [5] kernel end,
+// [6] stalled games taken by the stall breaker, [7] speculative rounds
+__device__ unsigned long long g_games_prof[8];
+__device__ __forceinline__ unsigned long long prof_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GAMES_PROF_MIN(i) atomicMin(&g_games_prof[i], prof_now())
+#define GAMES_PROF_MAX(i) atomicMax(&g_games_prof[i], prof_now())
+#define GAMES_PROF_ADD(i, v) atomicAdd(&g_games_prof[i], (unsigned long long)(v))
 #define TEAM_PROF_DECL long long _tp = clock64(), _tp0 = _tp; unsigned long long _pa = 0, _pb = 0, _pc = 0, _pl = 0
 #define TEAM_PROF_MARK(acc) do { const long long _n = clock64(); acc += (unsigned long long)(_n - _tp); _tp = _n; } while (0)
 #define TEAM_PROF_FLUSH() do { if (tid == 0u) { atomicAdd(&g_team_prof[0], _pa); atomicAdd(&g_team_prof[1], _pb); \
@@ -46,6 +59,9 @@ __device__ unsigned long long g_team_prof[8];
 #define TEAM_PROF_DECL
 #define TEAM_PROF_MARK(acc)
 #define TEAM_PROF_FLUSH()
+#define GAMES_PROF_MIN(i)
+#define GAMES_PROF_MAX(i)
+#define GAMES_PROF_ADD(i, v)
 #endif
 
 __device__ __forceinline__ void team_barrier(int id)
