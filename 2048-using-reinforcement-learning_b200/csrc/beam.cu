@@ -641,9 +641,26 @@ struct GameState {
     int32_t score, moves, valid, invalid;
     uint32_t highest, spawn_ctr, index;      // index = position in the caller's output arrays
     int32_t streak;                          // consecutive invalid moves so far
-    int32_t reserved;                        // pending entry of a MIGRATED game: its pusher reserved an idle group for it
+    int32_t reserved;                        // PendingKind of a pending entry (a migrated game's pusher reserved an idle group)
     int32_t ms[8];
 };
+
+// A long stall, split: the calls [gs.moves, max_moves) of a game whose agent keeps choosing an invalid move
+// are cut into `segs` ranges of `seg_len` calls that different SMs search at once (every call sees the same
+// board: an invalid move changes nothing).  The lowest range that holds a valid call decides where the stall
+// ends; ranges above it are cancelled.  The group that finishes the last range puts the game together again.
+constexpr int kMaxSegs = 8;
+constexpr int kSplitAfterRounds = 4;       // full-width rounds without a valid call before a stall is split
+constexpr int kMinSegCalls = 96;           // calls per range at least
+struct SegResult { int32_t first_valid; uint32_t action; long long nodes; };
+struct StallRecord {
+    GameState gs;                          // the game at the split; gs.moves = first call of range 0
+    int32_t seg_len, segs;
+    int32_t done;                          // ranges finished
+    int32_t first_valid_seg;               // lowest range that found a valid call (kMaxSegs: none so far)
+    SegResult res[kMaxSegs];
+};
+enum PendingKind { kEntryStalled = 0, kEntryMigrated = 1, kEntrySegment = 2 };   // GameState::reserved of a pending entry
 
 // Device-side counters of one g2048_play_games call (per-launch scratch, zeroed before the kernels).
 struct GameCounters {
@@ -655,6 +672,8 @@ struct GameCounters {
     unsigned int finish_work;     // queue head of the stall breaker
     unsigned int written;         // games whose results are final (the stall breaker leaves when this reaches n)
     int idle_groups;              // stall-breaker groups waiting for work that no migrating game has reserved yet
+    unsigned int record_count;    // StallRecords handed out
+    unsigned int pad[3];
 };
 
 struct GamesArgs {
@@ -665,6 +684,8 @@ struct GamesArgs {
     GameCounters *ctr;
     GameState *pending;            // stalled games handed to finish_games_kernel (nullptr: play them in place)
     unsigned int *pending_ready;   // pending[i] is complete (the stall breaker runs beside its producers)
+    StallRecord *records;          // split stalls (nullptr: never split)
+    unsigned int record_cap;
     GameState *tail;               // live games handed to team_games_kernel once few are left (nullptr: never)
     unsigned int tail_threshold;   // ... i.e. once n - finished <= tail_threshold
 };
@@ -727,6 +748,25 @@ constexpr int kStallStreak = G2048_STALL_STREAK;
 
 // A game leaves a play loop finished (done / move cap), stalled (-> stall breaker) or, in the
 // one-warp kernel, because few games are left (-> team kernel).  One thread calls this.
+// Read a record another block wrote (after its flag / counter was seen): through L2, not this SM's L1
+template <typename T>
+__device__ __forceinline__ T load_shared_record(const T *p)
+{
+    static_assert(sizeof(T) % 8 == 0, "copied in 8-byte pieces");
+    T out;
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(p);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&out);
+#pragma unroll
+    for (size_t i = 0; i < sizeof(T) / 8; ++i) dst[i] = __ldcg(src + i);
+    return out;
+}
+__device__ __forceinline__ void push_pending(const GamesArgs &a, const GameState &entry)
+{
+    const unsigned int slot = atomicAdd(&a.ctr->pending_count, 1u);
+    a.pending[slot] = entry;
+    __threadfence();                                       // the entry before its flag
+    *reinterpret_cast<volatile unsigned int *>(&a.pending_ready[slot]) = 1u;
+}
 enum RetireTo { kRetirePending = 0, kRetireTail = 1, kRetireMigrate = 2 };
 __device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, bool done, int to)
 {
@@ -737,11 +777,8 @@ __device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, b
     } else if (to == kRetireTail) {
         a.tail[atomicAdd(&a.ctr->tail_count, 1u)] = gs;
     } else {
-        gs.reserved = to == kRetireMigrate ? 1 : 0;
-        const unsigned int slot = atomicAdd(&a.ctr->pending_count, 1u);
-        a.pending[slot] = gs;
-        __threadfence();                                   // the entry before its flag
-        *reinterpret_cast<volatile unsigned int *>(&a.pending_ready[slot]) = 1u;
+        gs.reserved = to == kRetireMigrate ? kEntryMigrated : kEntryStalled;
+        push_pending(a, gs);
         if (to == kRetirePending) atomicAdd(&a.ctr->finished, 1u);
     }
 }
@@ -838,16 +875,81 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
     static_assert(kSpecGroups * kSpecWarps == kBeamWarps && kSpecWarps % kTeamWarps == 0, "groups must tile the block");
     __shared__ SpecSlot slots[kSpecGroups][2][kSpecWarps];
     __shared__ unsigned int next_game[kSpecGroups];
+    __shared__ int note[kSpecGroups][2];                   // leader -> group: cancel flag of a round / split record / finaliser
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
     const uint32_t lane = threadIdx.x & 31u;
     const int group = warp / kSpecWarps, w = warp % kSpecWarps;
+    const bool leader = w == 0 && lane == 0;
     const int quad = warp >> 2;                            // the group's team = its first four warps
     TeamScratch &ts = team_scratch(smem, quad);
     auto group_barrier = [&]() { asm volatile("barrier.sync %0, %1;" ::"r"(8 + group), "r"(kSpecWarps * 32) : "memory"); };
     constexpr unsigned int kNone = 0xFFFFFFFFu;
+    int buf = 0;
+
+    // One range of a split stall (all threads of the group).  Returns true when this group finished the LAST
+    // range of the record and the stall ended in a valid move: then gs / s hold the game after that move and
+    // the caller plays on.  Otherwise the game is someone else's (or was written here, at the move cap).
+    auto run_segment = [&](StallRecord *rec, int seg, GameState &gs, EnvState &s, bool &done) -> bool {
+        gs = load_shared_record(&rec->gs);
+        load_env(gs, s);
+        const uint32_t game = a.game0 + gs.index;
+        const uint32_t legal = env_legal_mask(s.board);
+        const int seg_len = __ldcg(&rec->seg_len), segs = __ldcg(&rec->segs);
+        const int lo = gs.moves + seg * seg_len, hi = min(lo + seg_len, a.max_moves);
+        long long nodes = 0;
+        int found = -1;
+        uint32_t action = 0u;
+        for (int m = lo; m < hi && found < 0; m += kSpecWarps) {
+            const int cnt = min(kSpecWarps, hi - m);
+            if (w < cnt) {
+                const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(m + w), row, ws);
+                if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
+            }
+            if (leader) note[group][buf] = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg) < seg;   // a lower range ended the stall
+            group_barrier();
+            if (leader) GAMES_PROF_ADD(7, 1);
+            const bool cancelled = note[group][buf] != 0;
+            for (int j = 0; j < cnt; ++j) {
+                nodes += slots[group][buf][j].nodes;
+                if ((legal >> slots[group][buf][j].action) & 1u) { found = m + j - lo; action = slots[group][buf][j].action; break; }
+            }
+            buf ^= 1;
+            if (cancelled) { found = -1; break; }
+        }
+        if (leader) {
+            rec->res[seg].first_valid = found; rec->res[seg].action = action; rec->res[seg].nodes = nodes;
+            if (found >= 0) atomicMin(&rec->first_valid_seg, seg);
+            __threadfence();
+            note[group][buf] = atomicAdd(&rec->done, 1) + 1 == segs;
+        }
+        group_barrier();
+        const bool last = note[group][buf] != 0;
+        buf ^= 1;
+        if (!last) return false;
+        __threadfence();
+        const int f = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg);
+        const volatile SegResult *res = rec->res;
+        if (f >= segs) {                                   // no valid call up to the move cap
+            for (int k = 0; k < segs; ++k) gs.nodes += res[k].nodes;
+            gs.invalid += a.max_moves - gs.moves;
+            gs.moves = a.max_moves;
+            if (leader) { write_game(a, gs); __threadfence(); atomicAdd(&a.ctr->written, 1u); }
+            return false;
+        }
+        for (int k = 0; k <= f; ++k) gs.nodes += res[k].nodes;
+        const int before = f * seg_len + res[f].first_valid;      // invalid moves: nothing else changes (env:188-192)
+        gs.invalid += before;
+        gs.moves += before;
+        BeamResult r;
+        r.action = res[f].action;
+        r.nodes = 0;
+        done = play_move(gs, s, r, a, row, game);
+        return true;
+    };
+
     for (;;) {
-        if (w == 0 && lane == 0) {
+        if (leader) {
             volatile unsigned int *head = &a.ctr->finish_work, *avail = &a.ctr->pending_count, *written = &a.ctr->written;
             unsigned int got = kNone;
             bool counted_idle = false;                     // this group is in ctr->idle_groups
@@ -859,7 +961,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                     __threadfence();
                     // a migrated game's pusher took one idle group off the count for it; keep the count
                     // right whoever ends up with the entry
-                    const int reserved = reinterpret_cast<volatile GameState *>(&a.pending[h])->reserved;
+                    const bool reserved = reinterpret_cast<volatile GameState *>(&a.pending[h])->reserved == kEntryMigrated;
                     if (counted_idle && !reserved) atomicSub(&a.ctr->idle_groups, 1);
                     if (!counted_idle && reserved) atomicAdd(&a.ctr->idle_groups, 1);
                     got = h;
@@ -875,27 +977,67 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         const unsigned int p = next_game[group];
         group_barrier();                                   // everyone has read it before the next round rewrites it
         if (p == kNone) break;
-        if (w == 0 && lane == 0) GAMES_PROF_ADD(6, 1);
-        GameState gs = a.pending[p];                       // every warp of the group keeps an identical copy
-        const uint32_t game = a.game0 + gs.index;
+        GameState gs = load_shared_record(&a.pending[p]);  // every warp of the group keeps an identical copy
         EnvState s;
-        load_env(gs, s);
         bool done = false;
-        int buf = 0;
-        int width = gs.streak >= kStallStreak ? kSpecWarps : 1;   // a stalled game, or a migrated one in normal play
+        if (gs.reserved == kEntrySegment) {                // a range of a split stall: gs.score = record, gs.moves = range
+            if (!run_segment(&a.records[gs.score], gs.moves, gs, s, done)) continue;
+        } else {
+            if (leader) GAMES_PROF_ADD(6, 1);
+            load_env(gs, s);
+        }
+        const uint32_t game = a.game0 + gs.index;
+        int width = gs.streak >= kStallStreak && gs.reserved == kEntryStalled ? kSpecWarps : 1;   // inside a stall, or normal play
+        int dry_rounds = 0;                                // full-width rounds without a valid call
+        bool mine = true;                                  // false: the game went to a split record
         while (!done && gs.moves < a.max_moves) {
+            // a long stall with plenty of calls left: cut the rest into ranges for several SMs
+            if (dry_rounds >= kSplitAfterRounds && a.records && a.max_moves - gs.moves >= 2 * kMinSegCalls) {
+                dry_rounds = 0;
+                if (leader) {
+                    int got = -1;
+                    const unsigned int idx = atomicAdd(&a.ctr->record_count, 1u);
+                    if (idx < a.record_cap) {
+                        StallRecord *rec = &a.records[idx];
+                        const int rem = a.max_moves - gs.moves;
+                        const int segs = min(kMaxSegs, rem / kMinSegCalls);
+                        store_env(gs, s);
+                        rec->gs = gs;
+                        rec->segs = segs;
+                        rec->seg_len = (rem + segs - 1) / segs;
+                        rec->done = 0;
+                        rec->first_valid_seg = kMaxSegs;
+                        __threadfence();
+                        GameState entry = gs;
+                        entry.reserved = kEntrySegment;
+                        entry.score = (int32_t)idx;
+                        for (int k = 1; k < segs; ++k) { entry.moves = k; push_pending(a, entry); }
+                        got = (int)idx;
+                    }
+                    note[group][buf] = got;
+                }
+                group_barrier();
+                const int idx = note[group][buf];
+                buf ^= 1;
+                group_barrier();
+                if (idx >= 0) {
+                    if (!run_segment(&a.records[idx], 0, gs, s, done)) { mine = false; break; }
+                    width = 1;
+                    continue;
+                }
+            }
             const int allowed = min(width, a.max_moves - gs.moves);
             if (allowed == 1) {
                 if (w < kTeamWarps) {
                     const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, 1 + quad);
-                    if (w == 0 && lane == 0) { slots[group][buf][0].action = r.action; slots[group][buf][0].nodes = r.nodes; }
+                    if (leader) { slots[group][buf][0].action = r.action; slots[group][buf][0].nodes = r.nodes; }
                 }
             } else if (w < allowed) {
                 const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(gs.moves + w), row, ws);
                 if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
             }
             group_barrier();
-            if (w == 0 && lane == 0) GAMES_PROF_ADD(7, 1);
+            if (leader) GAMES_PROF_ADD(7, 1);
             const uint32_t legal = env_legal_mask(s.board);
             int first_valid = -1;
             for (int j = 0; j < allowed; ++j) {
@@ -911,13 +1053,16 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                 r.nodes = 0;
                 done = play_move(gs, s, r, a, row, game);
                 width = 1;
+                dry_rounds = 0;
             } else {
+                dry_rounds = allowed == kSpecWarps ? dry_rounds + 1 : 0;
                 width = min(kSpecWarps, 2 * width);
             }
             buf ^= 1;
         }
+        if (!mine) continue;
         store_env(gs, s);
-        if (w == 0 && lane == 0) { write_game(a, gs); __threadfence(); atomicAdd(&a.ctr->written, 1u); }
+        if (leader) { write_game(a, gs); __threadfence(); atomicAdd(&a.ctr->written, 1u); }
     }
 }
 
@@ -1028,7 +1173,7 @@ namespace g2048 {
 #endif
 
 static int g_attr_done[kMaxDevices];
-static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, 0};
+static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, 0, 1};
 int step_tuning(int key) { return g_tuning[key]; }
 
 int set_tuning(int key, int value)
@@ -1127,9 +1272,14 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     const int64_t tail_thr = g_tuning[G2048_TUNE_TAIL_THRESHOLD] >= 0 ? g_tuning[G2048_TUNE_TAIL_THRESHOLD] : team_slots;
     const bool direct = !wide && n <= direct_max;
     const int64_t tail_cap = wide || direct ? 0 : (tail_thr < n ? tail_thr : n);
-    // scratch: counters | ready flags of the stalled games | stalled games (any game may stall) | games for the team kernel
-    const size_t flags_off = 256, flags_bytes = wide ? 0 : (((size_t)n * sizeof(unsigned int) + 255) & ~(size_t)255);
-    const size_t pending_off = flags_off + flags_bytes, tail_off = pending_off + (wide ? 0 : (size_t)n * sizeof(GameState));
+    // scratch: counters | ready flags of the pending entries | pending entries (stalled / migrated games, ranges of
+    // split stalls) | split-stall records | games for the team kernel
+    const size_t record_cap = wide ? 0 : (size_t)(n / 2 > 8 ? n / 2 : 8);
+    const size_t pending_cap = wide ? 0 : (size_t)n + (kMaxSegs - 1) * record_cap;
+    auto round256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t flags_off = 256, pending_off = flags_off + round256(pending_cap * sizeof(unsigned int));
+    const size_t records_off = pending_off + round256(pending_cap * sizeof(GameState));
+    const size_t tail_off = records_off + round256(record_cap * sizeof(StallRecord));
     LaunchScratch scratch;
     rc = scratch.alloc(tail_off + (size_t)tail_cap * sizeof(GameState), pending_off, stream);
     if (rc != G2048_OK) return rc;
@@ -1139,6 +1289,8 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
                 st->row, st->code, st->overflow, reinterpret_cast<GameCounters *>(base),
                 wide ? nullptr : reinterpret_cast<GameState *>(base + pending_off),
                 wide ? nullptr : reinterpret_cast<unsigned int *>(base + flags_off),
+                wide || !g_tuning[G2048_TUNE_SPLIT_STALLS] ? nullptr : reinterpret_cast<StallRecord *>(base + records_off),
+                (unsigned int)record_cap,
                 tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_cap};
     const int grid = (int)(n < st->sm_count ? n : st->sm_count);    // spread small runs over all SMs (see beam search)
     if (wide) {                                                     // wide beams: compatibility path, no stall breaker

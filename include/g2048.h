@@ -254,9 +254,11 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *   G2048_TUNE_TAIL_THRESHOLD   g2048_play_games with more games: one warp per game until this many are
  *                               left alive, then teams (-1 = default: the team slots; 0 = never)
  *   G2048_TUNE_STEP_TABLES      g2048_env_step*: 0 = table-free SWAR row move (default), 1 = row tables
- *                               read through L1/L2 (the round-1 form; kept for A/B measurements) */
+ *                               read through L1/L2 (the round-1 form; kept for A/B measurements)
+ *   G2048_TUNE_SPLIT_STALLS     g2048_play_games: 1 = a long stall (the agent keeps choosing an invalid move) is
+ *                               cut into call ranges that several SMs search at once (default), 0 = one SM */
 enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2,
-       G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_COUNT = 4 };
+       G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_SPLIT_STALLS = 4, G2048_TUNE_COUNT = 5 };
 int g2048_set_tuning(int key, int value);
 
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */

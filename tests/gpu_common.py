@@ -13,8 +13,9 @@ def lib():
     return _lib.use_device(0)
 
 
-TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD, TUNE_STEP_TABLES = 0, 1, 2, 3
-_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1, TUNE_STEP_TABLES: 0}
+TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD, TUNE_STEP_TABLES, TUNE_SPLIT_STALLS = 0, 1, 2, 3, 4
+_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1, TUNE_STEP_TABLES: 0,
+                  TUNE_SPLIT_STALLS: 1}
 
 
 class tuning:
@@ -34,8 +35,10 @@ class tuning:
 
 # scheduling paths of g2048_play_games: teams from the first move / one warp per game only /
 # one warp per game until `tail` games are left, then teams
+# (long stalls are cut into call ranges for several SMs on every path; "team, one SM per stall" switches that off)
 PLAY_PATHS = {"team": {TUNE_TEAM_DIRECT_MAX: 1 << 30}, "warp": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 0},
-              "warp+tail": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 40}}
+              "warp+tail": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 40},
+              "team, one SM per stall": {TUNE_TEAM_DIRECT_MAX: 1 << 30, TUNE_SPLIT_STALLS: 0}}
 
 
 def host_reset(n, seed, game0=0, spawn_ctr=None):

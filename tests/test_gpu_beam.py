@@ -230,6 +230,16 @@ def test_cfg5_whole_games_20_40_vs_oracle(orc):
     assert (out["invalid"] >= 32).any() and (out["moves"] == 10000).any(), "no stalled game in the set"
 
 
+def test_long_stalls_split_over_sms(orc):
+    """Many games, few moves per search: most games end in a stall that lasts to the move cap, some stalls end
+    after hundreds of invalid moves -- split ranges, cancelled ranges and re-assembled games, on both group sizes."""
+    for n, W, D, cap in ((300, 5, 7, 4000), (2300, 3, 5, 1500)):
+        out = X.host_play(n, W, D, SEED, game0=9000, max_moves=cap)
+        ref = orc.play_games(SEED, 9000, n, W, D, max_moves=cap)
+        _check_games(out, ref, n)
+        assert ((out["invalid"] >= 300) & (out["moves"] < cap)).any() and (out["moves"] == cap).any()
+
+
 def test_cfg5_whole_games_20_40_warp_then_team_tail(orc):
     """The many-games path of cfg 5 (one warp per game, hand-over to teams once few are left) on the same
     64 games, and the warp-only path on a slice of them: identical results on every path."""
