@@ -1267,8 +1267,11 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     const bool wide = beam_width > 32;
     const int teams_per_block = kBeamWarps / kTeamWarps;
     const int64_t team_slots = (int64_t)st->sm_count * teams_per_block;
-    // few games: teams from the first move; many: one warp per game until the live ones fit the teams
-    const int64_t direct_max = g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] >= 0 ? g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] : 2 * team_slots;
+    // Games that fit the team slots (six per SM): teams from the first move.  More: one warp per game until the
+    // live ones fit -- while every SM holds more than six games the run is bound by instruction throughput, and
+    // a team spends ~1.8x the instructions of a lone warp on a move (measured: 1,250 games at 20/40 take 0.199 s
+    // with teams from the start, 0.175 s with the hand-over at 888 live games).
+    const int64_t direct_max = g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] >= 0 ? g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] : team_slots;
     const int64_t tail_thr = g_tuning[G2048_TUNE_TAIL_THRESHOLD] >= 0 ? g_tuning[G2048_TUNE_TAIL_THRESHOLD] : team_slots;
     const bool direct = !wide && n <= direct_max;
     const int64_t tail_cap = wide || direct ? 0 : (tail_thr < n ? tail_thr : n);

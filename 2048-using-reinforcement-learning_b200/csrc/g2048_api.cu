@@ -87,6 +87,10 @@ struct StepArgs {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// The reset of a finished game, out of line: few envs end in a given step, and the ~300 instructions of
+// two spawns would otherwise sit in the fetch path of every warp.
+__device__ __noinline__ void env_reset_cold(EnvState &s, const PhiloxKey &K, uint32_t game) { env_reset(s, K, game); }
+
 // Game2048Env.step for n envs, one env per thread, one launch per step, with everything a
 // training loop wants next to it in the same launch: legal mask, done, the reset of a finished
 // game, the policy's observation (agents/ppo_agent.py:184-195) and the pre-reset state.
@@ -102,7 +106,6 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_fused_kernel(StepArgs a)
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
-    const bool want_reward = a.reward != nullptr || a.reward32 != nullptr;
     const uint32_t lane = threadIdx.x & 31u;
     // warps stay whole (the observation is written through shuffles): warp-aligned base, lane offset
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < a.n; base += (int64_t)gridDim.x * blockDim.x) {
@@ -119,14 +122,14 @@ __global__ void __launch_bounds__(kEnvThreads) env_step_fused_kernel(StepArgs a)
             uint32_t inj[2];
             if (a.inject) { inj[0] = a.inject[2 * i]; inj[1] = a.inject[2 * i + 1]; }
             const uint32_t game = a.game0 + (uint32_t)i;
-            StepResult2 r = want_reward
-                ? env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow)
-                : env_step_pairs<kSwarMove, false>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow);
+            // one code path: a launch runs every instruction once per warp, so instruction fetch is what it waits
+            // for most (ncu: no_instruction is the top stall); a second, reward-free copy of the step would double it
+            StepResult2 r = env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow);
             if (a.stepped) a.stepped[i] = s.board.u64();
             if (a.final_score) a.final_score[i] = s.score;
             if (a.final_highest) a.final_highest[i] = (uint8_t)s.highest;
             if (a.episodes && r.done) {                   // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
-                env_reset(s, a.K, game);
+                env_reset_cold(s, a.K, game);
                 a.episodes[i] += 1;
                 r.legal = env_legal_mask(s.board);
             }

@@ -250,7 +250,7 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *                               roots fit the GPU's team slots, else one warp per root), 1 = always one
  *                               warp per root, 2 = always teams
  *   G2048_TUNE_TEAM_DIRECT_MAX  g2048_play_games: up to this many games are played by teams from the
- *                               first move (-1 = default: twice the team slots of the device)
+ *                               first move (-1 = default: the team slots of the device, six per SM)
  *   G2048_TUNE_TAIL_THRESHOLD   g2048_play_games with more games: one warp per game until this many are
  *                               left alive, then teams (-1 = default: the team slots; 0 = never)
  *   G2048_TUNE_STEP_TABLES      g2048_env_step*: 0 = table-free SWAR row move (default), 1 = row tables
