@@ -9,9 +9,10 @@ from .packing import pack_board, pack_boards, unpack_board, unpack_boards  # noq
 from .env import Game2048Env, BatchedGame2048Env  # noqa: F401
 from .beam import BeamSearchAgent, BatchedBeamSearch  # noqa: F401
 from .ppo import PPORewardShaper  # noqa: F401
+from .hybrid import HybridBeamSearch  # noqa: F401
 from .parallel import shard_range, all_reduce_stats, describe_stats  # noqa: F401
 from .evaluation import run_evaluation, compile_results, write_overall_results, best_games  # noqa: F401
 
 __all__ = ["Game2048Env", "BatchedGame2048Env", "BeamSearchAgent", "BatchedBeamSearch",
            "pack_board", "pack_boards", "unpack_board", "unpack_boards",
-           "PPORewardShaper", "shard_range", "all_reduce_stats", "describe_stats", "run_evaluation", "G2048Error", "build_library"]
+           "PPORewardShaper", "HybridBeamSearch", "shard_range", "all_reduce_stats", "describe_stats", "run_evaluation", "G2048Error", "build_library"]

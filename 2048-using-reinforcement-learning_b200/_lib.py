@@ -53,6 +53,7 @@ _SIGNATURES = {
     "g2048_evaluate_pattern": ([_vp, _vp, _i64, _vp], C.c_int),
     "g2048_host_simulate_move": ([_vp] * 8 + [_i64], C.c_int),
     "g2048_hybrid_expand": ([_vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u32, _vp], C.c_int),
+    "g2048_hybrid_expand_items": ([_vp] * 10 + [_i64, _u64, _u32, _vp], C.c_int),
     "g2048_host_hybrid_expand": ([_vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u32], C.c_int),
     "g2048_ppo_features": ([_vp, _vp, _vp, _vp, _i64, _vp], C.c_int),
     "g2048_host_ppo_features": ([_vp, _vp, _vp, _vp, _i64], C.c_int),

@@ -157,6 +157,7 @@ __device__ __forceinline__ ChildEval spawn_and_eval(int c, int n_valid, uint32_t
     const bool draws = ev.active && n_empty > 0;                // agent:262-263: no draw on a full board
     const uint32_t bal = __ballot_sync(FULL, draws);
     const uint32_t ordinal = spawn_base + (uint32_t)__popc(bal & lane_lt);
+    G2048_ASSERT(!ev.active || c < (int)(sizeof(ws.cand) / sizeof(ws.cand[0])));
     // fast path: the caller has filled the ring (fill_spawn_ring); wide path: one block per child
     const SpawnWords w = HasSpawnRing<Scratch>::value ? ring_words(ws, ordinal)
                                                       : spawn_words(P.K, game, call, DOM_BEAM, ordinal);
@@ -313,6 +314,7 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
             }
             n_valid = __shfl_sync(FULL, incl, 31);
             int pos = incl - __popc(v);
+            G2048_ASSERT(incl <= kMaxCand);
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 if ((v >> a) & 1u) {
@@ -387,6 +389,8 @@ __device__ __forceinline__ BeamResult beam_search_warp(Board root, int legal_giv
             top = sort_desc32(key[0], lane);
         }
         const int pick = 127 - (int)((top >> 2) & 127u);
+        G2048_ASSERT((int)lane >= nb || (pick >= 0 && pick < n_valid && n_valid <= kMaxCand));
+        G2048_ASSERT(spawn_base <= ring_end && ring_end - spawn_base <= kSpawnRing);     // every word read was inside the ring
         if ((int)lane < nb) {
             mine = Board(ws.cand[pick]);
             my_first = top & 3u;
@@ -684,6 +688,7 @@ struct GamesArgs {
     GameCounters *ctr;
     GameState *pending;            // stalled games handed to finish_games_kernel (nullptr: play them in place)
     unsigned int *pending_ready;   // pending[i] is complete (the stall breaker runs beside its producers)
+    unsigned int pending_cap;      // entries pending[] can hold (games + ranges of split stalls)
     StallRecord *records;          // split stalls (nullptr: never split)
     unsigned int record_cap;
     GameState *tail;               // live games handed to team_games_kernel once few are left (nullptr: never)
@@ -763,6 +768,7 @@ __device__ __forceinline__ T load_shared_record(const T *p)
 __device__ __forceinline__ void push_pending(const GamesArgs &a, const GameState &entry)
 {
     const unsigned int slot = atomicAdd(&a.ctr->pending_count, 1u);
+    G2048_ASSERT(slot < a.pending_cap);
     a.pending[slot] = entry;
     __threadfence();                                       // the entry before its flag
     *reinterpret_cast<volatile unsigned int *>(&a.pending_ready[slot]) = 1u;
@@ -775,7 +781,9 @@ __device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, b
         atomicAdd(&a.ctr->finished, 1u);
         atomicAdd(&a.ctr->written, 1u);
     } else if (to == kRetireTail) {
-        a.tail[atomicAdd(&a.ctr->tail_count, 1u)] = gs;
+        const unsigned int slot = atomicAdd(&a.ctr->tail_count, 1u);
+        G2048_ASSERT(slot < a.tail_threshold);
+        a.tail[slot] = gs;
     } else {
         gs.reserved = to == kRetireMigrate ? kEntryMigrated : kEntryStalled;
         push_pending(a, gs);
@@ -981,6 +989,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         EnvState s;
         bool done = false;
         if (gs.reserved == kEntrySegment) {                // a range of a split stall: gs.score = record, gs.moves = range
+            G2048_ASSERT((unsigned int)gs.score < a.record_cap && gs.moves >= 1 && gs.moves < kMaxSegs);
             if (!run_segment(&a.records[gs.score], gs.moves, gs, s, done)) continue;
         } else {
             if (leader) GAMES_PROF_ADD(6, 1);
@@ -1107,6 +1116,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
         const unsigned int p = ts.next_item;
         team_barrier(bar);                                 // everyone has read it before the next round rewrites it
         if (p >= total) { if (leader) GAMES_PROF_MIN(1); break; }
+        G2048_ASSERT(!in || p < a.tail_threshold);
         EnvState s;
         GameState gs;
         if (in) { gs = in[p]; load_env(gs, s); }
@@ -1173,7 +1183,7 @@ namespace g2048 {
 #endif
 
 static int g_attr_done[kMaxDevices];
-static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, 0, 1};
+static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, -1, 1};
 int step_tuning(int key) { return g_tuning[key]; }
 
 int set_tuning(int key, int value)
@@ -1291,7 +1301,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
                 st->row, st->code, st->overflow, reinterpret_cast<GameCounters *>(base),
                 wide ? nullptr : reinterpret_cast<GameState *>(base + pending_off),
-                wide ? nullptr : reinterpret_cast<unsigned int *>(base + flags_off),
+                wide ? nullptr : reinterpret_cast<unsigned int *>(base + flags_off), (unsigned int)pending_cap,
                 wide || !g_tuning[G2048_TUNE_SPLIT_STALLS] ? nullptr : reinterpret_cast<StallRecord *>(base + records_off),
                 (unsigned int)record_cap,
                 tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_cap};

@@ -10,6 +10,15 @@
 #include <cuda_runtime.h>
 #endif
 
+// -DG2048_DEBUG (make ../libg2048_debug.so): device-side asserts on every scratch / queue index.  The product
+// build compiles them away; the GPU suite is run against the debug library once per round.
+#if defined(G2048_DEBUG) && !defined(G2048_HOST_EMUL)
+#include <cassert>
+#define G2048_ASSERT(cond) assert(cond)
+#else
+#define G2048_ASSERT(cond) ((void)0)
+#endif
+
 namespace g2048 {
 
 struct Board {

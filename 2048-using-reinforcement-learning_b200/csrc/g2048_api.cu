@@ -87,9 +87,13 @@ struct StepArgs {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// The reset of a finished game, out of line: few envs end in a given step, and the ~300 instructions of
-// two spawns would otherwise sit in the fetch path of every warp.
+// The reset of a finished game.  (-DG2048_STEP_RESET_NOINLINE moves it out of line: few envs end in a given
+// step; measured slower -- the call's register convention costs every thread more than the skipped fetch saves.)
+#ifdef G2048_STEP_RESET_NOINLINE
 __device__ __noinline__ void env_reset_cold(EnvState &s, const PhiloxKey &K, uint32_t game) { env_reset(s, K, game); }
+#else
+__device__ __forceinline__ void env_reset_cold(EnvState &s, const PhiloxKey &K, uint32_t game) { env_reset(s, K, game); }
+#endif
 
 // Game2048Env.step for n envs, one env per thread, one launch per step, with everything a
 // training loop wants next to it in the same launch: legal mask, done, the reset of a finished
@@ -353,6 +357,7 @@ __global__ void simulate_move_kernel(const uint64_t *boards, const uint8_t *acti
                     uint64_t ns = (cur.u64() & ~(15ull << (4 * cell))) | ((uint64_t)e << (4 * cell));
                     double r = shaped_reward(true, empty_before, cur, count_empty(cur), gained, hi_exp, prev_max);
                     cur = Board(ns);
+                    G2048_ASSERT(k < 30);
                     if (out_boards) out_boards[kSimStride * i + k] = ns;
                     if (out_reward) out_reward[kSimStride * i + k] = r;
                     if (out_done) out_done[kSimStride * i + k] = env_game_over(cur);
@@ -374,7 +379,7 @@ constexpr int kHybridStride = 8;
 __global__ void hybrid_expand_kernel(const uint64_t *boards, const uint8_t *actions, const uint32_t *call,
                                      const uint32_t *draw0, uint64_t *out_boards, double *out_reward, uint8_t *out_done,
                                      int32_t *count, uint32_t *draws, int64_t n, PhiloxKey K, uint32_t game0, uint32_t call0,
-                                     const uint16_t *row)
+                                     const uint16_t *row, const uint32_t *game_of)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const Board state(boards[i]);
@@ -394,7 +399,7 @@ __global__ void hybrid_expand_kernel(const uint64_t *boards, const uint8_t *acti
             const uint32_t old_max = max_exponent(state);
             const int picks = ne < 3 ? ne : 3;
             for (int p = 0; p < picks; ++p) {
-                Philox4 blk = philox4x32_10(draw >> 2, call ? call[i] : call0, game0 + (uint32_t)i, DOM_HYBRID, K);
+                Philox4 blk = philox4x32_10(draw >> 2, call ? call[i] : call0, game0 + (game_of ? game_of[i] : (uint32_t)i), DOM_HYBRID, K);
                 const uint32_t word = (draw & 3u) == 0 ? blk.w[0] : (draw & 3u) == 1 ? blk.w[1] : (draw & 3u) == 2 ? blk.w[2] : blk.w[3];
                 ++draw; ++used;
                 const int j = p + (int)__umulhi(word, (uint32_t)(ne - p));
@@ -407,6 +412,7 @@ __global__ void hybrid_expand_kernel(const uint64_t *boards, const uint8_t *acti
                     const long long bonus = new_max > old_max ? (1ll << new_max) : 0ll;
                     const double empty_bonus = __dmul_rn((double)(ne - 1), 0.1);
                     const double reward = __dadd_rn((double)(merge_reward + bonus), empty_bonus);
+                    G2048_ASSERT(k < 6 && cells[p] >= 0 && cells[p] < 16);
                     if (out_boards) out_boards[kHybridStride * i + k] = nb;
                     if (out_reward) out_reward[kHybridStride * i + k] = __dmul_rn(reward, e == 1 ? 0.9 : 0.1);
                     if (out_done) out_done[kHybridStride * i + k] = 0;
@@ -731,7 +737,18 @@ int g2048_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const ui
     G2048_ENTER(boards && actions);
     hybrid_expand_kernel<<<grid_for(n, 128, st->sm_count, 16), 128, 0, s>>>(boards, actions, call, draw0, next_boards, reward,
                                                                           done, count, draws, n, make_philox_key(seed), game0,
-                                                                          call0, st->row);
+                                                                          call0, st->row, nullptr);
+    G2048_LAUNCHED();
+}
+
+int g2048_hybrid_expand_items(const uint64_t *boards, const uint8_t *actions, const uint32_t *game, const uint32_t *call,
+                              const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                              uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0, void *stream)
+{
+    G2048_ENTER(boards && actions && game);
+    hybrid_expand_kernel<<<grid_for(n, 128, st->sm_count, 16), 128, 0, s>>>(boards, actions, call, draw0, next_boards, reward,
+                                                                          done, count, draws, n, make_philox_key(seed), game0,
+                                                                          0u, st->row, game);
     G2048_LAUNCHED();
 }
 
@@ -813,7 +830,10 @@ static int env_step_launch(StepArgs a, void *stream)
     a.row = st->row; a.code = st->code; a.overflow = st->overflow;
     const int grid = grid_for(n, kEnvThreads, st->sm_count, 16);
     cudaError_t e;
-    if (step_tuning(G2048_TUNE_STEP_TABLES)) e = launch_pdl(env_step_fused_kernel<false>, grid, kEnvThreads, s, a);
+    // table-free move: 15 % faster up to 65,536 envs (no dependent table round trip on a latency-bound launch);
+    // at a million envs the launch is ALU-bound and the table reads are hidden: row tables win by 8 %
+    const int tables = step_tuning(G2048_TUNE_STEP_TABLES);
+    if (tables == 1 || (tables < 0 && n >= (1 << 18))) e = launch_pdl(env_step_fused_kernel<false>, grid, kEnvThreads, s, a);
     else                                     e = launch_pdl(env_step_fused_kernel<true>, grid, kEnvThreads, s, a);
     count_launch();
     return check_cuda(e, __func__);
@@ -931,7 +951,14 @@ struct Arena {
     cudaStream_t stream = nullptr;
 };
 static Arena g_arena[kMaxDevices];
-static std::mutex g_host_mutex;
+// one staging arena, stream and lock per DEVICE: host calls for different GPUs do not serialise behind each other
+static std::mutex g_host_mutex[kMaxDevices];
+static std::mutex &host_mutex()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return g_host_mutex[dev];
+}
 
 static int arena_begin(Arena **out, size_t need)
 {
@@ -990,7 +1017,7 @@ int g2048_host_env_reset(uint64_t *boards, int32_t *score, uint8_t *highest_exp,
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_env_reset: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<int32_t>(n) + arena_bytes<uint8_t>(n) + arena_bytes<uint32_t>(n)));
     uint64_t *d_b; int32_t *d_s; uint8_t *d_h; uint32_t *d_c;
@@ -1016,7 +1043,7 @@ int g2048_host_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards || !actions) return set_error(G2048_EINVAL, "g2048_host_env_step: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<uint32_t>(2 * n) + 2 * arena_bytes<int32_t>(n) +
                                   arena_bytes<uint32_t>(n) + arena_bytes<double>(n) + 5 * arena_bytes<uint8_t>(n)));
@@ -1058,7 +1085,7 @@ int g2048_host_env_rollout(uint64_t *boards, int32_t *score, uint8_t *highest_ex
     if (n < 0 || !boards || !score || !highest_exp || !spawn_ctr)
         return set_error(G2048_EINVAL, "g2048_host_env_rollout: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<int32_t>(n) + arena_bytes<uint8_t>(n) +
                                   arena_bytes<uint32_t>(n) + arena_bytes<double>(n)));
@@ -1087,7 +1114,7 @@ int g2048_host_legal_masks(const uint64_t *boards, uint8_t *env_legal, uint8_t *
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_legal_masks: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<uint8_t>(n)));
     uint64_t *d_b; uint8_t *d_e = nullptr, *d_g = nullptr;
@@ -1106,7 +1133,7 @@ int g2048_host_ppo_features(const uint64_t *boards, float *obs, double *heuristi
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_ppo_features: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<float>(16 * n) + 2 * arena_bytes<double>(n)));
     uint64_t *d_b; float *d_o = nullptr; double *d_h = nullptr, *d_t = nullptr;
@@ -1128,7 +1155,7 @@ int g2048_host_simulate_move(const uint64_t *boards, const uint8_t *actions, con
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards || !actions) return set_error(G2048_EINVAL, "g2048_host_simulate_move: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<uint8_t>(n) + arena_bytes<uint64_t>(32 * n) +
                                   arena_bytes<double>(32 * n) + arena_bytes<uint8_t>(32 * n) + arena_bytes<int32_t>(n) +
@@ -1160,7 +1187,7 @@ int g2048_host_hybrid_expand(const uint64_t *boards, const uint8_t *actions, con
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards || !actions) return set_error(G2048_EINVAL, "g2048_host_hybrid_expand: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<uint8_t>(n) + 3 * arena_bytes<uint32_t>(n) +
                                   arena_bytes<uint64_t>(8 * n) + arena_bytes<double>(8 * n) + arena_bytes<uint8_t>(8 * n) +
@@ -1190,7 +1217,7 @@ int g2048_host_evaluate(const uint64_t *boards, int32_t *fast, double *full, int
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !boards) return set_error(G2048_EINVAL, "g2048_host_evaluate: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + arena_bytes<int32_t>(n) + arena_bytes<double>(3 * n)));
     uint64_t *d_b; int32_t *d_f = nullptr; double *d_u = nullptr;
@@ -1212,7 +1239,7 @@ int g2048_host_beam_search(const uint64_t *roots, const uint8_t *legal, const ui
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0 || !roots || !action) return set_error(G2048_EINVAL, "g2048_host_beam_search: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, arena_bytes<uint64_t>(n) + 2 * arena_bytes<uint8_t>(n) + arena_bytes<uint32_t>(n) +
                                   arena_bytes<float>(n) + arena_bytes<double>(n) + arena_bytes<int32_t>(n)));
@@ -1242,7 +1269,7 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
     if (!current_device_state()) return G2048_ENOTINIT;
     if (n < 0) return set_error(G2048_EINVAL, "g2048_host_play_games: bad argument");
     if (n == 0) return G2048_OK;
-    std::lock_guard<std::mutex> lock(g_host_mutex);
+    std::lock_guard<std::mutex> lock(host_mutex());
     Arena *a;
     G2048_TRY(arena_begin(&a, 4 * arena_bytes<int32_t>(n) + arena_bytes<uint8_t>(n) + arena_bytes<int32_t>(8 * n) +
                                   arena_bytes<int64_t>(n) + arena_bytes<uint64_t>(n) + arena_bytes<int64_t>(G2048_STATS_LEN)));

@@ -204,6 +204,8 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
         spawn_base += (uint32_t)((__popc(D.x) + __popc(D.y)) + (__popc(D.z) + __popc(D.w)));
 
         // ---- B: spawn + evaluate (agent:155-161) ---------------------------------------------------------
+        G2048_ASSERT(!valid || (pos < (uint32_t)n_valid && n_valid <= kTeamThreads));
+        G2048_ASSERT(!draws || (ordinal < ring_end && ring_end - ordinal <= kTeamRing));      // the word is in the ring
         const uint2 w = reinterpret_cast<const uint2 *>(ts.rng)[ordinal & (kTeamRing - 1u)];
         const SpawnPick sp = pick_spawn(zl, zh, cl, n_empty, w.x, w.y);
         if (draws) {
@@ -245,6 +247,7 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
         else if (groups == 6) rank = count_larger_keys<6>(ts.key, key);
         else                  rank = count_larger_keys<8>(ts.key, key);
         nb = min(P.width, n_valid);
+        G2048_ASSERT(nb >= 1 && nb <= 32 && (!valid || rank < (uint32_t)n_valid));
         if (valid && (int)rank < nb) {
             ts.beam[rank] = b.u64();
             ts.meta[rank] = (uint8_t)(first | (emax << 2));

@@ -133,6 +133,12 @@ int g2048_simulate_move(const uint64_t *boards, const uint8_t *actions, const ui
 int g2048_hybrid_expand(const uint64_t *boards, const uint8_t *actions, const uint32_t *call, uint32_t call0,
                         const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
                         uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0, void *stream);
+/* The same expansion for the items of a beam (DQNAgent.beam_search, agents/hybrid.py:814-907): item i belongs to
+ * game `game0 + game[i]`, so that all (beam entry, action) items of one game draw from ONE stream at the
+ * offsets draw0[i] the caller assigns in the reference's order (hybrid.py:840-844). */
+int g2048_hybrid_expand_items(const uint64_t *boards, const uint8_t *actions, const uint32_t *game, const uint32_t *call,
+                              const uint32_t *draw0, uint64_t *next_boards, double *reward, uint8_t *done, int32_t *count,
+                              uint32_t *draws, int64_t n, uint64_t seed, uint32_t game0, void *stream);
 /* Game2048Env._evaluate_pattern (env:313-339): max(snake, corner weighted tile sums) / 100. */
 int g2048_evaluate_pattern(const uint64_t *boards, double *pattern, int64_t n, void *stream);
 
@@ -253,8 +259,8 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *                               first move (-1 = default: the team slots of the device, six per SM)
  *   G2048_TUNE_TAIL_THRESHOLD   g2048_play_games with more games: one warp per game until this many are
  *                               left alive, then teams (-1 = default: the team slots; 0 = never)
- *   G2048_TUNE_STEP_TABLES      g2048_env_step*: 0 = table-free SWAR row move (default), 1 = row tables
- *                               read through L1/L2 (the round-1 form; kept for A/B measurements)
+ *   G2048_TUNE_STEP_TABLES      g2048_env_step*: 0 = table-free SWAR row move, 1 = row tables read through L1/L2,
+ *                               -1 = default: table-free below 262,144 envs per launch, tables from there on
  *   G2048_TUNE_SPLIT_STALLS     g2048_play_games: 1 = a long stall (the agent keeps choosing an invalid move) is
  *                               cut into call ranges that several SMs search at once (default), 0 = one SM */
 enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2,

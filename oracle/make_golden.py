@@ -265,6 +265,22 @@ def main():
         state = env.reset() if d else nxt
     G["ppo_remember"] = rem
 
+    # ---- DQNAgent.beam_search (agents/hybrid.py:814-907) with the fixed-weight Q-network of oracle/hybrid_driver.py
+    from oracle import hybrid_driver as H
+    hmodel = H.tiny_q_model()
+    hagent, hybrid_env = R.load_hybrid_agent(shim, hmodel)
+    hb = []
+    for g in range(160):
+        b = synthetic_board(SEED, 7000 + g)
+        if g % 3 == 0:                                     # few / small tiles: the Q-network path (hybrid.py:821-834)
+            b = np.where(np.arange(16) % 3 == 0, np.minimum(b, 32), 0).astype(np.int32)
+        if b.max() == 0:
+            continue
+        hybrid_env.board = b.reshape(4, 4).copy()
+        shim.select(P.DOM_HYBRID, g, 5, 0)
+        hb.append({"board": L(b), "game": g, "call": 5, "action": int(hagent.beam_search(b.copy())), "draws": shim.draw})
+    G["hybrid_beam"] = hb
+
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(G, f, separators=(",", ":"))

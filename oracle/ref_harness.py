@@ -83,3 +83,18 @@ def load_hybrid_env_class(shim):
         sys.modules.update(saved)
     mod.random = shim
     return mod.Game2048Env
+
+
+def load_hybrid_agent(shim, model):
+    """(agent, env): agents/hybrid.DQNAgent of the unmodified reference around `model`, without its constructor
+    (which builds optimisers and moves to a device): only the attributes beam_search reads (hybrid.py:790-798)."""
+    import torch
+    HEnv = load_hybrid_env_class(shim)
+    mod = sys.modules[HEnv.simulate_move.__module__] if HEnv.simulate_move.__module__ in sys.modules else None
+    DQNAgent = HEnv.simulate_move.__globals__["DQNAgent"]
+    env = HEnv.__new__(HEnv)
+    env.size = 4; env.score = 0
+    agent = object.__new__(DQNAgent)
+    agent.env = env; agent.model = model; agent.device = torch.device("cpu")
+    agent.beam_width = 15; agent.search_depth = 30; agent.beam_search_threshold = 64; agent.gamma = 0.99
+    return agent, env

@@ -41,5 +41,5 @@ for n in (16384, 65536, 1048576):
                 sixty_four()
             e.record(); torch.cuda.synchronize()
             res[key + "_eager_us_per_step"] = s.elapsed_time(e) * 1e3 / (4 * 64)
-_lib.check(lib.g2048_set_tuning(3, 0))
+_lib.check(lib.g2048_set_tuning(3, -1))
 print(json.dumps(res))

@@ -14,7 +14,7 @@ def lib():
 
 
 TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD, TUNE_STEP_TABLES, TUNE_SPLIT_STALLS = 0, 1, 2, 3, 4
-_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1, TUNE_STEP_TABLES: 0,
+_TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1, TUNE_STEP_TABLES: -1,
                   TUNE_SPLIT_STALLS: 1}
 
 

@@ -492,3 +492,40 @@ def test_ppo_remember_sequence_from_reference(golden):
         got = shaper.shape(st, nx, rw)
         assert float(got[0]) == float.fromhex(rec["stored"]) and bool(shaper.novel[0]) == rec["novel"], rec
         assert (1 << int(shaper.highest_seen_exp[0])) == rec["highest_seen"]
+
+
+def test_hybrid_beam_driver_vs_reference_goldens_and_oracle(orc, golden):
+    """DQNAgent.beam_search batched (one expansion launch pair and at most one Q-network call per
+    level).  The reference's actions (goldens, fixed-weight Q-network) and, with hybrid.py:871 'fixed', the full-depth
+    loop against the oracle driver: float64 scores within 1e-5 relative (the Q-network runs in float32 on the GPU)."""
+    import torch
+    from oracle import hybrid_driver as H
+    model = H.tiny_q_model()
+    recs = [r for r in golden["hybrid_beam"] if max(r["board"]) <= 32768]
+    boards = torch.from_numpy(G.pack_boards(np.array([r["board"] for r in recs])).view(np.int64)).cuda()
+    search = G.HybridBeamSearch(H.tiny_q_model(), device="cuda:0", seed=golden["seed"])
+    # every record is game r["game"] with call 5; games are consecutive ids here, so one batched call does
+    games = [r["game"] for r in recs]
+    got = torch.zeros(len(recs), dtype=torch.int64)
+    for lo in range(0, len(recs)):                           # game ids have gaps: one call per record
+        a, sc = search.get_actions(boards[lo:lo + 1], call=5, game0=games[lo])
+        got[lo] = a[0].cpu()
+    assert got.tolist() == [r["action"] for r in recs]
+    # batched, against the oracle driver, both forms of the loop
+    vals, packed = X.synthetic(orc, 96, SEED, 7000)
+    pb = torch.from_numpy(packed.view(np.int64)).cuda()
+    for early_exit, depth in ((True, 30), (False, 4)):
+        search = G.HybridBeamSearch(H.tiny_q_model(), search_depth=depth, device="cuda:0", seed=SEED, reference_early_exit=early_exit)
+        a, sc = search.get_actions(pb, call=2, game0=7000)
+        a = a.cpu().numpy(); sc = sc.cpu().numpy()
+        for i in range(96):
+            want, scores = H.beam_search(vals[i], model, SEED, 7000 + i, 2, search_depth=depth, reference_early_exit=early_exit)
+            if not scores:
+                assert a[i] == want
+                continue
+            for act, v in scores.items():
+                assert abs(sc[i, act] - v) <= 1e-5 * max(1.0, abs(v)), (i, act, sc[i], scores)
+            assert set(np.flatnonzero(~np.isnan(sc[i]))) == set(scores)
+            ranked = sorted(scores.values(), reverse=True)
+            if len(ranked) == 1 or ranked[0] - ranked[1] > 1e-4 * max(1.0, abs(ranked[0])):     # not a near-tie
+                assert a[i] == want, (i, sc[i], scores)

@@ -149,3 +149,11 @@ def test_ppo_remember_sequence(orc, golden):
         want, highest = orc.ppo_shape_reward(rec["state"], rec["next"], float.fromhex(rec["reward"]), highest, rec["novel"])
         assert want == float.fromhex(rec["stored"]) and highest == rec["highest_seen"], rec
     assert any(r["novel"] for r in golden["ppo_remember"]) and not all(r["novel"] for r in golden["ppo_remember"])
+
+
+def test_hybrid_beam_search(orc, golden):
+    from oracle import hybrid_driver as H
+    model = H.tiny_q_model()
+    for rec in golden["hybrid_beam"]:
+        got, _ = H.beam_search(rec["board"], model, golden["seed"], rec["game"], rec["call"])
+        assert got == rec["action"], rec

@@ -164,3 +164,26 @@ def test_ppo_remember_reward_shaping_vs_reference(orc):
         assert highest == ppo.highest_tile_seen
         state = env.reset() if done else nxt
     assert highest >= 64
+
+
+def test_hybrid_beam_search_vs_reference(orc):
+    """DQNAgent.beam_search (agents/hybrid.py:814-907) with a fixed-weight Q-network: the oracle driver picks the
+    reference's action on simple boards (Q-network path) and on complex ones (one level, hybrid.py:871)."""
+    from oracle import hybrid_driver as H
+    shim = P.StreamShim(SEED)
+    model = H.tiny_q_model()
+    agent, env = R.load_hybrid_agent(shim, model)
+    n_simple = n_beam = 0
+    for g in range(300):
+        b = orc.synthetic_board(SEED, 7000 + g)
+        if g % 3 == 0:                                     # early boards: few / small tiles -> the Q-network path
+            b = np.where(np.arange(16) % 3 == 0, np.minimum(b, 32), 0).astype(np.int32)
+        if b.max() == 0:
+            continue
+        env.board = b.reshape(4, 4).copy()
+        shim.select(P.DOM_HYBRID, g, 5, 0)
+        want = int(agent.beam_search(b.copy()))
+        got, scores = H.beam_search(b, model, SEED, g, 5)
+        assert got == want, (g, b, scores)
+        n_simple += not scores; n_beam += bool(scores)
+    assert n_simple >= 50 and n_beam >= 100
