@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 RAW_KEYS = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -97,8 +97,41 @@ def launch_list(path):
     return lines
 
 
+def stall_by_hot_loop(rep, lo, hi):
+    """Stall-reason shares over the instructions whose execution count lies in [lo, hi]: picks the level loop of the
+    ONE active team out of a team_games_kernel capture whose other 147 blocks only wait (profiles/ncu_cases.py lone)."""
+    rows = list(csv.reader(ncu(["-i", rep, "--page", "source", "--csv"]).splitlines()))
+    hdr = rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    tot = collections.Counter()
+    n = inst = samples = 0
+    for r in rows[2:]:
+        if len(r) < len(hdr):
+            continue
+        ex = int(r[ix["Instructions Executed"]])
+        if lo <= ex <= hi:
+            n += 1; inst += ex; samples += int(r[ix["# Samples"]])
+            for k in stalls:
+                tot[k] += int(r[ix[k]])
+    lines = [f"instructions of the level loop (executed {lo}..{hi} times): {n}; warp-instructions executed {inst}; samples {samples}",
+             "warp state of the team's warps over those samples:"]
+    for k, v in tot.most_common(8):
+        lines.append(f"  {k:28s} {100 * v / max(1, samples):5.1f} %")
+    return lines, inst
+
+
+def csrc_hash():
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.csrc_hash()
+
+
 def main():
     text = [f"# ncu summaries, round {tag} (B200, sm_100a)", ""]
+    consts = {"csrc_sha16": csrc_hash(), "round": tag,
+              "int32_peaks": {"alu_pipe_warp_inst_per_s": 5.79e11, "alu_plus_fma_warp_inst_per_s": 1.13e12,
+                              "source": "profiles/int32_peak_r01.json"}}
     ll = os.path.join(OUT, f"launches_{tag}.csv")
     if os.path.exists(ll):
         text += launch_list(ll) + [""]
@@ -107,18 +140,49 @@ def main():
     if os.path.exists(rep):
         lines, d = raw_summary(rep, "env_rollout_kernel (headline kernel)", ("board-step (warp-step = 32 board-steps)", n_steps, "65,536 envs x 2,000 steps per launch"))
         text += lines + opcode_hist(rep, n_steps, "warp-step") + [""]
-    rep = os.path.join(OUT, f"prof_beam_r01.ncu-rep".replace("r01", tag))
+        f = lambda k: float(d[k][1].replace(",", ""))          # noqa: E731
+        unit = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+        alu = f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
+        smsp_cycles = f("sm__cycles_elapsed.max") * 148 * 4 / n_steps
+        consts["rollout"] = {
+            "warp_inst_per_warp_step": f("smsp__inst_executed.sum") / n_steps,
+            "alu_warp_inst_per_warp_step": alu / 100 * 0.5 * smsp_cycles,
+            "dram_bytes_per_launch": int((f("dram__bytes_read.sum") * unit[d["dram__bytes_read.sum"][0]]) +
+                                         (f("dram__bytes_write.sum") * unit[d["dram__bytes_write.sum"][0]])),
+            "alu_pipe_pct_of_peak": alu, "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct_of_peak": f("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "source": f"profiles/ncu_summary_{tag}.md"}
+    rep = os.path.join(OUT, f"prof_beam_{tag}.ncu-rep")
     if os.path.exists(rep):
-        lines, d = raw_summary(rep, "beam_search_kernel (width 20, depth 40, 10,000 roots)")
+        lines, d = raw_summary(rep, "beam_search_kernel (width 20, depth 40, 10,000 roots, one warp per root)")
         text += lines + [""]
+        f = lambda k: float(d[k][1].replace(",", ""))          # noqa: E731
+        unit = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+        consts["beam"] = {"alu_pipe_pct_of_peak": f("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                          "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          "dram_bytes_per_launch": int((f("dram__bytes_read.sum") * unit[d["dram__bytes_read.sum"][0]]) +
+                                                       (f("dram__bytes_write.sum") * unit[d["dram__bytes_write.sum"][0]])),
+                          "source": f"profiles/ncu_summary_{tag}.md"}
     rep = os.path.join(OUT, f"prof_step_{tag}.ncu-rep")
     if os.path.exists(rep):
-        lines, d = raw_summary(rep, "env_step_kernel<global tables> (per-step API, 65,536 envs per launch)")
+        lines, d = raw_summary(rep, "env_step_fused_kernel<table-free move> (per-step API, 65,536 envs per launch, all outputs incl. observation)")
+        text += lines + [""]
+    rep = os.path.join(OUT, f"prof_lone_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        text += ["## team_games_kernel, ONE game (400 moves at 20/40): the sequential chain that bounds whole-game runs",
+                 f"report: {os.path.basename(rep)}; 147 of the 148 blocks only wait (they would break stalls), so the kernel-level",
+                 "metrics say nothing about the team; the per-instruction samples of its level loop do:", ""]
+        lines, inst = stall_by_hot_loop(rep, 20000, 60000)
         text += lines + [""]
     path = os.path.join(ROOT, "profiles", f"ncu_summary_{tag}.md")
     with open(path, "w") as f:
         f.write("\n".join(text) + "\n")
     print("wrote", path)
+    if "rollout" in consts and "beam" in consts:
+        cpath = os.path.join(ROOT, "profiles", "ncu_constants.json")
+        with open(cpath, "w") as f:
+            json.dump(consts, f, indent=1)
+        print("wrote", cpath, "for csrc", consts["csrc_sha16"])
 
 
 if __name__ == "__main__":
