@@ -1218,10 +1218,10 @@ static int ensure_attrs()
 struct LaunchScratch {
     void *ptr = nullptr;
     cudaStream_t stream = nullptr;
-    int alloc(size_t bytes, size_t zero_bytes, cudaStream_t s)
+    int alloc(DeviceState *st, size_t bytes, size_t zero_bytes, cudaStream_t s)
     {
         stream = s;
-        G2048_CUDA(cudaMallocAsync(&ptr, bytes, s));
+        G2048_CUDA(cudaMallocFromPoolAsync(&ptr, bytes, st->pool, s));
         G2048_CUDA(cudaMemsetAsync(ptr, 0, zero_bytes, s));
         return G2048_OK;
     }
@@ -1236,7 +1236,7 @@ int launch_beam_search(DeviceState *st, const uint64_t *roots, const uint8_t *le
     int rc = ensure_attrs();
     if (rc != G2048_OK) return rc;
     LaunchScratch scratch;
-    rc = scratch.alloc(sizeof(unsigned int), sizeof(unsigned int), stream);
+    rc = scratch.alloc(st, sizeof(unsigned int), sizeof(unsigned int), stream);
     if (rc != G2048_OK) return rc;
     BeamArgs a{roots, legal, call, call0, action, prob, best_score, nodes, n,
                BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
@@ -1294,7 +1294,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     const size_t records_off = pending_off + round256(pending_cap * sizeof(GameState));
     const size_t tail_off = records_off + round256(record_cap * sizeof(StallRecord));
     LaunchScratch scratch;
-    rc = scratch.alloc(tail_off + (size_t)tail_cap * sizeof(GameState), pending_off, stream);
+    rc = scratch.alloc(st, tail_off + (size_t)tail_cap * sizeof(GameState), pending_off, stream);
     if (rc != G2048_OK) return rc;
     uint8_t *base = static_cast<uint8_t *>(scratch.ptr);
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},

@@ -18,6 +18,10 @@ struct DeviceState {
     uint8_t *code = nullptr;                 // merge codes per 16-bit row
     unsigned long long *overflow = nullptr;  // sticky nibble-saturation counter
     int sm_count = 0;
+    // Stream-ordered pool for per-launch scratch.  Its release threshold is unlimited: the default pool hands
+    // free memory back to the driver at every synchronisation, so a host call that ends in a stream sync would
+    // pay a fresh device allocation (~0.4 ms) on its next launch.
+    cudaMemPool_t pool = nullptr;
 };
 
 // Returns the state of the current device, or nullptr (and sets the error) if g2048_init

@@ -663,6 +663,14 @@ int g2048_init(int device)
     G2048_CUDA(cudaMemcpy(st.code, code.data(), kCodeTableBytes, cudaMemcpyHostToDevice));
     G2048_CUDA(cudaMemset(st.overflow, 0, sizeof(unsigned long long)));
     G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    G2048_CUDA(cudaMemPoolCreate(&st.pool, &props));
+    uint64_t keep = UINT64_MAX;
+    G2048_CUDA(cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep));
     const int smem = (int)(kRowTableBytes + kCodeTableBytes);
     G2048_CUDA(cudaFuncSetAttribute(env_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     st.ready = true;
