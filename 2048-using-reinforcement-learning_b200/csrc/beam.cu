@@ -653,13 +653,17 @@ struct GameState {
 // are cut into `segs` ranges of `seg_len` calls that different SMs search at once (every call sees the same
 // board: an invalid move changes nothing).  The lowest range that holds a valid call decides where the stall
 // ends; ranges above it are cancelled.  The group that finishes the last range puts the game together again.
-constexpr int kMaxSegs = 8;
+constexpr int kMaxSegs = 32;
 constexpr int kSplitAfterRounds = 4;       // full-width rounds without a valid call before a stall is split
-constexpr int kMinSegCalls = 96;           // calls per range at least
+constexpr int kMinSegCalls = 96;           // calls per range at least (ranges searched by a group of the stall breaker)
+constexpr int kWarpSegCalls = 8;           // calls per range at least (ranges searched by one warp, play_games_kernel)
+constexpr int kWarpSplitFirst = 64;        // calls the first split of a stall covers; every dry split doubles the stretch
+constexpr int kWarpSplitMax = 1024;        // ... up to this many (the one-warp kernel ends when its last record does)
 struct SegResult { int32_t first_valid; uint32_t action; long long nodes; };
 struct StallRecord {
     GameState gs;                          // the game at the split; gs.moves = first call of range 0
     int32_t seg_len, segs;
+    int32_t calls;                         // calls the record covers: [gs.moves, gs.moves + calls)
     int32_t done;                          // ranges finished
     int32_t first_valid_seg;               // lowest range that found a valid call (kMaxSegs: none so far)
     SegResult res[kMaxSegs];
@@ -677,7 +681,13 @@ struct GameCounters {
     unsigned int written;         // games whose results are final (the stall breaker leaves when this reaches n)
     int idle_groups;              // stall-breaker groups waiting for work that no migrating game has reserved yet
     unsigned int record_count;    // StallRecords handed out
-    unsigned int pad[3];
+    unsigned int group_splits;    // ... of them by the stall breaker (its ranges travel through pending[])
+    unsigned int seg_tail;        // ranges pushed to segq (one-warp kernel)
+    unsigned int seg_head;        // ranges claimed from segq
+    unsigned int in_stall;        // games of the one-warp kernel that are inside a split stall (not counted as alive
+                                  // for the hand-over to the team kernel: they come back when their stall ends)
+    unsigned int handover;        // the one-warp kernel has started handing its games to the team kernel (sticky)
+    unsigned int pad[2];
 };
 
 struct GamesArgs {
@@ -691,6 +701,9 @@ struct GamesArgs {
     unsigned int pending_cap;      // entries pending[] can hold (games + ranges of split stalls)
     StallRecord *records;          // split stalls (nullptr: never split)
     unsigned int record_cap;
+    unsigned int group_split_cap;  // splits the stall breaker may make (each puts up to kMaxSegs - 1 entries into pending[])
+    unsigned int *segq;            // ranges for the warps of play_games_kernel: (record << 5 | range) + 1, 0 = not written yet
+    unsigned int segq_cap;
     GameState *tail;               // live games handed to team_games_kernel once few are left (nullptr: never)
     unsigned int tail_threshold;   // ... i.e. once n - finished <= tail_threshold
 };
@@ -708,6 +721,7 @@ __device__ __forceinline__ void write_game(const GamesArgs &a, const GameState &
         for (int m = 0; m < 8; ++m) a.milestone[8 * i + m] = g.ms[m];
     if (a.nodes) a.nodes[i] = g.nodes;
     if (a.final_board) a.final_board[i] = g.board;
+    GAME_EVT(0, i);
 }
 
 // Game2048Env() -> __init__ calls reset (env:27); state = env.reset() (evaluate_beam_search.py:30)
@@ -782,13 +796,27 @@ __device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, b
         atomicAdd(&a.ctr->written, 1u);
     } else if (to == kRetireTail) {
         const unsigned int slot = atomicAdd(&a.ctr->tail_count, 1u);
-        G2048_ASSERT(slot < a.tail_threshold);
+        G2048_ASSERT(slot < (unsigned int)a.n);
         a.tail[slot] = gs;
+        GAME_EVT(2, gs.index);
     } else {
+        GAME_EVT(to == kRetireMigrate ? 3 : 1, gs.index);
         gs.reserved = to == kRetireMigrate ? kEntryMigrated : kEntryStalled;
         push_pending(a, gs);
         if (to == kRetirePending) atomicAdd(&a.ctr->finished, 1u);
     }
+}
+
+// The hand-over to the team kernel starts when the games the one-warp kernel is still PLAYING (not finished, not
+// parked, not inside a split stall, not handed over yet) fall to the threshold; from then on every game leaves
+// after its current move, and a game that comes back from a stall is handed over at once (the flag is sticky).
+__device__ __forceinline__ bool handover_started(const GamesArgs &a)
+{
+    volatile GameCounters *c = a.ctr;
+    if (c->handover) return true;
+    if ((int)a.n - (int)c->finished - (int)c->in_stall - (int)c->tail_count > (int)a.tail_threshold) return false;
+    c->handover = 1u;
+    return true;
 }
 
 // Whole games (evaluate_beam_search.py:16-98), throughput form: one warp plays one game, fetching
@@ -796,39 +824,236 @@ __device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, b
 // still alive would all fit the team kernel (one team of four warps each), every warp hands its
 // game over after its current move and leaves: from there on the chain of moves of the longest
 // game, not the ALU pipe, bounds the run.
+//
+// Stalls are broken HERE, as they appear (a parked game would wait for the whole phase and then be the
+// last one to finish): the warp whose game has made kStallStreak invalid moves in a row cuts the next
+// calls -- 64 at first, twice the stretch after every dry split -- into ranges of >= 8 calls
+// (StallRecord), takes range 0 itself and puts the others into `segq`.  Every warp that needs work
+// takes a range before it takes a new game; warps without a game (few games per SM) wait for ranges.
+// A range is searched call by call (every call sees the same board) until one chooses a valid move
+// or a lower range has found one; the warp that finishes the LAST range of a record puts the game
+// together again (same arithmetic as the stall breaker's run_segment) and plays on with it.
+// The loop makes ONE search per iteration whatever the warp is doing, so the search is inlined once.
+// What a warp of play_games_kernel knows about its game / range, in shared memory: it is touched once per move
+// (by lane 0), while the search between two moves wants every register.
+struct WarpGame {
+    GameState gs;
+    StallRecord *rec;              // the range being searched: calls [m, hi) of `rec`, `lo` = its first call
+    int seg, lo, hi, m;
+    long long seg_nodes;
+};
+
 __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ WarpGame games[kBeamWarps];
     stage_row_table(smem, a.row);
     const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
+    WarpGame &wg = games[warp];
+    GameState &gs = wg.gs;
     const uint32_t lane = threadIdx.x & 31u;
-    const volatile unsigned int *finished = &a.ctr->finished;
-    for (;;) {
-        unsigned int g = 0;
-        if (lane == 0) g = atomicAdd(&a.ctr->work, 1u);
-        g = __shfl_sync(FULL, g, 0);
-        if ((int64_t)g >= a.n) break;
-        const uint32_t game = a.game0 + g;
-        EnvState s;
-        GameState gs;
-        start_game(gs, s, a.P.K, game, g);
-        bool done = false, to_tail = false;
-        while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
-            if (a.tail) {                                  // warp-uniform: lane 0 reads, everyone follows
-                unsigned int f = 0;
-                if (lane == 0) f = *finished;
-                f = __shfl_sync(FULL, f, 0);
-                to_tail = (unsigned int)a.n - f <= a.tail_threshold;
-                if (to_tail) break;
-            }
-            const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ws);
-            done = play_move(gs, s, r, a, row, game);
+    const bool can_split = a.pending && a.records && a.segq;
+#ifdef G2048_TEAM_PROFILE
+    if (threadIdx.x == 0) atomicMin(&g_game_ts[6][0], prof_now());
+#endif
+    enum { kNeedWork = 0, kPlaying = 1, kInRange = 2 };
+    int state = kNeedWork;
+    bool queue_dry = false, done = false;
+    EnvState s;                    // board, score, highest tile, spawn counter: registers (the search starts from the board)
+    uint32_t game = 0u, legal = 0u;
+
+    // env.step(action) and the bookkeeping of evaluate_beam_search.py:56-86 (play_move) on the shared-memory record
+    auto make_move = [&](uint32_t action, int nodes) {
+        const StepResult st = env_step<true, false, false>(s, action, row, a.code, a.P.K, game, nullptr, a.overflow);
+        if (lane == 0) {
+            gs.nodes += nodes;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (gs.ms[k] < 0 && s.highest >= (uint32_t)(6 + k)) gs.ms[k] = gs.moves;
+            if (st.valid) { ++gs.valid; gs.streak = 0; } else { ++gs.invalid; ++gs.streak; }
+            ++gs.moves;
         }
-        store_env(gs, s);
-        if (lane == 0) retire_game(a, gs, done, to_tail ? kRetireTail : kRetirePending);
         __syncwarp();
+        done = st.done;
+    };
+    auto begin_range = [&](StallRecord *r, int k) {
+        if (lane == 0) {
+            gs = load_shared_record(&r->gs);
+            const int seg_len = __ldcg(&r->seg_len);
+            wg.rec = r; wg.seg = k;
+            wg.lo = gs.moves + k * seg_len;
+            wg.hi = min(wg.lo + seg_len, gs.moves + __ldcg(&r->calls));
+            wg.m = wg.lo;
+            wg.seg_nodes = 0;
+        }
+        __syncwarp();
+        load_env(gs, s);
+        game = a.game0 + gs.index;
+        legal = env_legal_mask(s.board);
+        state = kInRange;
+    };
+    // Ends the range (found = offset of its valid call or -1).  The warp that finishes the record's last range
+    // re-assembles the game: then state = kPlaying with the game after the stall's valid move, or still inside
+    // the stall when the record covered no valid call (the next split is longer).
+    auto end_range = [&](int found, uint32_t action) {
+        unsigned int last = 0u;
+        StallRecord *rec = wg.rec;
+        const int segs = __ldcg(&rec->segs);
+        if (lane == 0) {
+            const int seg = wg.seg;
+            rec->res[seg].first_valid = found; rec->res[seg].action = action; rec->res[seg].nodes = wg.seg_nodes;
+            if (found >= 0) atomicMin(&rec->first_valid_seg, seg);
+            __threadfence();
+            last = atomicAdd(&rec->done, 1) + 1 == segs;
+        }
+        last = __shfl_sync(FULL, last, 0);
+        state = kNeedWork;
+        if (!last) return;
+        __threadfence();
+        const int f = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg);
+        const volatile SegResult *res = rec->res;
+        const int seg_len = __ldcg(&rec->seg_len), calls = __ldcg(&rec->calls);
+        state = kPlaying;
+        done = false;
+        if (f >= segs) {                                   // no valid call in this stretch: all of it was invalid moves
+            if (lane == 0) {
+                for (int k = 0; k < segs; ++k) gs.nodes += res[k].nodes;
+                gs.invalid += calls; gs.moves += calls; gs.streak += calls;
+            }
+            __syncwarp();
+            return;
+        }
+        const int before = f * seg_len + res[f].first_valid;      // invalid moves: nothing else changes (env:188-192)
+        if (lane == 0) {
+            for (int k = 0; k <= f; ++k) gs.nodes += res[k].nodes;
+            gs.invalid += before;
+            gs.moves += before;
+            gs.reserved = 0;
+            atomicSub(&a.ctr->in_stall, 1u);
+        }
+        __syncwarp();
+        make_move(res[f].action, 0);
+    };
+
+    for (;;) {
+        if (state == kNeedWork) {
+            if (can_split) {                               // a range of somebody's stall comes first
+                unsigned int task = 0u;
+                if (lane == 0) {
+                    volatile unsigned int *head = &a.ctr->seg_head, *tail = &a.ctr->seg_tail;
+                    for (;;) {
+                        const unsigned int h = *head;
+                        if (h >= *tail) break;
+                        if (atomicCAS(&a.ctr->seg_head, h, h + 1u) != h) continue;
+                        G2048_ASSERT(h < a.segq_cap);
+                        while ((task = *reinterpret_cast<volatile unsigned int *>(&a.segq[h])) == 0u) __nanosleep(100);
+                        __threadfence();
+                        break;
+                    }
+                }
+                task = __shfl_sync(FULL, task, 0);
+                if (task) begin_range(&a.records[(task - 1u) >> 5], (int)((task - 1u) & 31u));
+            }
+            if (state == kNeedWork && !queue_dry) {
+                unsigned int g = 0;
+                if (lane == 0) g = atomicAdd(&a.ctr->work, 1u);
+                g = __shfl_sync(FULL, g, 0);
+                if ((int64_t)g >= a.n) queue_dry = true;
+                else {
+                    game = a.game0 + g;
+                    GameState fresh;
+                    start_game(fresh, s, a.P.K, game, g);
+                    if (lane == 0) gs = fresh;
+                    __syncwarp();
+                    done = false;
+                    state = kPlaying;
+                }
+            }
+            if (state == kNeedWork) {                      // no game, no range
+                if (!can_split) break;
+                unsigned int over = 0u;
+                if (lane == 0) {
+                    const volatile GameCounters *c = a.ctr;
+                    over = (a.tail ? handover_started(a) : c->finished >= (unsigned int)a.n) && c->seg_head >= c->seg_tail;
+                    if (!over) __nanosleep(2000);
+                }
+                if (__shfl_sync(FULL, over, 0)) break;
+                continue;
+            }
+        }
+        if (state == kPlaying) {
+            const int moves = gs.moves, streak = gs.streak;
+            bool leave = done || moves >= a.max_moves;
+            int to = kRetirePending;
+            if (!leave && a.tail) {                        // warp-uniform: lane 0 reads, everyone follows
+                unsigned int go = 0u;
+                if (lane == 0) go = handover_started(a);
+                if (__shfl_sync(FULL, go, 0)) { leave = true; to = kRetireTail; }
+            }
+            if (!leave && a.pending && streak >= kStallStreak) {
+                // split the next stretch of calls into ranges
+                unsigned int idx = a.record_cap;
+                if (can_split && lane == 0) {
+                    const int rem = a.max_moves - moves;
+                    const int calls = min(rem, min(kWarpSplitMax, max(kWarpSplitFirst, streak)));
+                    const int seg_len = max(kWarpSegCalls, (calls + kMaxSegs - 1) / kMaxSegs);
+                    const int segs = (calls + seg_len - 1) / seg_len;            // no range is empty
+                    idx = atomicAdd(&a.ctr->record_count, 1u);
+                    if (idx < a.record_cap) {
+                        StallRecord *r = &a.records[idx];
+                        store_env(gs, s);
+                        if (!gs.reserved) { gs.reserved = 1; atomicAdd(&a.ctr->in_stall, 1u); }    // counted until the stall ends
+                        r->gs = gs;
+                        r->segs = segs;
+                        r->seg_len = seg_len;
+                        r->calls = calls;
+                        r->done = 0;
+                        r->first_valid_seg = kMaxSegs;
+                        GAME_EVT(5, gs.index);
+                        __threadfence();
+                        if (segs > 1) {
+                            const unsigned int slot = atomicAdd(&a.ctr->seg_tail, (unsigned int)(segs - 1));
+                            G2048_ASSERT(slot + (unsigned int)(segs - 1) <= a.segq_cap);
+                            for (int k = 1; k < segs; ++k)
+                                *reinterpret_cast<volatile unsigned int *>(&a.segq[slot + (unsigned int)(k - 1)]) = ((idx << 5) | (unsigned int)k) + 1u;
+                        }
+                    }
+                }
+                idx = __shfl_sync(FULL, idx, 0);
+                if (idx < a.record_cap) begin_range(&a.records[idx], 0);
+                else leave = true;                         // no record left: park the game for the stall breaker
+            }
+            if (leave) {
+                if (lane == 0) {
+                    store_env(gs, s);
+                    if (gs.reserved) { atomicSub(&a.ctr->in_stall, 1u); gs.reserved = 0; }   // move cap / handed over inside a stall
+                    retire_game(a, gs, done, to);
+                }
+                __syncwarp();
+                state = kNeedWork;
+                continue;
+            }
+        }
+        // ---- one get_action call: the game's next move, or call m of the range -----------------------------
+        const uint32_t call = state == kInRange ? (uint32_t)wg.m : (uint32_t)gs.moves;
+        const BeamResult r = beam_search_warp(s.board, -1, a.P, game, call, row, ws);
+        if (state == kPlaying) {
+            make_move(r.action, r.nodes);
+        } else {
+            const int m = wg.m;
+            __syncwarp();
+            if (lane == 0) { wg.seg_nodes += r.nodes; wg.m = m + 1; }
+            __syncwarp();
+            if ((legal >> r.action) & 1u) end_range(m - wg.lo, r.action);
+            else {
+                unsigned int cancelled = 0u;               // a lower range ended the stall
+                if (lane == 0) cancelled = *reinterpret_cast<volatile int32_t *>(&wg.rec->first_valid_seg) < wg.seg;
+                cancelled = __shfl_sync(FULL, cancelled, 0);
+                if (m + 1 >= wg.hi || cancelled) end_range(-1, 0u);
+            }
+        }
     }
 }
 
@@ -992,7 +1217,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
             G2048_ASSERT((unsigned int)gs.score < a.record_cap && gs.moves >= 1 && gs.moves < kMaxSegs);
             if (!run_segment(&a.records[gs.score], gs.moves, gs, s, done)) continue;
         } else {
-            if (leader) GAMES_PROF_ADD(6, 1);
+            if (leader) { GAMES_PROF_ADD(6, 1); GAME_EVT(4, gs.index); }
             load_env(gs, s);
         }
         const uint32_t game = a.game0 + gs.index;
@@ -1005,7 +1230,8 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                 dry_rounds = 0;
                 if (leader) {
                     int got = -1;
-                    const unsigned int idx = atomicAdd(&a.ctr->record_count, 1u);
+                    const unsigned int idx = atomicAdd(&a.ctr->group_splits, 1u) < a.group_split_cap
+                                                 ? atomicAdd(&a.ctr->record_count, 1u) : a.record_cap;
                     if (idx < a.record_cap) {
                         StallRecord *rec = &a.records[idx];
                         const int rem = a.max_moves - gs.moves;
@@ -1016,6 +1242,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                         rec->seg_len = (rem + segs - 1) / segs;
                         rec->done = 0;
                         rec->first_valid_seg = kMaxSegs;
+                        GAME_EVT(5, gs.index);
                         __threadfence();
                         GameState entry = gs;
                         entry.reserved = kEntrySegment;
@@ -1116,7 +1343,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
         const unsigned int p = ts.next_item;
         team_barrier(bar);                                 // everyone has read it before the next round rewrites it
         if (p >= total) { if (leader) GAMES_PROF_MIN(1); break; }
-        G2048_ASSERT(!in || p < a.tail_threshold);
+        G2048_ASSERT(!in || p < (unsigned int)a.n);
         EnvState s;
         GameState gs;
         if (in) { gs = in[p]; load_env(gs, s); }
@@ -1178,6 +1405,17 @@ extern "C" int g2048_debug_games_profile(unsigned long long *out8)
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
     if (cudaMemcpyFromSymbol(out8, g2048::g_games_prof, sizeof init) != cudaSuccess) return -1;
     return cudaMemcpyToSymbol(g2048::g_games_prof, init, sizeof init) == cudaSuccess ? 0 : -1;
+}
+// per-game event times of the last g2048_play_games call (see g_game_ts): out = uint64[7][16384]; resets them
+extern "C" int g2048_debug_game_times(unsigned long long *out)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out, g2048::g_game_ts, sizeof g2048::g_game_ts) != cudaSuccess) return -1;
+    void *p = nullptr;
+    if (cudaGetSymbolAddress(&p, g2048::g_game_ts) != cudaSuccess) return -1;
+    if (cudaMemset(p, 0, sizeof g2048::g_game_ts) != cudaSuccess) return -1;
+    const unsigned long long big = ~0ull;
+    return cudaMemcpy(reinterpret_cast<unsigned long long *>(p) + 6 * g2048::kProfGames, &big, sizeof big, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
 }
 namespace g2048 {
 #endif
@@ -1284,27 +1522,36 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     const int64_t direct_max = g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] >= 0 ? g_tuning[G2048_TUNE_TEAM_DIRECT_MAX] : team_slots;
     const int64_t tail_thr = g_tuning[G2048_TUNE_TAIL_THRESHOLD] >= 0 ? g_tuning[G2048_TUNE_TAIL_THRESHOLD] : team_slots;
     const bool direct = !wide && n <= direct_max;
-    const int64_t tail_cap = wide || direct ? 0 : (tail_thr < n ? tail_thr : n);
-    // scratch: counters | ready flags of the pending entries | pending entries (stalled / migrated games, ranges of
-    // split stalls) | split-stall records | games for the team kernel
-    const size_t record_cap = wide ? 0 : (size_t)(n / 2 > 8 ? n / 2 : 8);
-    const size_t pending_cap = wide ? 0 : (size_t)n + (kMaxSegs - 1) * record_cap;
+    // (games that are inside a split stall at the hand-over follow later: the tail array can hold every game)
+    const int64_t tail_cap = wide || direct || tail_thr <= 0 ? 0 : n;
+    const int64_t tail_threshold = tail_thr < n ? tail_thr : n;
+    // scratch: counters | ready flags of the pending entries | range queue of the one-warp kernel | pending entries
+    // (stalled / migrated games, ranges of stalls the stall breaker split) | split-stall records | games for the
+    // team kernel.  Everything before the pending entries is zeroed.
+    const bool warp_phase = !wide && !direct;
+    const size_t group_split_cap = wide ? 0 : (size_t)(n / 8 > 8 ? n / 8 : 8);
+    const size_t record_cap = wide ? 0 : group_split_cap + (warp_phase ? 2 * (size_t)n + 64 : 0);
+    const size_t pending_cap = wide ? 0 : (size_t)n + (kMaxSegs - 1) * group_split_cap;
+    const size_t segq_cap = warp_phase ? (kMaxSegs - 1) * (2 * (size_t)n + 64) : 0;
     auto round256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t flags_off = 256, pending_off = flags_off + round256(pending_cap * sizeof(unsigned int));
+    const size_t flags_off = 256, segq_off = flags_off + round256(pending_cap * sizeof(unsigned int));
+    const size_t pending_off = segq_off + round256(segq_cap * sizeof(unsigned int));
     const size_t records_off = pending_off + round256(pending_cap * sizeof(GameState));
     const size_t tail_off = records_off + round256(record_cap * sizeof(StallRecord));
     LaunchScratch scratch;
     rc = scratch.alloc(st, tail_off + (size_t)tail_cap * sizeof(GameState), pending_off, stream);
     if (rc != G2048_OK) return rc;
     uint8_t *base = static_cast<uint8_t *>(scratch.ptr);
+    const bool split = !wide && g_tuning[G2048_TUNE_SPLIT_STALLS] != 0;
     GamesArgs a{n, BeamParams{beam_width, search_depth, early_thr, mid_thr, make_philox_key(seed)},
                 max_moves, game0, score, highest_exp, moves, valid, invalid, milestone, nodes, final_board,
                 st->row, st->code, st->overflow, reinterpret_cast<GameCounters *>(base),
                 wide ? nullptr : reinterpret_cast<GameState *>(base + pending_off),
                 wide ? nullptr : reinterpret_cast<unsigned int *>(base + flags_off), (unsigned int)pending_cap,
-                wide || !g_tuning[G2048_TUNE_SPLIT_STALLS] ? nullptr : reinterpret_cast<StallRecord *>(base + records_off),
-                (unsigned int)record_cap,
-                tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_cap};
+                split ? reinterpret_cast<StallRecord *>(base + records_off) : nullptr,
+                (unsigned int)record_cap, (unsigned int)group_split_cap,
+                split && segq_cap ? reinterpret_cast<unsigned int *>(base + segq_off) : nullptr, (unsigned int)segq_cap,
+                tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_threshold};
     const int grid = (int)(n < st->sm_count ? n : st->sm_count);    // spread small runs over all SMs (see beam search)
     if (wide) {                                                     // wide beams: compatibility path, no stall breaker
         int64_t wwarps = (n + grid - 1) / grid;

@@ -47,6 +47,11 @@ __device__ __forceinline__ unsigned long long prof_now()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// per-game event times (globaltimer, ns): [0] final results written, [1] parked as stalled, [2] handed to the team
+// kernel, [3] migrated, [4] claimed by a stall-breaker group, [5] its stall was split; [6][0] = start of the one-warp kernel
+constexpr int kProfGames = 16384;
+__device__ unsigned long long g_game_ts[7][kProfGames];
+#define GAME_EVT(kind, index) (g_game_ts[kind][(index) & (kProfGames - 1)] = prof_now())
 #define GAMES_PROF_MIN(i) atomicMin(&g_games_prof[i], prof_now())
 #define GAMES_PROF_MAX(i) atomicMax(&g_games_prof[i], prof_now())
 #define GAMES_PROF_ADD(i, v) atomicAdd(&g_games_prof[i], (unsigned long long)(v))
@@ -62,6 +67,7 @@ __device__ __forceinline__ unsigned long long prof_now()
 #define GAMES_PROF_MIN(i)
 #define GAMES_PROF_MAX(i)
 #define GAMES_PROF_ADD(i, v)
+#define GAME_EVT(kind, index)
 #endif
 
 __device__ __forceinline__ void team_barrier(int id)
