@@ -659,16 +659,27 @@ constexpr int kMinSegCalls = 96;           // calls per range at least (ranges s
 constexpr int kWarpSegCalls = 8;           // calls per range at least (ranges searched by one warp, play_games_kernel)
 constexpr int kWarpSplitFirst = 64;        // calls the first split of a stall covers; every dry split doubles the stretch
 constexpr int kWarpSplitMax = 1024;        // ... up to this many (the one-warp kernel ends when its last record does)
+constexpr int kBulkStreak = 256;           // a stall this long is cut up to the move cap at once, into ranges of
+constexpr int kBulkSegCalls = 32;          // ... this many calls (at most kBulkMaxSegs ranges), searched only by
+constexpr int kBulkMaxSegs = 1023;         // warps / teams whose SM plays no game: bulk work must not slow the games
+constexpr unsigned int kVoidTask = 0xFFFFFFFFu;    // a queue slot that was handed out but holds no range
 struct SegResult { int32_t first_valid; uint32_t action; long long nodes; };
 struct StallRecord {
     GameState gs;                          // the game at the split; gs.moves = first call of range 0
     int32_t seg_len, segs;
     int32_t calls;                         // calls the record covers: [gs.moves, gs.moves + calls)
     int32_t done;                          // ranges finished
-    int32_t first_valid_seg;               // lowest range that found a valid call (kMaxSegs: none so far)
+    int32_t first_valid_seg;               // lowest range that found a valid call (kNoValidSeg: none so far)
+    SegResult *big;                        // results of a bulk record's ranges (more than kMaxSegs), else nullptr
     SegResult res[kMaxSegs];
 };
-enum PendingKind { kEntryStalled = 0, kEntryMigrated = 1, kEntrySegment = 2 };   // GameState::reserved of a pending entry
+constexpr int32_t kNoValidSeg = 1 << 20;
+__device__ __forceinline__ SegResult *results_of(StallRecord *rec)
+{
+    SegResult *big = reinterpret_cast<SegResult *>(__ldcg(reinterpret_cast<const unsigned long long *>(&rec->big)));
+    return big ? big : rec->res;
+}
+enum PendingKind { kEntryStalled = 0, kEntryMigrated = 1, kEntrySegment = 2, kEntryResumed = 3 };   // GameState::reserved of a pending entry
 
 // Device-side counters of one g2048_play_games call (per-launch scratch, zeroed before the kernels).
 struct GameCounters {
@@ -687,7 +698,10 @@ struct GameCounters {
     unsigned int in_stall;        // games of the one-warp kernel that are inside a split stall (not counted as alive
                                   // for the hand-over to the team kernel: they come back when their stall ends)
     unsigned int handover;        // the one-warp kernel has started handing its games to the team kernel (sticky)
-    unsigned int pad[2];
+    unsigned int bulk_tail;       // ranges pushed to / claimed from bulkq (long stalls: searched where no game is played)
+    unsigned int bulk_head;
+    unsigned int big_count;       // SegResult slots handed out of big_results
+    unsigned int pad[3];
 };
 
 struct GamesArgs {
@@ -702,8 +716,12 @@ struct GamesArgs {
     StallRecord *records;          // split stalls (nullptr: never split)
     unsigned int record_cap;
     unsigned int group_split_cap;  // splits the stall breaker may make (each puts up to kMaxSegs - 1 entries into pending[])
-    unsigned int *segq;            // ranges for the warps of play_games_kernel: (record << 5 | range) + 1, 0 = not written yet
+    unsigned int *segq;            // queued ranges of split stalls: (record << 10 | range) + 1, 0 = not written yet
     unsigned int segq_cap;
+    unsigned int *bulkq;           // ... of stalls that have lasted kBulkStreak calls already (most likely up to the move cap)
+    unsigned int bulkq_cap;
+    SegResult *big_results;        // result slots of bulk records
+    unsigned int big_cap;
     GameState *tail;               // live games handed to team_games_kernel once few are left (nullptr: never)
     unsigned int tail_threshold;   // ... i.e. once n - finished <= tail_threshold
 };
@@ -779,13 +797,36 @@ __device__ __forceinline__ T load_shared_record(const T *p)
     for (size_t i = 0; i < sizeof(T) / 8; ++i) dst[i] = __ldcg(src + i);
     return out;
 }
+// pending[] is a ring: ticket t lives in slot t % cap, and its flag holds the ticket's generation (t / cap + 1)
+// while the entry waits, 0 once it has been read.  A game is in one place at a time, so fewer than `cap` entries
+// are ever outstanding and a writer practically never waits for its slot.
 __device__ __forceinline__ void push_pending(const GamesArgs &a, const GameState &entry)
 {
-    const unsigned int slot = atomicAdd(&a.ctr->pending_count, 1u);
-    G2048_ASSERT(slot < a.pending_cap);
+    const unsigned int t = atomicAdd(&a.ctr->pending_count, 1u);
+    const unsigned int slot = t % a.pending_cap, gen = t / a.pending_cap + 1u;
+    volatile unsigned int *flag = &a.pending_ready[slot];
+    while (*flag != 0u) __nanosleep(100);                  // the slot's previous entry has been read
     a.pending[slot] = entry;
     __threadfence();                                       // the entry before its flag
-    *reinterpret_cast<volatile unsigned int *>(&a.pending_ready[slot]) = 1u;
+    *flag = gen;
+}
+// Claims the oldest waiting entry, if any.  One thread.
+__device__ __forceinline__ bool pop_pending(const GamesArgs &a, GameState &out)
+{
+    volatile GameCounters *c = a.ctr;
+    for (;;) {
+        const unsigned int h = c->finish_work;
+        if (h >= c->pending_count) return false;
+        if (atomicCAS(&a.ctr->finish_work, h, h + 1u) != h) continue;
+        const unsigned int slot = h % a.pending_cap, gen = h / a.pending_cap + 1u;
+        volatile unsigned int *flag = &a.pending_ready[slot];
+        while (*flag != gen) __nanosleep(200);
+        __threadfence();
+        out = load_shared_record(&a.pending[slot]);
+        __threadfence();
+        *flag = 0u;
+        return true;
+    }
 }
 enum RetireTo { kRetirePending = 0, kRetireTail = 1, kRetireMigrate = 2 };
 __device__ __forceinline__ void retire_game(const GamesArgs &a, GameState &gs, bool done, int to)
@@ -834,6 +875,93 @@ __device__ __forceinline__ bool handover_started(const GamesArgs &a)
 // or a lower range has found one; the warp that finishes the LAST range of a record puts the game
 // together again (same arithmetic as the stall breaker's run_segment) and plays on with it.
 // The loop makes ONE search per iteration whatever the warp is doing, so the search is inlined once.
+// ---- stalls cut into ranges searched by single warps (both games kernels) --------------------------------------
+// Cuts the next calls of the stalled game `gs` (its env already stored in it) into ranges and queues ranges
+// first_pushed .. segs-1 (the caller searches the ones below itself).  One thread.  Returns the record index,
+// or a.record_cap when no record is left.  A stall that has lasted kBulkStreak calls is cut up to the move cap
+// and goes to the bulk queue (all its ranges: first_pushed is ignored, *bulk = true).
+__device__ __forceinline__ unsigned int split_stall(const GamesArgs &a, const GameState &gs, int first_pushed, bool *bulk)
+{
+    const int rem = a.max_moves - gs.moves;
+    *bulk = false;
+    int calls = min(rem, min(kWarpSplitMax, max(kWarpSplitFirst, gs.streak)));
+    int seg_len = max(kWarpSegCalls, (calls + kMaxSegs - 1) / kMaxSegs);
+    int segs = (calls + seg_len - 1) / seg_len;                  // no range is empty
+    SegResult *big = nullptr;
+    unsigned int qslot = 0u;
+    if (a.bulkq && gs.streak >= kBulkStreak && rem > kWarpSplitMax) {
+        const int blen = max(kBulkSegCalls, (rem + kBulkMaxSegs - 1) / kBulkMaxSegs);
+        const int bsegs = (rem + blen - 1) / blen;
+        const unsigned int off = atomicAdd(&a.ctr->big_count, (unsigned int)bsegs);
+        if (off + (unsigned int)bsegs <= a.big_cap) {
+            qslot = atomicAdd(&a.ctr->bulk_tail, (unsigned int)bsegs);
+            if (qslot + (unsigned int)bsegs <= a.bulkq_cap) {
+                big = a.big_results + off;
+                calls = rem; seg_len = blen; segs = bsegs; first_pushed = 0;
+                *bulk = true;
+            } else {                                             // queue full: mark the slots it handed out as void
+                for (unsigned int k = qslot; k < a.bulkq_cap; ++k)
+                    *reinterpret_cast<volatile unsigned int *>(&a.bulkq[k]) = kVoidTask;
+            }
+        }
+    }
+    const unsigned int idx = atomicAdd(&a.ctr->record_count, 1u);
+    if (idx >= a.record_cap) {
+        G2048_ASSERT(!big);                                      // sized so that records outlast the bulk slots
+        return a.record_cap;
+    }
+    StallRecord *r = &a.records[idx];
+    r->gs = gs;
+    r->segs = segs;
+    r->seg_len = seg_len;
+    r->calls = calls;
+    r->done = 0;
+    r->first_valid_seg = kNoValidSeg;
+    r->big = big;
+    GAME_EVT(5, gs.index);
+    __threadfence();
+    if (big) {
+        for (int k = 0; k < segs; ++k)
+            *reinterpret_cast<volatile unsigned int *>(&a.bulkq[qslot + (unsigned int)k]) = ((idx << 10) | (unsigned int)k) + 1u;
+    } else if (segs > first_pushed) {
+        const unsigned int count = (unsigned int)(segs - first_pushed);
+        const unsigned int slot = atomicAdd(&a.ctr->seg_tail, count);
+        G2048_ASSERT(slot + count <= a.segq_cap);
+        for (int k = first_pushed; k < segs; ++k)
+            *reinterpret_cast<volatile unsigned int *>(&a.segq[slot + (unsigned int)(k - first_pushed)]) = ((idx << 10) | (unsigned int)k) + 1u;
+    }
+    return idx;
+}
+// Claims a queued range: (record << 10 | range) + 1, or 0 when there is none.  One thread.
+__device__ __forceinline__ unsigned int pop_queue(unsigned int *head_ptr, const unsigned int *tail_ptr, const unsigned int *q, unsigned int cap)
+{
+    volatile unsigned int *head = head_ptr;
+    const volatile unsigned int *tail = tail_ptr;
+    for (;;) {
+        const unsigned int h = *head;
+        if (h >= *tail || h >= cap) return 0u;
+        if (atomicCAS(head_ptr, h, h + 1u) != h) continue;
+        unsigned int task;
+        while ((task = *reinterpret_cast<const volatile unsigned int *>(&q[h])) == 0u) __nanosleep(100);
+        if (task == kVoidTask) continue;
+        __threadfence();
+        return task;
+    }
+}
+// urgent ranges first; bulk ranges only for a caller whose SM plays no game
+__device__ __forceinline__ unsigned int pop_range(const GamesArgs &a, bool bulk_ok)
+{
+    unsigned int task = pop_queue(&a.ctr->seg_head, &a.ctr->seg_tail, a.segq, a.segq_cap);
+    if (!task && bulk_ok && a.bulkq) task = pop_queue(&a.ctr->bulk_head, &a.ctr->bulk_tail, a.bulkq, a.bulkq_cap);
+    return task;
+}
+__device__ __forceinline__ bool ranges_waiting(const GamesArgs &a, bool bulk_ok)
+{
+    const volatile GameCounters *c = a.ctr;
+    if (c->seg_head < c->seg_tail) return true;
+    return bulk_ok && a.bulkq && c->bulk_head < c->bulk_tail && c->bulk_head < a.bulkq_cap;
+}
+
 // What a warp of play_games_kernel knows about its game / range, in shared memory: it is touched once per move
 // (by lane 0), while the search between two moves wants every register.
 struct WarpGame {
@@ -855,6 +983,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
     GameState &gs = wg.gs;
     const uint32_t lane = threadIdx.x & 31u;
     const bool can_split = a.pending && a.records && a.segq;
+    const bool bulk_ok = a.tail == nullptr;                // bulk ranges wait for the team kernel, if one follows
 #ifdef G2048_TEAM_PROFILE
     if (threadIdx.x == 0) atomicMin(&g_game_ts[6][0], prof_now());
 #endif
@@ -903,7 +1032,8 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         const int segs = __ldcg(&rec->segs);
         if (lane == 0) {
             const int seg = wg.seg;
-            rec->res[seg].first_valid = found; rec->res[seg].action = action; rec->res[seg].nodes = wg.seg_nodes;
+            SegResult *out = results_of(rec) + seg;
+            out->first_valid = found; out->action = action; out->nodes = wg.seg_nodes;
             if (found >= 0) atomicMin(&rec->first_valid_seg, seg);
             __threadfence();
             last = atomicAdd(&rec->done, 1) + 1 == segs;
@@ -913,7 +1043,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         if (!last) return;
         __threadfence();
         const int f = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg);
-        const volatile SegResult *res = rec->res;
+        const volatile SegResult *res = results_of(rec);
         const int seg_len = __ldcg(&rec->seg_len), calls = __ldcg(&rec->calls);
         state = kPlaying;
         done = false;
@@ -941,20 +1071,9 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
         if (state == kNeedWork) {
             if (can_split) {                               // a range of somebody's stall comes first
                 unsigned int task = 0u;
-                if (lane == 0) {
-                    volatile unsigned int *head = &a.ctr->seg_head, *tail = &a.ctr->seg_tail;
-                    for (;;) {
-                        const unsigned int h = *head;
-                        if (h >= *tail) break;
-                        if (atomicCAS(&a.ctr->seg_head, h, h + 1u) != h) continue;
-                        G2048_ASSERT(h < a.segq_cap);
-                        while ((task = *reinterpret_cast<volatile unsigned int *>(&a.segq[h])) == 0u) __nanosleep(100);
-                        __threadfence();
-                        break;
-                    }
-                }
+                if (lane == 0) task = pop_range(a, bulk_ok);
                 task = __shfl_sync(FULL, task, 0);
-                if (task) begin_range(&a.records[(task - 1u) >> 5], (int)((task - 1u) & 31u));
+                if (task) begin_range(&a.records[(task - 1u) >> 10], (int)((task - 1u) & 1023u));
             }
             if (state == kNeedWork && !queue_dry) {
                 unsigned int g = 0;
@@ -976,7 +1095,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
                 unsigned int over = 0u;
                 if (lane == 0) {
                     const volatile GameCounters *c = a.ctr;
-                    over = (a.tail ? handover_started(a) : c->finished >= (unsigned int)a.n) && c->seg_head >= c->seg_tail;
+                    over = (a.tail ? handover_started(a) : c->finished >= (unsigned int)a.n) && !ranges_waiting(a, bulk_ok);
                     if (!over) __nanosleep(2000);
                 }
                 if (__shfl_sync(FULL, over, 0)) break;
@@ -994,36 +1113,22 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
             }
             if (!leave && a.pending && streak >= kStallStreak) {
                 // split the next stretch of calls into ranges
-                unsigned int idx = a.record_cap;
+                unsigned int idx = a.record_cap, bulk = 0u;
                 if (can_split && lane == 0) {
-                    const int rem = a.max_moves - moves;
-                    const int calls = min(rem, min(kWarpSplitMax, max(kWarpSplitFirst, streak)));
-                    const int seg_len = max(kWarpSegCalls, (calls + kMaxSegs - 1) / kMaxSegs);
-                    const int segs = (calls + seg_len - 1) / seg_len;            // no range is empty
-                    idx = atomicAdd(&a.ctr->record_count, 1u);
-                    if (idx < a.record_cap) {
-                        StallRecord *r = &a.records[idx];
-                        store_env(gs, s);
-                        if (!gs.reserved) { gs.reserved = 1; atomicAdd(&a.ctr->in_stall, 1u); }    // counted until the stall ends
-                        r->gs = gs;
-                        r->segs = segs;
-                        r->seg_len = seg_len;
-                        r->calls = calls;
-                        r->done = 0;
-                        r->first_valid_seg = kMaxSegs;
-                        GAME_EVT(5, gs.index);
-                        __threadfence();
-                        if (segs > 1) {
-                            const unsigned int slot = atomicAdd(&a.ctr->seg_tail, (unsigned int)(segs - 1));
-                            G2048_ASSERT(slot + (unsigned int)(segs - 1) <= a.segq_cap);
-                            for (int k = 1; k < segs; ++k)
-                                *reinterpret_cast<volatile unsigned int *>(&a.segq[slot + (unsigned int)(k - 1)]) = ((idx << 5) | (unsigned int)k) + 1u;
-                        }
-                    }
+                    store_env(gs, s);
+                    const bool counted = gs.reserved != 0;
+                    bool b = false;
+                    gs.reserved = 1;
+                    idx = split_stall(a, gs, 1, &b);
+                    bulk = b;
+                    if (idx >= a.record_cap) gs.reserved = counted ? 1 : 0;
+                    else if (!counted) atomicAdd(&a.ctr->in_stall, 1u);        // counted until the stall ends
                 }
                 idx = __shfl_sync(FULL, idx, 0);
-                if (idx < a.record_cap) begin_range(&a.records[idx], 0);
-                else leave = true;                         // no record left: park the game for the stall breaker
+                bulk = __shfl_sync(FULL, bulk, 0);
+                if (idx >= a.record_cap) leave = true;     // no record left: park the game for the stall breaker
+                else if (bulk) { state = kNeedWork; continue; }                // all of it is queued: the game comes back later
+                else begin_range(&a.records[idx], 0);
             }
             if (leave) {
                 if (lane == 0) {
@@ -1108,6 +1213,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
     static_assert(kSpecGroups * kSpecWarps == kBeamWarps && kSpecWarps % kTeamWarps == 0, "groups must tile the block");
     __shared__ SpecSlot slots[kSpecGroups][2][kSpecWarps];
     __shared__ unsigned int next_game[kSpecGroups];
+    __shared__ GameState taken[kSpecGroups];               // the entry the leader claimed from pending[]
     __shared__ int note[kSpecGroups][2];                   // leader -> group: cancel flag of a round / split record / finaliser
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
@@ -1151,7 +1257,8 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
             if (cancelled) { found = -1; break; }
         }
         if (leader) {
-            rec->res[seg].first_valid = found; rec->res[seg].action = action; rec->res[seg].nodes = nodes;
+            SegResult *out = results_of(rec) + seg;
+            out->first_valid = found; out->action = action; out->nodes = nodes;
             if (found >= 0) atomicMin(&rec->first_valid_seg, seg);
             __threadfence();
             note[group][buf] = atomicAdd(&rec->done, 1) + 1 == segs;
@@ -1162,7 +1269,7 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         if (!last) return false;
         __threadfence();
         const int f = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg);
-        const volatile SegResult *res = rec->res;
+        const volatile SegResult *res = results_of(rec);
         if (f >= segs) {                                   // no valid call up to the move cap
             for (int k = 0; k < segs; ++k) gs.nodes += res[k].nodes;
             gs.invalid += a.max_moves - gs.moves;
@@ -1183,21 +1290,17 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
 
     for (;;) {
         if (leader) {
-            volatile unsigned int *head = &a.ctr->finish_work, *avail = &a.ctr->pending_count, *written = &a.ctr->written;
+            volatile unsigned int *written = &a.ctr->written;
             unsigned int got = kNone;
             bool counted_idle = false;                     // this group is in ctr->idle_groups
             for (;;) {
-                const unsigned int h = *head;
-                if (h < *avail) {
-                    if (atomicCAS(&a.ctr->finish_work, h, h + 1u) != h) continue;
-                    while (*reinterpret_cast<volatile unsigned int *>(&a.pending_ready[h]) == 0u) __nanosleep(200);
-                    __threadfence();
+                if (pop_pending(a, taken[group])) {
                     // a migrated game's pusher took one idle group off the count for it; keep the count
                     // right whoever ends up with the entry
-                    const bool reserved = reinterpret_cast<volatile GameState *>(&a.pending[h])->reserved == kEntryMigrated;
+                    const bool reserved = taken[group].reserved == kEntryMigrated;
                     if (counted_idle && !reserved) atomicSub(&a.ctr->idle_groups, 1);
                     if (!counted_idle && reserved) atomicAdd(&a.ctr->idle_groups, 1);
-                    got = h;
+                    got = 0u;
                     break;
                 }
                 if (*written >= (unsigned int)a.n) break;
@@ -1210,7 +1313,8 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         const unsigned int p = next_game[group];
         group_barrier();                                   // everyone has read it before the next round rewrites it
         if (p == kNone) break;
-        GameState gs = load_shared_record(&a.pending[p]);  // every warp of the group keeps an identical copy
+        GameState gs = taken[group];                       // every warp of the group keeps an identical copy
+        group_barrier();                                   // ... before the leader claims the next entry
         EnvState s;
         bool done = false;
         if (gs.reserved == kEntrySegment) {                // a range of a split stall: gs.score = record, gs.moves = range
@@ -1241,7 +1345,8 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                         rec->segs = segs;
                         rec->seg_len = (rem + segs - 1) / segs;
                         rec->done = 0;
-                        rec->first_valid_seg = kMaxSegs;
+                        rec->first_valid_seg = kNoValidSeg;
+                        rec->big = nullptr;
                         GAME_EVT(5, gs.index);
                         __threadfence();
                         GameState entry = gs;
@@ -1311,80 +1416,258 @@ __global__ void __launch_bounds__(kBeamThreads, 1) finish_games_kernel(GamesArgs
     break_stalls<kSpecWarps>(a, smem, reinterpret_cast<const uint16_t *>(smem));
 }
 
-// Whole games, latency form: one TEAM of four warps plays one game (beam_search_team).  Games come
-// from `in` (hand-overs of play_games_kernel, ctr->tail_count of them) or, with in == nullptr, are
-// the fresh games 0..n-1.  A block whose six teams have run
-// out of games turns into a stall breaker (break_stalls) until every game of the call is final: the
-// stalls are broken on the SMs the finished games leave, while the long games are still being played.
-// Always launched with kBeamThreads threads on every SM.
-template <int kSpecWarps>
+// Whole games, latency form: one TEAM of four warps plays one game (beam_search_team).  Games come from
+// `in` (hand-overs of play_games_kernel, ctr->tail_count of them) or, with in == nullptr, are the fresh
+// games 0..n-1, and later from pending[] (games that resume after a stall, games that migrate).
+// Always launched with kBeamThreads threads on every SM; every team stays until every game of the call
+// is final, because a team without a game is what breaks stalls:
+//   * a team whose game has made kStallStreak invalid moves in a row cuts the game's next calls into ranges
+//     (split_stall) and queues them; it is then free for other work;
+//   * a free team first looks for a game in pending[] (a game coming back from a stall is most likely on
+//     the critical path), then for a fresh game, then each of its four warps takes ONE queued range and
+//     searches it with the one-warp search -- so whatever part of the GPU is not playing searches ranges,
+//     from the first stall on, and a resumed game waits for the end of one range at most;
+//   * the warp that finishes the last range of a record puts the game together: it goes to pending[] when
+//     the stall ended in a valid move, is cut again (twice the stretch) when the stretch held none.
+// Once the queue of fresh games is dry, SMs that still hold several games run them slower (six teams share
+// four schedulers; three run at full speed) than an SM holding few: a team that is one of more than three
+// playing on its SM checks every fourth move for teams that wait on an emptier SM and sends its game there.
+struct TeamJob {
+    GameState gs;                  // the game a team is about to play (leader -> team)
+    int32_t kind;
+};
+enum { kJobExit = 0, kJobGame = 1, kJobRanges = 2 };
+
 __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a, const GameState *in)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kTeams = kBeamWarps / kTeamWarps;
+    __shared__ TeamJob jobs[kTeams];
+    __shared__ WarpGame ranges[kBeamWarps];
+    __shared__ int active_teams;                           // teams of this block that are playing a game
     stage_row_table(smem, a.row);
     const uint16_t *row = reinterpret_cast<const uint16_t *>(smem);
-    const int quad = threadIdx.x >> 7;
-    TeamScratch &ts = team_scratch(smem, quad);
+    const int warp = threadIdx.x >> 5, quad = warp >> 2;
+    const uint32_t lane = threadIdx.x & 31u;
+    TeamScratch &ts = team_scratch(smem, quad);            // overlays the four WarpScratch the range searches use
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
+    TeamJob &job = jobs[quad];
+    WarpGame &wg = ranges[warp];
     const int bar = 1 + quad;
     const bool leader = (threadIdx.x & (kTeamThreads - 1)) == 0;
+    const bool can_split = a.pending && a.records && a.segq;
     const unsigned int total = in ? a.ctr->tail_count : (unsigned int)a.n;
-    __shared__ int active_teams;                           // teams of this block that are playing a game
     if (threadIdx.x == 0) active_teams = 0;
     __syncthreads();
-    // Every game comes from the queue, so whichever blocks are resident can play all of them (a block
-    // that is not scheduled yet holds nothing back, and the blocks that wait in break_stalls below
-    // wait only for work that resident blocks do).  Team q of a block asks a little later than team
-    // q - 1: when there are fewer games than teams, they spread over all SMs instead of filling a few.
     if (threadIdx.x == 0) GAMES_PROF_MIN(0);
+    // Team q of a block asks a little later than team q - 1: when there are fewer games than teams, they
+    // spread over all SMs instead of filling a few.
     if (leader) __nanosleep(4000u * (unsigned int)quad);
+    // ctr->idle_groups = room for full-speed games: the sum over all blocks of max(0, 3 - games played on the block),
+    // kept exact by the transitions of every block's `active_teams` (a migrating game reserves its place beforehand).
+    if (threadIdx.x == 0) atomicAdd(&a.ctr->idle_groups, 3);
+    // A team takes a game that waits in pending[] at once when its block plays fewer than three (room for a full-speed
+    // game), otherwise only after a while; bulk ranges are searched by the teams of blocks that play no game.
+    // (A/B knobs, measured within noise of each other on cfg 5: which teams of a block take games from pending[],
+    // and which search bulk ranges while the block plays no game)
+#ifndef G2048_RECEIVERS
+#define G2048_RECEIVERS 6
+#endif
+#ifndef G2048_BULK_TEAMS_FROM
+#define G2048_BULK_TEAMS_FROM 0
+#endif
+    const bool receiver = quad < G2048_RECEIVERS;
+    const bool bulk_team = quad >= G2048_BULK_TEAMS_FROM;
+    bool queue_dry = false;                                // leader only
+
     for (;;) {
-        if (leader) ts.next_item = atomicAdd(&a.ctr->team_work, 1u);
-        team_barrier(bar);
-        const unsigned int p = ts.next_item;
-        team_barrier(bar);                                 // everyone has read it before the next round rewrites it
-        if (p >= total) { if (leader) GAMES_PROF_MIN(1); break; }
-        G2048_ASSERT(!in || p < (unsigned int)a.n);
-        EnvState s;
-        GameState gs;
-        if (in) { gs = in[p]; load_env(gs, s); }
-        else start_game(gs, s, a.P.K, a.game0 + p, p);
-        const uint32_t game = a.game0 + gs.index;
-        bool done = false, migrate = false;
-        if (leader) atomicAdd(&active_teams, 1);
-        while (!done && gs.moves < a.max_moves && !(a.pending && gs.streak >= kStallStreak)) {
-            // Once the queue is dry, SMs that still hold several games run them slower (six teams share four
-            // schedulers) than an SM holding one; blocks that have turned stall breaker and found nothing
-            // to do count themselves in idle_groups.  Every fourth move the team checks: a game that shares
-            // its SM moves to such a group (which plays it with a team of its own, break_stalls).
-            if (a.pending && (gs.moves & 3) == 3) {
-                if (leader) {
-                    unsigned int go = 0u;
-                    if (*reinterpret_cast<volatile int *>(&active_teams) > 1 &&
-                        *reinterpret_cast<volatile unsigned int *>(&a.ctr->team_work) >= total &&
-                        *reinterpret_cast<volatile int *>(&a.ctr->idle_groups) > 0) {
-                        if (atomicSub(&a.ctr->idle_groups, 1) > 0) go = 1u;            // reserved one idle group
-                        else atomicAdd(&a.ctr->idle_groups, 1);
-                    }
-                    ts.next_item = go;
-                }
-                team_barrier(bar);
-                migrate = ts.next_item != 0u;
-                team_barrier(bar);
-                if (migrate) break;
-            }
-            const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
-            done = play_move(gs, s, r, a, row, game);
-        }
-        store_env(gs, s);
+        // ---- the leader finds the team's next job -------------------------------------------------------------
         if (leader) {
-            atomicSub(&active_teams, 1);
-            retire_game(a, gs, done, migrate ? kRetireMigrate : kRetirePending);
-            GAMES_PROF_MAX(2);
+            volatile GameCounters *c = a.ctr;
+            int kind = -1;
+            bool deferred = false, reserved = false;
+            while (kind < 0) {
+                if (a.pending && c->finish_work < c->pending_count) {           // 1. a game that waits in pending[]
+                    // ... goes to a receiver on a block with room; anybody else waits a while first (then nobody with room is free)
+                    if (!(receiver && *reinterpret_cast<volatile int *>(&active_teams) < 3) && !deferred) {
+                        deferred = true;
+                        __nanosleep(50000);
+                        continue;
+                    }
+                    if (pop_pending(a, job.gs)) {
+                        G2048_ASSERT(job.gs.reserved != kEntrySegment);
+                        reserved = job.gs.reserved == kEntryMigrated;          // its pusher took the room it needs off the count
+                        GAME_EVT(4, job.gs.index);
+                        kind = kJobGame;
+                        break;
+                    }
+                }
+                if (!queue_dry) {                                              // 2. a fresh (or handed-over) game
+                    const unsigned int p = atomicAdd(&a.ctr->team_work, 1u);
+                    if (p < total) {
+                        G2048_ASSERT(!in || p < (unsigned int)a.n);
+                        if (in) job.gs = in[p];
+                        else {
+                            EnvState s0;
+                            start_game(job.gs, s0, a.P.K, a.game0 + p, p);
+                            store_env(job.gs, s0);
+                        }
+                        kind = kJobGame;
+                        break;
+                    }
+                    queue_dry = true;
+                    GAMES_PROF_MIN(1);
+                }
+                if (can_split && ranges_waiting(a, bulk_team && *reinterpret_cast<volatile int *>(&active_teams) == 0)) {   // 3. ranges of split stalls
+                    kind = kJobRanges;
+                    break;
+                }
+                if (c->written >= (unsigned int)a.n) { kind = kJobExit; break; }               // 4. every game is final
+                __nanosleep(1000);
+            }
+            if (kind == kJobGame) {
+                const bool uses_room = atomicAdd(&active_teams, 1) < 3;
+                if (reserved && !uses_room) atomicAdd(&a.ctr->idle_groups, 1);                 // the reservation goes back
+                if (!reserved && uses_room) atomicSub(&a.ctr->idle_groups, 1);
+            }
+            job.kind = kind;
         }
+        team_barrier(bar);
+        const int kind = job.kind;
+        if (kind == kJobExit) break;
+
+        if (kind == kJobGame) {
+            GameState gs = job.gs;                         // every thread of the team keeps an identical copy
+            EnvState s;
+            load_env(gs, s);
+            const uint32_t game = a.game0 + gs.index;
+            bool done = false, migrate = false, split = false, may_split = can_split;
+            team_barrier(bar);                             // everyone has its copy before the leader reuses `job`
+            while (!done && gs.moves < a.max_moves) {
+                if (a.pending && gs.streak >= kStallStreak && may_split) {
+                    // the agent keeps choosing an invalid move: cut the next calls into ranges for every free warp
+                    if (leader) {
+                        store_env(gs, s);
+                        gs.reserved = 0;
+                        bool bulk;
+                        ts.next_item = split_stall(a, gs, 0, &bulk);
+                    }
+                    team_barrier(bar);
+                    split = ts.next_item < a.record_cap;
+                    team_barrier(bar);
+                    if (split) break;
+                    may_split = false;                     // no record left: play through the stall
+                }
+                // every fourth move: does the game share a crowded SM while a team waits on an emptier one?
+#ifndef G2048_NO_MIGRATE
+                if (a.pending && (gs.moves & 3) == 3) {
+                    if (leader) {
+                        unsigned int go = 0u;
+                        if (*reinterpret_cast<volatile int *>(&active_teams) > 3 &&
+                            *reinterpret_cast<volatile unsigned int *>(&a.ctr->team_work) >= total &&
+                            *reinterpret_cast<volatile int *>(&a.ctr->idle_groups) > 0) {
+                            if (atomicSub(&a.ctr->idle_groups, 1) > 0) go = 1u;            // reserved room on an emptier block
+                            else atomicAdd(&a.ctr->idle_groups, 1);
+                        }
+                        ts.next_item = go;
+                    }
+                    team_barrier(bar);
+                    migrate = ts.next_item != 0u;
+                    team_barrier(bar);
+                    if (migrate) break;
+                }
+#endif
+                const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
+                done = play_move(gs, s, r, a, row, game);
+            }
+            if (leader) {
+                if (atomicSub(&active_teams, 1) <= 3) atomicAdd(&a.ctr->idle_groups, 1);       // room for a full-speed game again
+                if (!split) {                              // finished (written) or migrating (to pending[])
+                    store_env(gs, s);
+                    retire_game(a, gs, done, kRetireMigrate);
+                    GAMES_PROF_MAX(2);
+                }
+            }
+            team_barrier(bar);
+            continue;
+        }
+
+        // ---- kJobRanges: every warp of the team takes one queued range ------------------------------------------
+        unsigned int task = 0u;
+        if (lane == 0) task = pop_range(a, bulk_team && *reinterpret_cast<volatile int *>(&active_teams) == 0);
+        task = __shfl_sync(FULL, task, 0);
+        if (task) {
+            StallRecord *rec = &a.records[(task - 1u) >> 10];
+            const int seg = (int)((task - 1u) & 1023u);
+            GameState &gs = wg.gs;
+            if (lane == 0) gs = load_shared_record(&rec->gs);
+            __syncwarp();
+            EnvState s;
+            load_env(gs, s);
+            const uint32_t game = a.game0 + gs.index;
+            const uint32_t legal = env_legal_mask(s.board);
+            const int seg_len = __ldcg(&rec->seg_len), calls = __ldcg(&rec->calls), segs = __ldcg(&rec->segs);
+            const int first = gs.moves;
+            const int lo = first + seg * seg_len, hi = min(lo + seg_len, first + calls);
+            long long nodes = 0;
+            int found = -1;
+            uint32_t action = 0u;
+            for (int m = lo; m < hi; ++m) {
+                const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)m, row, ws);
+                nodes += r.nodes;
+                if ((legal >> r.action) & 1u) { found = m - lo; action = r.action; break; }
+                unsigned int cancelled = 0u;               // a lower range ended the stall
+                if (lane == 0) cancelled = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg) < seg;
+                if (__shfl_sync(FULL, cancelled, 0)) break;
+            }
+            unsigned int last = 0u;
+            if (lane == 0) {
+                SegResult *out = results_of(rec) + seg;
+            out->first_valid = found; out->action = action; out->nodes = nodes;
+                if (found >= 0) atomicMin(&rec->first_valid_seg, seg);
+                __threadfence();
+                last = atomicAdd(&rec->done, 1) + 1 == segs;
+            }
+            last = __shfl_sync(FULL, last, 0);
+            if (last) {                                    // this warp puts the game together again
+                __threadfence();
+                const int f = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg);
+                const volatile SegResult *res = results_of(rec);
+                bool done = false;
+                if (f >= segs) {                           // no valid call in this stretch: all of it was invalid moves
+                    if (lane == 0) {
+                        for (int k = 0; k < segs; ++k) gs.nodes += res[k].nodes;
+                        gs.invalid += calls; gs.moves += calls; gs.streak += calls;
+                    }
+                } else {
+                    const int before = f * seg_len + res[f].first_valid;      // invalid moves: nothing else changes (env:188-192)
+                    if (lane == 0) {
+                        for (int k = 0; k <= f; ++k) gs.nodes += res[k].nodes;
+                        gs.invalid += before;
+                        gs.moves += before;
+                    }
+                    __syncwarp();
+                    GameState g2 = gs;
+                    BeamResult r;
+                    r.action = res[f].action;
+                    r.nodes = 0;
+                    done = play_move(g2, s, r, a, row, game);
+                    store_env(g2, s);
+                    if (lane == 0) gs = g2;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    bool bulk_unused;
+                    gs.reserved = 0;
+                    if (done || gs.moves >= a.max_moves) retire_game(a, gs, done, kRetirePending);       // written
+                    else if (f >= segs && split_stall(a, gs, 0, &bulk_unused) < a.record_cap) { }       // still stalled: cut again
+                    else { gs.reserved = kEntryResumed; push_pending(a, gs); GAME_EVT(3, gs.index); }   // plays on with a team
+                }
+                __syncwarp();
+            }
+        }
+        team_barrier(bar);
     }
-    __syncthreads();                                       // all six teams of the block are out of games
-    if (threadIdx.x == 0) { GAMES_PROF_MIN(3); GAMES_PROF_MAX(4); }
-    break_stalls<kSpecWarps>(a, smem, row);
     if (threadIdx.x == 0) GAMES_PROF_MAX(5);
 }
 
@@ -1441,8 +1724,7 @@ static int ensure_attrs()
         G2048_CUDA(cudaFuncSetAttribute(beam_search_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(play_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
-        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
-        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
+        G2048_CUDA(cudaFuncSetAttribute(team_games_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         G2048_CUDA(cudaFuncSetAttribute(finish_games_kernel<kBeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBeamSmemBytes));
         g_attr_done[dev] = 1;
@@ -1528,16 +1810,21 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     // scratch: counters | ready flags of the pending entries | range queue of the one-warp kernel | pending entries
     // (stalled / migrated games, ranges of stalls the stall breaker split) | split-stall records | games for the
     // team kernel.  Everything before the pending entries is zeroed.
-    const bool warp_phase = !wide && !direct;
     const size_t group_split_cap = wide ? 0 : (size_t)(n / 8 > 8 ? n / 8 : 8);
-    const size_t record_cap = wide ? 0 : group_split_cap + (warp_phase ? 2 * (size_t)n + 64 : 0);
+    const size_t record_cap = wide ? 0 : group_split_cap + 2 * (size_t)n + 64;
     const size_t pending_cap = wide ? 0 : (size_t)n + (kMaxSegs - 1) * group_split_cap;
-    const size_t segq_cap = warp_phase ? (kMaxSegs - 1) * (2 * (size_t)n + 64) : 0;
+    const size_t segq_cap = wide ? 0 : kMaxSegs * (2 * (size_t)n + 64);
+    // bulk records (stalls that run to the move cap, ~5 % of the games): n / 8 + 16 of them, cut into ranges of 32 calls
+    const size_t bulk_segs = (size_t)((max_moves + kBulkSegCalls - 1) / kBulkSegCalls < kBulkMaxSegs
+                                          ? (max_moves + kBulkSegCalls - 1) / kBulkSegCalls : kBulkMaxSegs);
+    const size_t bulkq_cap = wide ? 0 : ((size_t)n / 8 + 16) * (bulk_segs > 0 ? bulk_segs : 1);
     auto round256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t flags_off = 256, segq_off = flags_off + round256(pending_cap * sizeof(unsigned int));
-    const size_t pending_off = segq_off + round256(segq_cap * sizeof(unsigned int));
+    const size_t bulkq_off = segq_off + round256(segq_cap * sizeof(unsigned int));
+    const size_t pending_off = bulkq_off + round256(bulkq_cap * sizeof(unsigned int));
     const size_t records_off = pending_off + round256(pending_cap * sizeof(GameState));
-    const size_t tail_off = records_off + round256(record_cap * sizeof(StallRecord));
+    const size_t big_off = records_off + round256(record_cap * sizeof(StallRecord));
+    const size_t tail_off = big_off + round256(bulkq_cap * sizeof(SegResult));
     LaunchScratch scratch;
     rc = scratch.alloc(st, tail_off + (size_t)tail_cap * sizeof(GameState), pending_off, stream);
     if (rc != G2048_OK) return rc;
@@ -1551,6 +1838,8 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
                 split ? reinterpret_cast<StallRecord *>(base + records_off) : nullptr,
                 (unsigned int)record_cap, (unsigned int)group_split_cap,
                 split && segq_cap ? reinterpret_cast<unsigned int *>(base + segq_off) : nullptr, (unsigned int)segq_cap,
+                split && bulkq_cap ? reinterpret_cast<unsigned int *>(base + bulkq_off) : nullptr, (unsigned int)bulkq_cap,
+                reinterpret_cast<SegResult *>(base + big_off), (unsigned int)bulkq_cap,
                 tail_cap ? reinterpret_cast<GameState *>(base + tail_off) : nullptr, (unsigned int)tail_threshold};
     const int grid = (int)(n < st->sm_count ? n : st->sm_count);    // spread small runs over all SMs (see beam search)
     if (wide) {                                                     // wide beams: compatibility path, no stall breaker
@@ -1564,8 +1853,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     // per round) each; beyond, three games per SM (8 calls per round each).
     const bool whole_sm = n <= 2048;
     if (direct) {
-        if (whole_sm) team_games_kernel<kBeamWarps><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, nullptr);
-        else          team_games_kernel<8><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, nullptr);
+        team_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, nullptr);
         count_launch();
         return check_cuda(cudaGetLastError(), "team_games_kernel");
     }
@@ -1573,8 +1861,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     count_launch();
     G2048_CUDA(cudaGetLastError());
     if (tail_cap) {                                                 // how many were handed over is only known on the device
-        if (whole_sm) team_games_kernel<kBeamWarps><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
-        else          team_games_kernel<8><<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
+        team_games_kernel<<<st->sm_count, kBeamThreads, kBeamSmemBytes, stream>>>(a, a.tail);
         count_launch();
         return check_cuda(cudaGetLastError(), "team_games_kernel");
     }
