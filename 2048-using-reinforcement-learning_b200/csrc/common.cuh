@@ -22,7 +22,11 @@ struct DeviceState {
     // free memory back to the driver at every synchronisation, so a host call that ends in a stream sync would
     // pay a fresh device allocation (~0.4 ms) on its next launch.
     cudaMemPool_t pool = nullptr;
+    // 512-entry pair table (board.cuh: pair_table_entry) followed by the 16 float32 observation values e / 15:
+    // the per-step kernel copies them into shared memory instead of computing them in every block
+    uint32_t *step_tables = nullptr;
 };
+constexpr int kStepTableWords = 512 + 16;
 
 // Returns the state of the current device, or nullptr (and sets the error) if g2048_init
 // has not been called for it.

@@ -72,6 +72,7 @@ struct StepArgs {
     double *reward; float *reward32; int32_t *score_delta; uint8_t *valid; uint8_t *legal; uint8_t *done;
     int64_t n; PhiloxKey K; uint32_t game0;
     const uint16_t *row; const uint8_t *code; unsigned long long *overflow;
+    const uint32_t *tables;        // DeviceState::step_tables
     int32_t *episodes;             // non-null: reset an env right after the step that ended its game
     // fused extras (all optional)
     float *obs;                    // float32[n][16] observation of the board the caller acts on next
@@ -100,13 +101,18 @@ __device__ __forceinline__ void env_reset_cold(EnvState &s, const PhiloxKey &K, 
 // game, the policy's observation (agents/ppo_agent.py:184-195) and the pre-reset state.
 // No 192 KiB tables: the move is table-free SWAR (kSwarMove) or reads the tables through L1/L2;
 // scores and tile sums come from a 2 KiB pair table built per block.
+constexpr int kStepMaxThreads = 1024;
 template <bool kSwarMove>
-__global__ void __launch_bounds__(kEnvThreads) env_step_fused_kernel(StepArgs a)
+__global__ void __launch_bounds__(kStepMaxThreads) env_step_fused_kernel(StepArgs a)
 {
-    __shared__ uint32_t pairs[kPairEntries];
-    __shared__ float obs_lut[16];
-    for (int i = threadIdx.x; i < kPairEntries; i += blockDim.x) pairs[i] = pair_table_entry(i);
-    if (threadIdx.x < 16) obs_lut[threadIdx.x] = (float)threadIdx.x / 15.0f;     // log2(tile) / 15.0 in float32
+    __shared__ __align__(16) uint32_t tables[kStepTableWords + 32];
+    // 528 words = 132 16-byte pieces: the block's first threads copy one each (constant tables, written once by
+    // g2048_init: reading them does not have to wait for the launch before this one)
+    static_assert(kStepTableWords % 4 == 0 && kStepTableWords / 4 <= 160, "copied by the first five warps at most");
+    for (int i = threadIdx.x; i < kStepTableWords / 4; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tables)[i] = __ldg(reinterpret_cast<const uint4 *>(a.tables) + i);
+    const uint32_t *pairs = tables;
+    const float *obs_lut = reinterpret_cast<const float *>(tables + kPairEntries);
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
@@ -663,6 +669,14 @@ int g2048_init(int device)
     G2048_CUDA(cudaMemcpy(st.code, code.data(), kCodeTableBytes, cudaMemcpyHostToDevice));
     G2048_CUDA(cudaMemset(st.overflow, 0, sizeof(unsigned long long)));
     G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
+    std::vector<uint32_t> step_tables(kStepTableWords);
+    for (int i = 0; i < kPairEntries; ++i) step_tables[i] = pair_table_entry((uint32_t)i);
+    for (int i = 0; i < 16; ++i) {
+        const float v = (float)i / 15.0f;                                  // log2(tile) / 15.0 in float32
+        memcpy(&step_tables[kPairEntries + i], &v, sizeof v);
+    }
+    G2048_CUDA(cudaMalloc(&st.step_tables, kStepTableWords * sizeof(uint32_t)));
+    G2048_CUDA(cudaMemcpy(st.step_tables, step_tables.data(), kStepTableWords * sizeof(uint32_t), cudaMemcpyHostToDevice));
     cudaMemPoolProps props = {};
     props.allocType = cudaMemAllocationTypePinned;
     props.handleTypes = cudaMemHandleTypeNone;
@@ -835,14 +849,23 @@ static int env_step_launch(StepArgs a, void *stream)
 {
     const int64_t n = a.n;
     G2048_ENTER(a.boards && a.actions);
-    a.row = st->row; a.code = st->code; a.overflow = st->overflow;
-    const int grid = grid_for(n, kEnvThreads, st->sm_count, 16);
+    a.row = st->row; a.code = st->code; a.overflow = st->overflow; a.tables = st->step_tables;
+    // One block per SM, sized to the batch: a step costs ~800 instructions per warp and a launch is as long as its
+    // busiest SM, so 65,536 envs run as 148 blocks of 14 warps (the 2,048 warps spread evenly: 256 blocks of 8
+    // warps would put 16 warps on most SMs and 8 on the others), and one copy of the tables per SM is enough.
+    // Batches beyond 16 warps per SM run as blocks of 8 warps, several per SM (measured at 1,048,576 envs: 38 us
+    // per step against 43 us with 1,024-thread blocks, whose tails leave SMs idle).
+    const int64_t warps = (n + 31) / 32;
+    int64_t per_block = (warps + st->sm_count - 1) / st->sm_count;
+    if (per_block > 16) per_block = 8;
+    const int threads = 32 * (int)per_block;
+    const int grid = (int)((warps + per_block - 1) / per_block);
     cudaError_t e;
     // table-free move: 15 % faster up to 65,536 envs (no dependent table round trip on a latency-bound launch);
     // at a million envs the launch is ALU-bound and the table reads are hidden: row tables win by 8 %
     const int tables = step_tuning(G2048_TUNE_STEP_TABLES);
-    if (tables == 1 || (tables < 0 && n >= (1 << 18))) e = launch_pdl(env_step_fused_kernel<false>, grid, kEnvThreads, s, a);
-    else                                     e = launch_pdl(env_step_fused_kernel<true>, grid, kEnvThreads, s, a);
+    if (tables == 1 || (tables < 0 && n >= (1 << 18))) e = launch_pdl(env_step_fused_kernel<false>, grid, threads, s, a);
+    else                                     e = launch_pdl(env_step_fused_kernel<true>, grid, threads, s, a);
     count_launch();
     return check_cuda(e, __func__);
 }
@@ -854,7 +877,7 @@ int g2048_env_step(uint64_t *boards, const uint8_t *actions, const uint32_t *spa
                    int64_t n, uint64_t seed, uint32_t game0, void *stream)
 {
     StepArgs a{boards, actions, spawn_inject, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, nullptr,
+               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, nullptr, nullptr,
                nullptr, nullptr, nullptr, nullptr};
     return env_step_launch(a, stream);
 }
@@ -867,7 +890,7 @@ int g2048_env_step_autoreset(uint64_t *boards, const uint8_t *actions,
 {
     if (!episodes || !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_autoreset: episodes and spawn_ctr are required");
     StepArgs a{boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, episodes,
+               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, nullptr, episodes,
                nullptr, nullptr, nullptr, nullptr};
     return env_step_launch(a, stream);
 }
@@ -881,7 +904,7 @@ int g2048_env_step_fused(uint64_t *boards, const uint8_t *actions,
 {
     if (episodes && !spawn_ctr) return set_error(G2048_EINVAL, "g2048_env_step_fused: auto-reset (episodes) needs spawn_ctr");
     StepArgs a{boards, actions, nullptr, score, highest_exp, spawn_ctr, reward, reward32, score_delta,
-               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, episodes,
+               valid, legal, done, n, make_philox_key(seed), game0, nullptr, nullptr, nullptr, nullptr, episodes,
                obs, stepped_boards, final_score, final_highest_exp};
     return env_step_launch(a, stream);
 }
