@@ -654,8 +654,6 @@ struct GameState {
 // board: an invalid move changes nothing).  The lowest range that holds a valid call decides where the stall
 // ends; ranges above it are cancelled.  The group that finishes the last range puts the game together again.
 constexpr int kMaxSegs = 32;
-constexpr int kSplitAfterRounds = 4;       // full-width rounds without a valid call before a stall is split
-constexpr int kMinSegCalls = 96;           // calls per range at least (ranges searched by a group of the stall breaker)
 constexpr int kWarpSegCalls = 8;           // calls per range at least (ranges searched by one warp, play_games_kernel)
 constexpr int kWarpSplitFirst = 64;        // calls the first split of a stall covers; every dry split doubles the stretch
 constexpr int kWarpSplitMax = 1024;        // ... up to this many (the one-warp kernel ends when its last record does)
@@ -679,7 +677,7 @@ __device__ __forceinline__ SegResult *results_of(StallRecord *rec)
     SegResult *big = reinterpret_cast<SegResult *>(__ldcg(reinterpret_cast<const unsigned long long *>(&rec->big)));
     return big ? big : rec->res;
 }
-enum PendingKind { kEntryStalled = 0, kEntryMigrated = 1, kEntrySegment = 2, kEntryResumed = 3 };   // GameState::reserved of a pending entry
+enum PendingKind { kEntryStalled = 0, kEntryMigrated = 1, kEntryResumed = 3 };   // GameState::reserved of a pending entry
 
 // Device-side counters of one g2048_play_games call (per-launch scratch, zeroed before the kernels).
 struct GameCounters {
@@ -692,7 +690,7 @@ struct GameCounters {
     unsigned int written;         // games whose results are final (the stall breaker leaves when this reaches n)
     int idle_groups;              // stall-breaker groups waiting for work that no migrating game has reserved yet
     unsigned int record_count;    // StallRecords handed out
-    unsigned int group_splits;    // ... of them by the stall breaker (its ranges travel through pending[])
+    unsigned int unused0;
     unsigned int seg_tail;        // ranges pushed to segq (one-warp kernel)
     unsigned int seg_head;        // ranges claimed from segq
     unsigned int in_stall;        // games of the one-warp kernel that are inside a split stall (not counted as alive
@@ -715,7 +713,6 @@ struct GamesArgs {
     unsigned int pending_cap;      // entries pending[] can hold (games + ranges of split stalls)
     StallRecord *records;          // split stalls (nullptr: never split)
     unsigned int record_cap;
-    unsigned int group_split_cap;  // splits the stall breaker may make (each puts up to kMaxSegs - 1 entries into pending[])
     unsigned int *segq;            // queued ranges of split stalls: (record << 10 | range) + 1, 0 = not written yet
     unsigned int segq_cap;
     unsigned int *bulkq;           // ... of stalls that have lasted kBulkStreak calls already (most likely up to the move cap)
@@ -1214,7 +1211,6 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
     __shared__ SpecSlot slots[kSpecGroups][2][kSpecWarps];
     __shared__ unsigned int next_game[kSpecGroups];
     __shared__ GameState taken[kSpecGroups];               // the entry the leader claimed from pending[]
-    __shared__ int note[kSpecGroups][2];                   // leader -> group: cancel flag of a round / split record / finaliser
     const int warp = threadIdx.x >> 5;
     WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem + kRowTableBytes)[warp];
     const uint32_t lane = threadIdx.x & 31u;
@@ -1225,68 +1221,6 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
     auto group_barrier = [&]() { asm volatile("barrier.sync %0, %1;" ::"r"(8 + group), "r"(kSpecWarps * 32) : "memory"); };
     constexpr unsigned int kNone = 0xFFFFFFFFu;
     int buf = 0;
-
-    // One range of a split stall (all threads of the group).  Returns true when this group finished the LAST
-    // range of the record and the stall ended in a valid move: then gs / s hold the game after that move and
-    // the caller plays on.  Otherwise the game is someone else's (or was written here, at the move cap).
-    auto run_segment = [&](StallRecord *rec, int seg, GameState &gs, EnvState &s, bool &done) -> bool {
-        gs = load_shared_record(&rec->gs);
-        load_env(gs, s);
-        const uint32_t game = a.game0 + gs.index;
-        const uint32_t legal = env_legal_mask(s.board);
-        const int seg_len = __ldcg(&rec->seg_len), segs = __ldcg(&rec->segs);
-        const int lo = gs.moves + seg * seg_len, hi = min(lo + seg_len, a.max_moves);
-        long long nodes = 0;
-        int found = -1;
-        uint32_t action = 0u;
-        for (int m = lo; m < hi && found < 0; m += kSpecWarps) {
-            const int cnt = min(kSpecWarps, hi - m);
-            if (w < cnt) {
-                const BeamResult r = beam_search_warp(s.board, -1, a.P, game, (uint32_t)(m + w), row, ws);
-                if (lane == 0) { slots[group][buf][w].action = r.action; slots[group][buf][w].nodes = r.nodes; }
-            }
-            if (leader) note[group][buf] = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg) < seg;   // a lower range ended the stall
-            group_barrier();
-            if (leader) GAMES_PROF_ADD(7, 1);
-            const bool cancelled = note[group][buf] != 0;
-            for (int j = 0; j < cnt; ++j) {
-                nodes += slots[group][buf][j].nodes;
-                if ((legal >> slots[group][buf][j].action) & 1u) { found = m + j - lo; action = slots[group][buf][j].action; break; }
-            }
-            buf ^= 1;
-            if (cancelled) { found = -1; break; }
-        }
-        if (leader) {
-            SegResult *out = results_of(rec) + seg;
-            out->first_valid = found; out->action = action; out->nodes = nodes;
-            if (found >= 0) atomicMin(&rec->first_valid_seg, seg);
-            __threadfence();
-            note[group][buf] = atomicAdd(&rec->done, 1) + 1 == segs;
-        }
-        group_barrier();
-        const bool last = note[group][buf] != 0;
-        buf ^= 1;
-        if (!last) return false;
-        __threadfence();
-        const int f = *reinterpret_cast<volatile int32_t *>(&rec->first_valid_seg);
-        const volatile SegResult *res = results_of(rec);
-        if (f >= segs) {                                   // no valid call up to the move cap
-            for (int k = 0; k < segs; ++k) gs.nodes += res[k].nodes;
-            gs.invalid += a.max_moves - gs.moves;
-            gs.moves = a.max_moves;
-            if (leader) { write_game(a, gs); __threadfence(); atomicAdd(&a.ctr->written, 1u); }
-            return false;
-        }
-        for (int k = 0; k <= f; ++k) gs.nodes += res[k].nodes;
-        const int before = f * seg_len + res[f].first_valid;      // invalid moves: nothing else changes (env:188-192)
-        gs.invalid += before;
-        gs.moves += before;
-        BeamResult r;
-        r.action = res[f].action;
-        r.nodes = 0;
-        done = play_move(gs, s, r, a, row, game);
-        return true;
-    };
 
     for (;;) {
         if (leader) {
@@ -1317,56 +1251,11 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
         group_barrier();                                   // ... before the leader claims the next entry
         EnvState s;
         bool done = false;
-        if (gs.reserved == kEntrySegment) {                // a range of a split stall: gs.score = record, gs.moves = range
-            G2048_ASSERT((unsigned int)gs.score < a.record_cap && gs.moves >= 1 && gs.moves < kMaxSegs);
-            if (!run_segment(&a.records[gs.score], gs.moves, gs, s, done)) continue;
-        } else {
-            if (leader) { GAMES_PROF_ADD(6, 1); GAME_EVT(4, gs.index); }
-            load_env(gs, s);
-        }
+        if (leader) { GAMES_PROF_ADD(6, 1); GAME_EVT(4, gs.index); }
+        load_env(gs, s);
         const uint32_t game = a.game0 + gs.index;
         int width = gs.streak >= kStallStreak && gs.reserved == kEntryStalled ? kSpecWarps : 1;   // inside a stall, or normal play
-        int dry_rounds = 0;                                // full-width rounds without a valid call
-        bool mine = true;                                  // false: the game went to a split record
         while (!done && gs.moves < a.max_moves) {
-            // a long stall with plenty of calls left: cut the rest into ranges for several SMs
-            if (dry_rounds >= kSplitAfterRounds && a.records && a.max_moves - gs.moves >= 2 * kMinSegCalls) {
-                dry_rounds = 0;
-                if (leader) {
-                    int got = -1;
-                    const unsigned int idx = atomicAdd(&a.ctr->group_splits, 1u) < a.group_split_cap
-                                                 ? atomicAdd(&a.ctr->record_count, 1u) : a.record_cap;
-                    if (idx < a.record_cap) {
-                        StallRecord *rec = &a.records[idx];
-                        const int rem = a.max_moves - gs.moves;
-                        const int segs = min(kMaxSegs, rem / kMinSegCalls);
-                        store_env(gs, s);
-                        rec->gs = gs;
-                        rec->segs = segs;
-                        rec->seg_len = (rem + segs - 1) / segs;
-                        rec->done = 0;
-                        rec->first_valid_seg = kNoValidSeg;
-                        rec->big = nullptr;
-                        GAME_EVT(5, gs.index);
-                        __threadfence();
-                        GameState entry = gs;
-                        entry.reserved = kEntrySegment;
-                        entry.score = (int32_t)idx;
-                        for (int k = 1; k < segs; ++k) { entry.moves = k; push_pending(a, entry); }
-                        got = (int)idx;
-                    }
-                    note[group][buf] = got;
-                }
-                group_barrier();
-                const int idx = note[group][buf];
-                buf ^= 1;
-                group_barrier();
-                if (idx >= 0) {
-                    if (!run_segment(&a.records[idx], 0, gs, s, done)) { mine = false; break; }
-                    width = 1;
-                    continue;
-                }
-            }
             const int allowed = min(width, a.max_moves - gs.moves);
             if (allowed == 1) {
                 if (w < kTeamWarps) {
@@ -1394,14 +1283,11 @@ __device__ __noinline__ void break_stalls(const GamesArgs &a, uint8_t *smem, con
                 r.nodes = 0;
                 done = play_move(gs, s, r, a, row, game);
                 width = 1;
-                dry_rounds = 0;
             } else {
-                dry_rounds = allowed == kSpecWarps ? dry_rounds + 1 : 0;
                 width = min(kSpecWarps, 2 * width);
             }
             buf ^= 1;
         }
-        if (!mine) continue;
         store_env(gs, s);
         if (leader) { write_game(a, gs); __threadfence(); atomicAdd(&a.ctr->written, 1u); }
     }
@@ -1495,7 +1381,6 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
                         continue;
                     }
                     if (pop_pending(a, job.gs)) {
-                        G2048_ASSERT(job.gs.reserved != kEntrySegment);
                         reserved = job.gs.reserved == kEntryMigrated;          // its pusher took the room it needs off the count
                         GAME_EVT(4, job.gs.index);
                         kind = kJobGame;
@@ -1810,9 +1695,8 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     // scratch: counters | ready flags of the pending entries | range queue of the one-warp kernel | pending entries
     // (stalled / migrated games, ranges of stalls the stall breaker split) | split-stall records | games for the
     // team kernel.  Everything before the pending entries is zeroed.
-    const size_t group_split_cap = wide ? 0 : (size_t)(n / 8 > 8 ? n / 8 : 8);
-    const size_t record_cap = wide ? 0 : group_split_cap + 2 * (size_t)n + 64;
-    const size_t pending_cap = wide ? 0 : (size_t)n + (kMaxSegs - 1) * group_split_cap;
+    const size_t record_cap = wide ? 0 : 2 * (size_t)n + 64;
+    const size_t pending_cap = wide ? 0 : (size_t)n + 64;        // a ring: a game is in one place at a time
     const size_t segq_cap = wide ? 0 : kMaxSegs * (2 * (size_t)n + 64);
     // bulk records (stalls that run to the move cap, ~5 % of the games): n / 8 + 16 of them, cut into ranges of 32 calls
     const size_t bulk_segs = (size_t)((max_moves + kBulkSegCalls - 1) / kBulkSegCalls < kBulkMaxSegs
@@ -1836,7 +1720,7 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
                 wide ? nullptr : reinterpret_cast<GameState *>(base + pending_off),
                 wide ? nullptr : reinterpret_cast<unsigned int *>(base + flags_off), (unsigned int)pending_cap,
                 split ? reinterpret_cast<StallRecord *>(base + records_off) : nullptr,
-                (unsigned int)record_cap, (unsigned int)group_split_cap,
+                (unsigned int)record_cap,
                 split && segq_cap ? reinterpret_cast<unsigned int *>(base + segq_off) : nullptr, (unsigned int)segq_cap,
                 split && bulkq_cap ? reinterpret_cast<unsigned int *>(base + bulkq_off) : nullptr, (unsigned int)bulkq_cap,
                 reinterpret_cast<SegResult *>(base + big_off), (unsigned int)bulkq_cap,

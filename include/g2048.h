@@ -261,8 +261,10 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *                               left alive, then teams (-1 = default: the team slots; 0 = never)
  *   G2048_TUNE_STEP_TABLES      g2048_env_step*: 0 = table-free SWAR row move, 1 = row tables read through L1/L2,
  *                               -1 = default: table-free below 262,144 envs per launch, tables from there on
- *   G2048_TUNE_SPLIT_STALLS     g2048_play_games: 1 = a long stall (the agent keeps choosing an invalid move) is
- *                               cut into call ranges that several SMs search at once (default), 0 = one SM */
+ *   G2048_TUNE_SPLIT_STALLS     g2048_play_games: 1 = the calls of a stall (the agent keeps choosing an invalid move)
+ *                               are cut into ranges that every free warp of the GPU searches (default); 0 = a stalled
+ *                               game is parked for the stall breaker (one-warp kernel) or played through move by
+ *                               move (team kernel): a test path, slow on games that stall up to the move cap */
 enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2,
        G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_SPLIT_STALLS = 4, G2048_TUNE_COUNT = 5 };
 int g2048_set_tuning(int key, int value);

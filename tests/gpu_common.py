@@ -35,10 +35,12 @@ class tuning:
 
 # scheduling paths of g2048_play_games: teams from the first move / one warp per game only /
 # one warp per game until `tail` games are left, then teams
-# (long stalls are cut into call ranges for several SMs on every path; "team, one SM per stall" switches that off)
+# (stalls are cut into call ranges for every free warp on every path; the "no split" paths switch that off: the team
+# kernel then plays through a stall move by move, the one-warp kernel parks the game for finish_games_kernel)
 PLAY_PATHS = {"team": {TUNE_TEAM_DIRECT_MAX: 1 << 30}, "warp": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 0},
               "warp+tail": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 40},
-              "team, one SM per stall": {TUNE_TEAM_DIRECT_MAX: 1 << 30, TUNE_SPLIT_STALLS: 0}}
+              "team, no split": {TUNE_TEAM_DIRECT_MAX: 1 << 30, TUNE_SPLIT_STALLS: 0},
+              "warp, parked stalls": {TUNE_TEAM_DIRECT_MAX: 0, TUNE_TAIL_THRESHOLD: 0, TUNE_SPLIT_STALLS: 0}}
 
 
 def host_reset(n, seed, game0=0, spawn_ctr=None):
