@@ -22,11 +22,12 @@ struct DeviceState {
     // free memory back to the driver at every synchronisation, so a host call that ends in a stream sync would
     // pay a fresh device allocation (~0.4 ms) on its next launch.
     cudaMemPool_t pool = nullptr;
-    // 512-entry pair table (board.cuh: pair_table_entry) followed by the 16 float32 observation values e / 15:
-    // the per-step kernel copies them into shared memory instead of computing them in every block
+    // 512-entry pair table (board.cuh: pair_table_entry) followed by 256 float2 observation pairs (entry b = the
+    // float32 values e / 15 of the two nibbles of byte b): the per-step kernel copies them into shared memory
+    // instead of computing them in every block
     uint32_t *step_tables = nullptr;
 };
-constexpr int kStepTableWords = 512 + 16;
+constexpr int kStepTableWords = 512 + 2 * 256;
 
 // Returns the state of the current device, or nullptr (and sets the error) if g2048_init
 // has not been called for it.

@@ -105,69 +105,76 @@ constexpr int kStepMaxThreads = 1024;
 template <bool kSwarMove>
 __global__ void __launch_bounds__(kStepMaxThreads) env_step_fused_kernel(StepArgs a)
 {
-    __shared__ __align__(16) uint32_t tables[kStepTableWords + 32];
-    // 528 words = 132 16-byte pieces: the block's first threads copy one each (constant tables, written once by
-    // g2048_init: reading them does not have to wait for the launch before this one)
-    static_assert(kStepTableWords % 4 == 0 && kStepTableWords / 4 <= 160, "copied by the first five warps at most");
+    __shared__ __align__(16) uint32_t tables[kStepTableWords];
+    // 1,024 words = 256 16-byte pieces (constant tables, written once by g2048_init: reading them does not have to
+    // wait for the launch before this one; reading them in place through L1 instead was measured slower at every size)
+    static_assert(kStepTableWords % 4 == 0, "copied in 16-byte pieces");
     for (int i = threadIdx.x; i < kStepTableWords / 4; i += blockDim.x)
         reinterpret_cast<uint4 *>(tables)[i] = __ldg(reinterpret_cast<const uint4 *>(a.tables) + i);
     const uint32_t *pairs = tables;
-    const float *obs_lut = reinterpret_cast<const float *>(tables + kPairEntries);
+    const char *obs_pairs = reinterpret_cast<const char *>(tables + kPairEntries);      // float2[256]
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t lane = threadIdx.x & 31u;
-    // warps stay whole (the observation is written through shuffles): warp-aligned base, lane offset
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < a.n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = base + lane;
-        const bool live = i < a.n;
-        EnvState s;
-        s.board = Board(0u, 0u); s.score = 0; s.highest = 0u; s.spawn_ctr = 0u;
-        if (live) {
-            s.board = Board(a.boards[i]);
-            s.score = a.score ? a.score[i] : 0;
-            s.highest = a.highest ? a.highest[i] : 0u;
-            s.spawn_ctr = a.spawn_ctr ? a.spawn_ctr[i] : 0u;
-            const uint32_t action = a.actions[i];
-            uint32_t inj[2];
-            if (a.inject) { inj[0] = a.inject[2 * i]; inj[1] = a.inject[2 * i + 1]; }
-            const uint32_t game = a.game0 + (uint32_t)i;
-            // one code path: a launch runs every instruction once per warp, so instruction fetch is what it waits
-            // for most (ncu: no_instruction is the top stall); a second, reward-free copy of the step would double it
-            StepResult2 r = env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow);
-            if (a.stepped) a.stepped[i] = s.board.u64();
-            if (a.final_score) a.final_score[i] = s.score;
-            if (a.final_highest) a.final_highest[i] = (uint8_t)s.highest;
-            if (a.episodes && r.done) {                   // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
-                env_reset_cold(s, a.K, game);
-                a.episodes[i] += 1;
-                r.legal = env_legal_mask(s.board);
-            }
-            a.boards[i] = s.board.u64();
-            if (a.score) a.score[i] = s.score;
-            if (a.highest) a.highest[i] = (uint8_t)s.highest;
-            if (a.spawn_ctr) a.spawn_ctr[i] = s.spawn_ctr;
-            if (a.reward) a.reward[i] = r.reward;
-            if (a.reward32) a.reward32[i] = (float)r.reward;
-            if (a.score_delta) a.score_delta[i] = (int32_t)r.score_delta;
-            if (a.valid) a.valid[i] = r.valid;
-            if (a.legal) a.legal[i] = (uint8_t)r.legal;
-            if (a.done) a.done[i] = r.done;
-        }
-        if (a.obs) {
-            // 32 envs x 16 floats = 2 KiB per warp, written as four fully coalesced 512-byte rows:
-            // store k, lane l writes float4 number 32k + l = cells 4q..4q+3 of env 8k + l/4, q = l%4
-            float4 *out = reinterpret_cast<float4 *>(a.obs + 16 * base);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int src = 8 * k + (int)(lane >> 2);
-                const uint32_t lo = __shfl_sync(0xFFFFFFFFu, s.board.lo, src), hi = __shfl_sync(0xFFFFFFFFu, s.board.hi, src);
-                const uint32_t q = lane & 3u;
-                const uint32_t cells = ((q & 2u) ? hi : lo) >> (16u * (q & 1u));
-                if (base + src < a.n)
-                    out[32 * k + lane] = make_float4(obs_lut[cells & 15u], obs_lut[(cells >> 4) & 15u],
-                                                     obs_lut[(cells >> 8) & 15u], obs_lut[(cells >> 12) & 15u]);
-            }
+    // one env per thread; the launch covers the batch (env_step_launch), so there is no loop
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)a.n) return;
+    EnvState s;
+    s.board = Board(a.boards[i]);
+    s.score = a.score ? a.score[i] : 0;
+    s.highest = a.highest ? a.highest[i] : 0u;
+    s.spawn_ctr = a.spawn_ctr ? a.spawn_ctr[i] : 0u;
+    const uint32_t action = a.actions[i];
+    uint32_t inj[2];
+    if (a.inject) { inj[0] = a.inject[2 * (size_t)i]; inj[1] = a.inject[2 * (size_t)i + 1]; }
+    const uint32_t game = a.game0 + i;
+    // one code path: a launch runs every instruction once per warp, and a warp runs them nearly one dependent
+    // instruction at a time, so the instruction count is the launch time; a second, reward-free copy of the step
+    // would only add instruction-cache misses
+    StepResult2 r = env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow);
+    if (a.stepped) a.stepped[i] = s.board.u64();
+    if (a.final_score) a.final_score[i] = s.score;
+    if (a.final_highest) a.final_highest[i] = (uint8_t)s.highest;
+    if (a.episodes && r.done) {                   // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
+        env_reset_cold(s, a.K, game);
+        a.episodes[i] += 1;
+        r.legal = env_legal_mask(s.board);
+    }
+    a.boards[i] = s.board.u64();
+    if (a.score) a.score[i] = s.score;
+    if (a.highest) a.highest[i] = (uint8_t)s.highest;
+    if (a.spawn_ctr) a.spawn_ctr[i] = s.spawn_ctr;
+    if (a.reward) a.reward[i] = r.reward;
+    if (a.reward32) a.reward32[i] = (float)r.reward;
+    if (a.score_delta) a.score_delta[i] = (int32_t)r.score_delta;
+    if (a.valid) a.valid[i] = r.valid;
+    if (a.legal) a.legal[i] = (uint8_t)r.legal;
+    if (a.done) a.done[i] = r.done;
+    if (a.obs) {
+        // float32[16] = log2(tile) / 15 of the board the policy acts on next (after a reset, if there was one), from
+        // byte-indexed float2 lookups.  Lanes 2j and 2j+1 write their two envs together: every 16-byte store of the
+        // even lane and the one of the odd lane next to it fill one 32-byte sector (a lane writing its own 64 bytes
+        // alone would half-fill two sectors per store, and the launch is then bound by store transactions).
+        auto quad = [&](uint32_t cells16) {                 // four cells -> float4
+            const float2 p = *reinterpret_cast<const float2 *>(obs_pairs + ((cells16 << 3) & 0x7F8u));
+            const float2 q = *reinterpret_cast<const float2 *>(obs_pairs + ((cells16 >> 5) & 0x7F8u));
+            return make_float4(p.x, p.y, q.x, q.y);
+        };
+        const uint32_t lo = s.board.lo, hi = s.board.hi;
+        if ((i | 31u) < (uint32_t)a.n) {                    // the whole warp is here
+            const uint32_t plo = __shfl_xor_sync(0xFFFFFFFFu, lo, 1), phi = __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
+            const bool odd = (i & 1u) != 0u;
+            const uint32_t elo = odd ? plo : lo, ehi = odd ? phi : hi;       // board of the pair's even env
+            const uint32_t olo = odd ? lo : plo, ohi = odd ? hi : phi;       // ... and of its odd env
+            const uint32_t sh = odd ? 16u : 0u;
+            float4 *even_env = reinterpret_cast<float4 *>(a.obs + 16 * (size_t)(i & ~1u)) + (odd ? 1 : 0);
+            even_env[0] = quad(elo >> sh);
+            even_env[4] = quad(olo >> sh);
+            even_env[2] = quad(ehi >> sh);
+            even_env[6] = quad(ohi >> sh);
+        } else {
+            float4 *out = reinterpret_cast<float4 *>(a.obs + 16 * (size_t)i);
+            out[0] = quad(lo); out[1] = quad(lo >> 16); out[2] = quad(hi); out[3] = quad(hi >> 16);
         }
     }
 }
@@ -620,7 +627,7 @@ int step_tuning(int key);      // beam.cu: g2048_set_tuning values
 
 // Launch with the programmatic-serialization attribute (see pdl_wait above).
 template <typename... Params, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(Params...), int grid, int threads, cudaStream_t stream, Args... args)
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(Params...), int grid, int threads, cudaStream_t stream, Args... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -631,7 +638,7 @@ static cudaError_t launch_pdl(void (*kernel)(Params...), int grid, int threads, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
@@ -671,9 +678,9 @@ int g2048_init(int device)
     G2048_CUDA(cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, device));
     std::vector<uint32_t> step_tables(kStepTableWords);
     for (int i = 0; i < kPairEntries; ++i) step_tables[i] = pair_table_entry((uint32_t)i);
-    for (int i = 0; i < 16; ++i) {
-        const float v = (float)i / 15.0f;                                  // log2(tile) / 15.0 in float32
-        memcpy(&step_tables[kPairEntries + i], &v, sizeof v);
+    for (int b = 0; b < 256; ++b) {
+        const float v[2] = {(float)(b & 15) / 15.0f, (float)(b >> 4) / 15.0f};  // log2(tile) / 15.0 in float32
+        memcpy(&step_tables[kPairEntries + 2 * b], v, sizeof v);
     }
     G2048_CUDA(cudaMalloc(&st.step_tables, kStepTableWords * sizeof(uint32_t)));
     G2048_CUDA(cudaMemcpy(st.step_tables, step_tables.data(), kStepTableWords * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -806,14 +813,14 @@ int g2048_ppo_shape_rewards(const uint64_t *state_boards, const uint64_t *next_b
     const int grid = grid_for(n, 256, st->sm_count, 8);
     const uint64_t mask = set_keys ? (uint64_t)set_capacity - 1 : 0;
     if (set_keys) {
-        cudaError_t e = launch_pdl(novelty_insert_kernel, grid, 256, s, next_boards,
+        cudaError_t e = launch_pdl(true, novelty_insert_kernel, grid, 256, s, next_boards,
                                    reinterpret_cast<unsigned long long *>(set_keys),
                                    reinterpret_cast<unsigned long long *>(set_claims), mask, step, n,
                                    reinterpret_cast<unsigned long long *>(set_dropped));
         count_launch();
         G2048_CUDA(e);
     }
-    cudaError_t e = launch_pdl(ppo_shape_kernel, grid, 256, s, state_boards, next_boards, reward_in, highest_seen_exp,
+    cudaError_t e = launch_pdl(true, ppo_shape_kernel, grid, 256, s, state_boards, next_boards, reward_in, highest_seen_exp,
                                reinterpret_cast<const unsigned long long *>(set_keys),
                                reinterpret_cast<const unsigned long long *>(set_claims), mask, step, reward_out, novel, n);
     count_launch();
@@ -850,22 +857,28 @@ static int env_step_launch(StepArgs a, void *stream)
     const int64_t n = a.n;
     G2048_ENTER(a.boards && a.actions);
     a.row = st->row; a.code = st->code; a.overflow = st->overflow; a.tables = st->step_tables;
-    // One block per SM, sized to the batch: a step costs ~800 instructions per warp and a launch is as long as its
-    // busiest SM, so 65,536 envs run as 148 blocks of 14 warps (the 2,048 warps spread evenly: 256 blocks of 8
-    // warps would put 16 warps on most SMs and 8 on the others), and one copy of the tables per SM is enough.
-    // Batches beyond 16 warps per SM run as blocks of 8 warps, several per SM (measured at 1,048,576 envs: 38 us
-    // per step against 43 us with 1,024-thread blocks, whose tails leave SMs idle).
+    // One block per SM, sized to the batch, up to 28 warps: a step costs ~900 instructions per warp and a launch is as
+    // long as its busiest SM, so 65,536 envs run as 147 blocks of 14 warps (the 2,048 warps spread evenly: 256 blocks
+    // of 8 warps would put 16 warps on most SMs and 8 on the others), and one copy of the tables per SM is enough.
+    // Larger batches run as blocks of 14 warps, several per SM.
     const int64_t warps = (n + 31) / 32;
     int64_t per_block = (warps + st->sm_count - 1) / st->sm_count;
-    if (per_block > 16) per_block = 8;
+    if (per_block > 28) per_block = 14;
+    const int forced = step_tuning(G2048_TUNE_STEP_BLOCK_WARPS);
+    if (forced > 0 && forced <= kStepMaxThreads / 32) per_block = forced;
     const int threads = 32 * (int)per_block;
     const int grid = (int)((warps + per_block - 1) / per_block);
+    // Programmatic dependent launch lets the next step's blocks start (and copy their tables) while this one drains:
+    // -8 % at 16,384 envs per launch.  With more envs it hurts -- the early blocks of the next launch take SM slots
+    // unevenly (65,536 envs: 5.2 us per step with it, 4.5 us without) -- so only small batches use it.
+    const int pdl_knob = step_tuning(G2048_TUNE_PDL);
+    const bool pdl = pdl_knob < 0 ? n <= 32768 : pdl_knob != 0;
     cudaError_t e;
     // table-free move: 15 % faster up to 65,536 envs (no dependent table round trip on a latency-bound launch);
     // at a million envs the launch is ALU-bound and the table reads are hidden: row tables win by 8 %
     const int tables = step_tuning(G2048_TUNE_STEP_TABLES);
-    if (tables == 1 || (tables < 0 && n >= (1 << 18))) e = launch_pdl(env_step_fused_kernel<false>, grid, threads, s, a);
-    else                                     e = launch_pdl(env_step_fused_kernel<true>, grid, threads, s, a);
+    if (tables == 1 || (tables < 0 && n >= (1 << 18))) e = launch_pdl(pdl, env_step_fused_kernel<false>, grid, threads, s, a);
+    else                                     e = launch_pdl(pdl, env_step_fused_kernel<true>, grid, threads, s, a);
     count_launch();
     return check_cuda(e, __func__);
 }

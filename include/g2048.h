@@ -264,9 +264,13 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *   G2048_TUNE_SPLIT_STALLS     g2048_play_games: 1 = the calls of a stall (the agent keeps choosing an invalid move)
  *                               are cut into ranges that every free warp of the GPU searches (default); 0 = a stalled
  *                               game is parked for the stall breaker (one-warp kernel) or played through move by
- *                               move (team kernel): a test path, slow on games that stall up to the move cap */
+ *                               move (team kernel): a test path, slow on games that stall up to the move cap
+ *   G2048_TUNE_STEP_BLOCK_WARPS g2048_env_step*: warps per block (-1 = default: sized to the batch, see env_step_launch)
+ *   G2048_TUNE_PDL              g2048_env_step*: 1 = launched with programmatic dependent launch, 0 = plain,
+ *                               -1 = default: with it up to 32,768 envs per launch */
 enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2,
-       G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_SPLIT_STALLS = 4, G2048_TUNE_COUNT = 5 };
+       G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_SPLIT_STALLS = 4, G2048_TUNE_STEP_BLOCK_WARPS = 5, G2048_TUNE_PDL = 6,
+       G2048_TUNE_COUNT = 7 };
 int g2048_set_tuning(int key, int value);
 
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */

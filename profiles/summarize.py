@@ -89,7 +89,7 @@ def launch_list(path):
             agg[k][0] += 1
             agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
-    lines = [f"## launch list ({os.path.basename(path)}: ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 10 --warmup 3`)",
+    lines = [f"## launch list ({os.path.basename(path)}: ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 5 --warmup 3`)",
              "per-launch times are cold-cache and serialised: compare SHARES, not absolutes", "",
              f"{'kernel':72s} {'launches':>8s} {'total ms':>10s} {'avg us':>9s} {'share':>7s}"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
@@ -166,6 +166,11 @@ def main():
     rep = os.path.join(OUT, f"prof_step_{tag}.ncu-rep")
     if os.path.exists(rep):
         lines, d = raw_summary(rep, "env_step_fused_kernel<table-free move> (per-step API, 65,536 envs per launch, all outputs incl. observation)")
+        text += lines + [""]
+    rep = os.path.join(OUT, f"prof_step_warm_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        lines, d = raw_summary(rep, "env_step_fused_kernel, the same launch with --cache-control none (state and tables L2-resident, as inside "
+                                    "a training loop / CUDA graph; the capture above starts from flushed caches)")
         text += lines + [""]
     rep = os.path.join(OUT, f"prof_lone_{tag}.ncu-rep")
     if os.path.exists(rep):
