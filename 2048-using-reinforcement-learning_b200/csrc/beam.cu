@@ -986,6 +986,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
 #endif
     enum { kNeedWork = 0, kPlaying = 1, kInRange = 2 };
     int state = kNeedWork;
+    unsigned int nap = 2000u;                              // lane 0: sleep between two looks at the queues while idle
     bool queue_dry = false, done = false;
     EnvState s;                    // board, score, highest tile, spawn counter: registers (the search starts from the board)
     uint32_t game = 0u, legal = 0u;
@@ -1070,7 +1071,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
                 unsigned int task = 0u;
                 if (lane == 0) task = pop_range(a, bulk_ok);
                 task = __shfl_sync(FULL, task, 0);
-                if (task) begin_range(&a.records[(task - 1u) >> 10], (int)((task - 1u) & 1023u));
+                if (task) { nap = 2000u; begin_range(&a.records[(task - 1u) >> 10], (int)((task - 1u) & 1023u)); }
             }
             if (state == kNeedWork && !queue_dry) {
                 unsigned int g = 0;
@@ -1093,7 +1094,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) play_games_kernel(GamesArgs a
                 if (lane == 0) {
                     const volatile GameCounters *c = a.ctr;
                     over = (a.tail ? handover_started(a) : c->finished >= (unsigned int)a.n) && !ranges_waiting(a, bulk_ok);
-                    if (!over) __nanosleep(2000);
+                    if (!over) { __nanosleep(nap); nap = min(2u * nap, 32000u); }   // idle warps back off
                 }
                 if (__shfl_sync(FULL, over, 0)) break;
                 continue;
@@ -1372,6 +1373,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
             volatile GameCounters *c = a.ctr;
             int kind = -1;
             bool deferred = false, reserved = false;
+            unsigned int nap = 1000u;                      // idle leaders back off: five of them share an SM with a lone game
             while (kind < 0) {
                 if (a.pending && c->finish_work < c->pending_count) {           // 1. a game that waits in pending[]
                     // ... goes to a receiver on a block with room; anybody else waits a while first (then nobody with room is free)
@@ -1408,7 +1410,8 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
                     break;
                 }
                 if (c->written >= (unsigned int)a.n) { kind = kJobExit; break; }               // 4. every game is final
-                __nanosleep(1000);
+                __nanosleep(nap);
+                nap = min(2u * nap, 32000u);
             }
             if (kind == kJobGame) {
                 const bool uses_room = atomicAdd(&active_teams, 1) < 3;
@@ -1422,18 +1425,20 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
         if (kind == kJobExit) break;
 
         if (kind == kJobGame) {
-            GameState gs = job.gs;                         // every thread of the team keeps an identical copy
+            // The game's record stays in shared memory (job.gs, kept by the leader): across a search the threads only
+            // hold the env (five registers), the move count and the streak -- the search wants every register.
+            GameState &gs = job.gs;
             EnvState s;
             load_env(gs, s);
             const uint32_t game = a.game0 + gs.index;
+            int moves = gs.moves, streak = gs.streak;
             bool done = false, migrate = false, split = false, may_split = can_split;
-            team_barrier(bar);                             // everyone has its copy before the leader reuses `job`
-            while (!done && gs.moves < a.max_moves) {
-                if (a.pending && gs.streak >= kStallStreak && may_split) {
+            while (!done && moves < a.max_moves) {
+                if (a.pending && streak >= kStallStreak && may_split) {
                     // the agent keeps choosing an invalid move: cut the next calls into ranges for every free warp
                     if (leader) {
                         store_env(gs, s);
-                        gs.reserved = 0;
+                        gs.moves = moves; gs.streak = streak; gs.reserved = 0;
                         bool bulk;
                         ts.next_item = split_stall(a, gs, 0, &bulk);
                     }
@@ -1445,7 +1450,7 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
                 }
                 // every fourth move: does the game share a crowded SM while a team waits on an emptier one?
 #ifndef G2048_NO_MIGRATE
-                if (a.pending && (gs.moves & 3) == 3) {
+                if (a.pending && (moves & 3) == 3) {
                     if (leader) {
                         unsigned int go = 0u;
                         if (*reinterpret_cast<volatile int *>(&active_teams) > 3 &&
@@ -1462,13 +1467,25 @@ __global__ void __launch_bounds__(kBeamThreads, 1) team_games_kernel(GamesArgs a
                     if (migrate) break;
                 }
 #endif
-                const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)gs.moves, row, ts, bar);
-                done = play_move(gs, s, r, a, row, game);
+                const BeamResult r = beam_search_team(s.board, -1, a.P, game, (uint32_t)moves, row, ts, bar);
+                // env.step(action) and the bookkeeping of evaluate_beam_search.py:56-86 (play_move), the latter by the leader
+                const StepResult st = env_step<true, false, false>(s, r.action, row, a.code, a.P.K, game, nullptr, a.overflow);
+                if (leader) {
+                    gs.nodes += r.nodes;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (gs.ms[k] < 0 && s.highest >= (uint32_t)(6 + k)) gs.ms[k] = moves;
+                    if (st.valid) ++gs.valid; else ++gs.invalid;
+                }
+                streak = st.valid ? 0 : streak + 1;
+                ++moves;
+                done = st.done;
             }
             if (leader) {
                 if (atomicSub(&active_teams, 1) <= 3) atomicAdd(&a.ctr->idle_groups, 1);       // room for a full-speed game again
                 if (!split) {                              // finished (written) or migrating (to pending[])
                     store_env(gs, s);
+                    gs.moves = moves; gs.streak = streak;
                     retire_game(a, gs, done, kRetireMigrate);
                     GAMES_PROF_MAX(2);
                 }
