@@ -153,15 +153,17 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
     uint32_t ring_end = 0u;      // ts.rng holds the spawn words of ordinals [ring_end - 512, ring_end)
     const uint32_t *corners = corner_table();
 
+    // A level draws at most 128 spawns; one pass (a Philox block per thread) adds 256 ordinals and overwrites
+    // ordinals below ring_end - 256, all consumed (spawn_base > ring_end - 128).  The first pass is made here, the
+    // later ones inside phase C of the level before the one that needs them: the block's ten rounds of multiplies
+    // then interleave with the key loads of the counting rank instead of standing alone at the head of a level.
+    {
+        const Philox4 p = philox4x32_10(tid, call, game, DOM_BEAM, P.K);
+        ts.rng[tid] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
+        ring_end = 256u;
+    }
     TEAM_PROF_DECL;
     for (int d = 0; d < depth; ++d) {
-        // a level draws at most 128 spawns; one pass (a Philox block per thread) adds 256 ordinals and
-        // overwrites ordinals below ring_end - 256, all consumed (spawn_base > ring_end - 128)
-        if (ring_end - spawn_base < 128u) {
-            const Philox4 p = philox4x32_10((ring_end >> 1) + tid, call, game, DOM_BEAM, P.K);
-            ts.rng[((ring_end & (kTeamRing - 1u)) >> 1) + tid] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
-            ring_end += 256u;
-        }
         // ---- A: my child (agent:112-123 for the root, agent:142-167 below it) ------------------------
         Board parent = root;
         uint32_t pmeta = tw | (root_emax << 2);
@@ -244,6 +246,11 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
         ts.key[tid] = key;
         team_barrier(bar);                                              // (2) all keys of the level are visible
         TEAM_PROF_MARK(_pb);
+        if (ring_end - spawn_base < 128u) {                             // the next level's spawn words (see above)
+            const Philox4 p = philox4x32_10((ring_end >> 1) + tid, call, game, DOM_BEAM, P.K);
+            ts.rng[((ring_end & (kTeamRing - 1u)) >> 1) + tid] = make_uint4(p.w[0], p.w[1], p.w[2], p.w[3]);
+            ring_end += 256u;
+        }
 
         // ---- C: stable top-k by counting (agent:131-132,174-175) -----------------------------------------
         const int groups = d == 0 ? 1 : (nb + 3) >> 2;                 // 16-byte key groups per action in use
