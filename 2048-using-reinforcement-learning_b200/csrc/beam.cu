@@ -1606,7 +1606,7 @@ namespace g2048 {
 #endif
 
 static int g_attr_done[kMaxDevices];
-static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, -1, 1, -1, -1};
+static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, -1, 1, -1, -1, -1};
 int step_tuning(int key) { return g_tuning[key]; }
 
 int set_tuning(int key, int value)
@@ -1713,7 +1713,8 @@ int launch_play_games(DeviceState *st, int64_t n, int beam_width, int search_dep
     // (stalled / migrated games, ranges of stalls the stall breaker split) | split-stall records | games for the
     // team kernel.  Everything before the pending entries is zeroed.
     const size_t record_cap = wide ? 0 : 2 * (size_t)n + 64;
-    const size_t pending_cap = wide ? 0 : (size_t)n + 64;        // a ring: a game is in one place at a time
+    const size_t pending_cap = wide ? 0 : g_tuning[G2048_TUNE_PENDING_CAP] > 0 ? (size_t)g_tuning[G2048_TUNE_PENDING_CAP]
+                                                                                : (size_t)n + 64;   // a ring: a game is in one place at a time
     const size_t segq_cap = wide ? 0 : kMaxSegs * (2 * (size_t)n + 64);
     // bulk records (stalls that run to the move cap, ~5 % of the games): n / 8 + 16 of them, cut into ranges of 32 calls
     const size_t bulk_segs = (size_t)((max_moves + kBulkSegCalls - 1) / kBulkSegCalls < kBulkMaxSegs
