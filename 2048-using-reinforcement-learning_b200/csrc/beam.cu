@@ -1606,7 +1606,7 @@ namespace g2048 {
 #endif
 
 static int g_attr_done[kMaxDevices];
-static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, -1, 1, -1, -1, -1};
+static int g_tuning[G2048_TUNE_COUNT] = {0, -1, -1, -1, 1, -1, -1, -1, -1};
 int step_tuning(int key) { return g_tuning[key]; }
 
 int set_tuning(int key, int value)

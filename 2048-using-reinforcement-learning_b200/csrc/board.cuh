@@ -218,7 +218,7 @@ __device__ __forceinline__ uint32_t edge_sum_pairs(Board b, uint32_t total, cons
 //   3. close the holes: cells right of a hole move one nibble left.
 // `codes` gets, on the cell that received a merge, the exponent before it (= merged exponent - 1,
 // the code of row_tables.h): one pair-table lookup per byte then gives the score and the saturation flag.
-struct HalfMove { uint32_t rows, codes; };
+struct HalfMove { uint32_t rows, codes, occupied; };    // occupied: nz_flags of the INPUT rows (a by-product)
 __device__ __forceinline__ HalfMove move_left_half(uint32_t x)
 {
     const uint32_t nz = nz_flags(x), z = nz ^ LSB4;
@@ -235,6 +235,7 @@ __device__ __forceinline__ HalfMove move_left_half(uint32_t x)
     e &= ~((e & 0x00100010u) << 4);                                           // m2 = e2 & ~m1
     const uint32_t em = e * 15u;
     HalfMove r;
+    r.occupied = nz;
     r.codes = y & em;
     const uint32_t sat = r.codes & (r.codes >> 1) & (r.codes >> 2) & (r.codes >> 3) & LSB4;   // merging two 32768s
     y = (y + (e ^ sat)) & ~(em << 4);
@@ -286,9 +287,9 @@ __device__ __forceinline__ Board env_move(Board b, uint32_t action, const uint16
 // empty neighbour in that direction or two equal neighbours along it can merge.
 __device__ __forceinline__ uint32_t eq_flags(uint32_t a, uint32_t b) { return zero_flags(a ^ b); }
 
-__device__ __forceinline__ uint32_t env_legal_mask(Board b)
+// nl / nh: occupancy flags (bit 0 of every non-empty nibble) of b.lo / b.hi
+__device__ __forceinline__ uint32_t env_legal_mask_flags(Board b, uint32_t nl, uint32_t nh)
 {
-    const uint32_t nl = nz_flags(b.lo), nh = nz_flags(b.hi);
     // horizontal pairs (c, c+1): flag sits on nibble c, c = 0..2 of each row
     const uint32_t HP = 0x01110111u;
     uint32_t nl1 = nl >> 4, nh1 = nh >> 4;                       // occupancy of the right neighbour
@@ -310,6 +311,7 @@ __device__ __forceinline__ uint32_t env_legal_mask(Board b)
     mask |= ((mv | sd) != 0u) ? 8u : 0u;
     return mask;
 }
+__device__ __forceinline__ uint32_t env_legal_mask(Board b) { return env_legal_mask_flags(b, nz_flags(b.lo), nz_flags(b.hi)); }
 // is_game_over (env:279-288): no empty cell and no equal neighbours
 __device__ __forceinline__ bool env_game_over(Board b) { return env_legal_mask(b) == 0u; }
 // Out-of-line copy for hot loops: a full board is rare, and a call cannot be if-converted

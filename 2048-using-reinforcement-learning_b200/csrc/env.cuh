@@ -82,29 +82,45 @@ struct StepResult2 {
     uint32_t score_delta, legal;
     bool valid, done;
 };
-template <bool kSwarMove, bool kReward>
+// `tables_ready()` is called once, by every thread, right before the first use of `pairs`: the kernel publishes its
+// shared-memory copy of the tables there (a block-wide barrier), so the table-free move above it overlaps the copy.
+template <bool kSwarMove, bool kReward, class TablesReady>
 __device__ __forceinline__ StepResult2 env_step_pairs(EnvState &s, uint32_t action, const uint16_t *row, const uint8_t *code,
                                                       const uint32_t *pairs, const PhiloxKey &K, uint32_t game,
-                                                      const uint32_t *inject, unsigned long long *overflow)
+                                                      const uint32_t *inject, unsigned long long *overflow,
+                                                      TablesReady tables_ready)
 {
     StepResult2 r;
     const Board prev = s.board;
+    const uint32_t prev_max = max_exponent(prev);
     const Board line = to_line(prev, action);
+    const bool in_range = action < 4u;                                       // env:99-114 has no else branch
     Board moved;
     uint32_t gained;
+    int empty_before;
+    bool max_merged = false;                 // two tiles of the board's largest exponent merged
     if (kSwarMove) {
         const HalfMove lo = move_left_half(line.lo), hi = move_left_half(line.hi);
         moved = Board(lo.rows, hi.rows);
+        tables_ready();
         gained = code_score_pairs(lo.codes, hi.codes, pairs);
+        // by-products of the move: the line view is a permutation of the board, so its occupancy counts the board's
+        // empty cells; a code nibble is the exponent of the two tiles that merged, and only a merge of two tiles of
+        // the largest exponent raises the board's maximum (a zero nibble of codes ^ max..max; "any zero nibble" by the
+        // borrow trick is exact as an any-test).  A tile-less board has no merges.
+        empty_before = 16 - __popc(lo.occupied) - __popc(hi.occupied);
+        const uint32_t rep = prev_max * LSB4, x = lo.codes ^ rep, y = hi.codes ^ rep;
+        max_merged = in_range && prev_max != 0u && ((((x - LSB4) & ~x) | ((y - LSB4) & ~y)) & MSB4) != 0u;
     } else {
         moved = move_left<false>(line, row);
+        tables_ready();
         gained = merge_score_pairs<false>(line, code, pairs);
+        empty_before = count_empty(prev);
     }
-    const bool in_range = action < 4u;                                       // env:99-114 has no else branch
     Board next = select(in_range, from_line(moved, action), prev);           // env:185
     gained = in_range ? gained : 0u;
     r.score_delta = gained & (kPairSaturated - 1u);
-    if (gained >> 28) atomicAdd(overflow, 1ull);                             // 32768+32768: nibble saturated
+    if ((gained >> 28) && overflow) atomicAdd(overflow, 1ull);               // 32768+32768: nibble saturated (null: not counted)
     s.score += (int32_t)r.score_delta;
     r.valid = next != prev;                                                  // env:188
     uint32_t nzl = nz_flags(next.lo), nzh = nz_flags(next.hi);
@@ -115,6 +131,7 @@ __device__ __forceinline__ StepResult2 env_step_pairs(EnvState &s, uint32_t acti
     if (inject) { w.pos = inject[0]; w.val = inject[1]; }
     else w = spawn_words(K, game, 0u, DOM_ENV, s.spawn_ctr);                  // computed for every lane, used by the valid ones
     const SpawnPick sp = pick_spawn(zl, zh, cl, empty_after, w.pos, w.val);
+    uint32_t spawned = 0u;
     if (r.valid) {                                                           // env:191-192, always >= 1 empty here
         next.lo |= sp.flag_lo * sp.exponent;
         next.hi |= sp.flag_hi * sp.exponent;
@@ -122,16 +139,28 @@ __device__ __forceinline__ StepResult2 env_step_pairs(EnvState &s, uint32_t acti
         nzh |= sp.flag_hi;
         if (!inject) s.spawn_ctr += 1u;
         empty_after -= 1;
+        spawned = sp.exponent;
     }
     r.reward = 0.0;
     if (kReward)                                                             // env:195, uses the OLD highest_tile
-        r.reward = shaped_reward_tracked(r.valid, count_empty(prev), next, empty_after, nzl, nzh, r.score_delta, s.highest,
-                                         max_exponent(prev), tile_total_pairs(next, pairs), pairs);
-    r.legal = env_legal_mask(next);
+        r.reward = shaped_reward_tracked(r.valid, empty_before, next, empty_after, nzl, nzh, r.score_delta, s.highest,
+                                         prev_max, tile_total_pairs(next, pairs), pairs);
+    r.legal = env_legal_mask_flags(next, nzl, nzh);
     r.done = r.legal == 0u;                                                  // env:198
-    s.highest = max(s.highest, max_exponent(next));                          // env:200-203
+    // env:200-203.  The new board's largest exponent: the old one, one more when two such tiles merged (a merge of
+    // two 32768s saturates at 15, row_tables.h), or the spawned tile on a board that had none above it
+    const uint32_t next_max = kSwarMove ? max(min(prev_max + (max_merged ? 1u : 0u), 15u), spawned) : max_exponent(next);
+    s.highest = max(s.highest, next_max);
     s.board = next;
     return r;
+}
+
+template <bool kSwarMove, bool kReward>
+__device__ __forceinline__ StepResult2 env_step_pairs(EnvState &s, uint32_t action, const uint16_t *row, const uint8_t *code,
+                                                      const uint32_t *pairs, const PhiloxKey &K, uint32_t game,
+                                                      const uint32_t *inject, unsigned long long *overflow)
+{
+    return env_step_pairs<kSwarMove, kReward>(s, action, row, code, pairs, K, game, inject, overflow, [] {});
 }
 
 // ---- fused-rollout fast path ----------------------------------------------------------------

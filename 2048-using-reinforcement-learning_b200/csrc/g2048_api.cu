@@ -79,6 +79,7 @@ struct StepArgs {
     uint64_t *stepped;             // board after the step, BEFORE an auto-reset (the `next_state` of the transition)
     int32_t *final_score;          // score / highest exponent after the step, before an auto-reset
     uint8_t *final_highest;
+    int32_t tables_early;          // the block publishes its copy of the tables before it waits for the previous launch (PDL)
 };
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
@@ -87,6 +88,20 @@ struct StepArgs {
 // block's lookup tables) overlaps the predecessor's tail; without the attribute both are no-ops.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// A global load that stays where it is written: ptxas sinks plain loads (and non-volatile asm loads) to their first use.
+__device__ __forceinline__ uint64_t load_now(const uint64_t *p)
+{
+    uint64_t v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ uint32_t load_now(const uint32_t *p)
+{
+    uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ uint32_t load_now(const uint8_t *p)
+{
+    uint32_t v; asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
 
 // The reset of a finished game.  (-DG2048_STEP_RESET_NOINLINE moves it out of line: few envs end in a given
 // step; measured slower -- the call's register convention costs every thread more than the skipped fetch saves.)
@@ -102,55 +117,87 @@ __device__ __forceinline__ void env_reset_cold(EnvState &s, const PhiloxKey &K, 
 // No 192 KiB tables: the move is table-free SWAR (kSwarMove) or reads the tables through L1/L2;
 // scores and tile sums come from a 2 KiB pair table built per block.
 constexpr int kStepMaxThreads = 1024;
-template <bool kSwarMove>
+// kOutputs: what the host already knows about the optional arrays (env_step_launch looks at the pointers once, so the
+// kernel does not test them per thread: a test is a 64-bit compare and a branch around every load / store, ~90 of the
+// step's instructions when everything is asked for, and the instruction count is the launch time here):
+//   0  any combination;  1  score, highest, spawn_ctr, reward, reward32, score_delta, valid, legal, done present and no
+//   injected spawn words (every step of BatchedGame2048Env);  2  also episodes, obs, stepped, final_score, final_highest
+//   (BatchedGame2048Env.step_fused of a PPO rollout).
+template <int kOutputs, int kLevel, class T>
+__device__ __forceinline__ bool present(T *p) { return kOutputs >= kLevel || p != nullptr; }
+template <bool kSwarMove, int kOutputs>
 __global__ void __launch_bounds__(kStepMaxThreads) env_step_fused_kernel(StepArgs a)
 {
     __shared__ __align__(16) uint32_t tables[kStepTableWords];
     // 1,024 words = 256 16-byte pieces (constant tables, written once by g2048_init: reading them does not have to
-    // wait for the launch before this one; reading them in place through L1 instead was measured slower at every size)
-    static_assert(kStepTableWords % 4 == 0, "copied in 16-byte pieces");
-    for (int i = threadIdx.x; i < kStepTableWords / 4; i += blockDim.x)
-        reinterpret_cast<uint4 *>(tables)[i] = __ldg(reinterpret_cast<const uint4 *>(a.tables) + i);
+    // wait for the launch before this one).  A thread fetches piece tid into registers here and stores it only where
+    // the step first needs a table (`tables_ready`, after the table-free move): the fetch, the state loads and the
+    // move then overlap instead of queueing behind one another.  Blocks of fewer than 8 warps copy the rest in a
+    // plain loop, one piece in flight per thread.  (Measured and dropped: reading the tables in place through L1 --
+    // 2.7 -> 3.6 us per step at 4,096 envs -- and, for the one-warp blocks of small batches, all seven loads of a
+    // thread in flight together -- 3.0 -> 4.7 us at 32,768 envs: those blocks belong to the NEXT launch and run their
+    // prologue while the current one computes; the slow loop keeps them out of its way.)
+    static_assert(kStepTableWords == 1024, "copied as 256 16-byte pieces, one per thread of the first eight warps");
+    uint4 piece = make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x < 256u) piece = __ldg(reinterpret_cast<const uint4 *>(a.tables) + threadIdx.x);
+#pragma unroll 1
+    for (unsigned int extra = threadIdx.x + blockDim.x; extra < 256u; extra += blockDim.x)
+        reinterpret_cast<uint4 *>(tables)[extra] = __ldg(reinterpret_cast<const uint4 *>(a.tables) + extra);
     const uint32_t *pairs = tables;
     const char *obs_pairs = reinterpret_cast<const char *>(tables + kPairEntries);      // float2[256]
-    __syncthreads();
+    // With programmatic dependent launch the block is here while the launch before it still runs: it publishes the
+    // tables at once (that wait is free) instead of inside the step.
+    const bool early = a.tables_early != 0;
+    auto publish = [&]() {
+        if (threadIdx.x < 256u) reinterpret_cast<uint4 *>(tables)[threadIdx.x] = piece;
+        __syncthreads();
+    };
+    auto tables_ready = [&]() { if (!early) publish(); };
+    if (early) publish();
     pdl_launch_dependents();
     pdl_wait();
-    // one env per thread; the launch covers the batch (env_step_launch), so there is no loop
+    // one env per thread; the launch covers the batch (env_step_launch), so there is no loop.  The threads past the end
+    // of the batch run the step of the last env (every thread has to reach the barrier inside it) and store nothing.
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint32_t)a.n) return;
+    const bool live = i < (uint32_t)a.n;
+    const uint32_t j = live ? i : (uint32_t)a.n - 1u;
+    // (all state loads are issued here, together: left to itself the compiler sinks the ones the move does not need
+    // to their first use, behind the barrier, and the spawn's Philox then waits a second memory round trip)
     EnvState s;
-    s.board = Board(a.boards[i]);
-    s.score = a.score ? a.score[i] : 0;
-    s.highest = a.highest ? a.highest[i] : 0u;
-    s.spawn_ctr = a.spawn_ctr ? a.spawn_ctr[i] : 0u;
-    const uint32_t action = a.actions[i];
+    s.board = Board(load_now(a.boards + j));
+    const uint32_t action = load_now(a.actions + j);
+    s.spawn_ctr = present<kOutputs, 1>(a.spawn_ctr) ? load_now(a.spawn_ctr + j) : 0u;
+    s.score = present<kOutputs, 1>(a.score) ? (int32_t)load_now(reinterpret_cast<const uint32_t *>(a.score) + j) : 0;
+    s.highest = present<kOutputs, 1>(a.highest) ? load_now(a.highest + j) : 0u;
     uint32_t inj[2];
-    if (a.inject) { inj[0] = a.inject[2 * (size_t)i]; inj[1] = a.inject[2 * (size_t)i + 1]; }
-    const uint32_t game = a.game0 + i;
+    const bool injected = kOutputs == 0 && a.inject != nullptr;
+    if (injected) { inj[0] = a.inject[2 * (size_t)j]; inj[1] = a.inject[2 * (size_t)j + 1]; }
+    const uint32_t game = a.game0 + j;
     // one code path: a launch runs every instruction once per warp, and a warp runs them nearly one dependent
     // instruction at a time, so the instruction count is the launch time; a second, reward-free copy of the step
     // would only add instruction-cache misses
-    StepResult2 r = env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, a.inject ? inj : nullptr, a.overflow);
-    if (a.stepped) a.stepped[i] = s.board.u64();
-    if (a.final_score) a.final_score[i] = s.score;
-    if (a.final_highest) a.final_highest[i] = (uint8_t)s.highest;
-    if (a.episodes && r.done) {                   // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
+    StepResult2 r = env_step_pairs<kSwarMove, true>(s, action, a.row, a.code, pairs, a.K, game, injected ? inj : nullptr,
+                                                    live ? a.overflow : nullptr, tables_ready);
+    if (!live) return;
+    if (present<kOutputs, 2>(a.stepped)) a.stepped[i] = s.board.u64();
+    if (present<kOutputs, 2>(a.final_score)) a.final_score[i] = s.score;
+    if (present<kOutputs, 2>(a.final_highest)) a.final_highest[i] = (uint8_t)s.highest;
+    if (present<kOutputs, 2>(a.episodes) && r.done) {   // `if done: state = env.reset()` of the caller's loop (train.py:49,107)
         env_reset_cold(s, a.K, game);
         a.episodes[i] += 1;
         r.legal = env_legal_mask(s.board);
     }
     a.boards[i] = s.board.u64();
-    if (a.score) a.score[i] = s.score;
-    if (a.highest) a.highest[i] = (uint8_t)s.highest;
-    if (a.spawn_ctr) a.spawn_ctr[i] = s.spawn_ctr;
-    if (a.reward) a.reward[i] = r.reward;
-    if (a.reward32) a.reward32[i] = (float)r.reward;
-    if (a.score_delta) a.score_delta[i] = (int32_t)r.score_delta;
-    if (a.valid) a.valid[i] = r.valid;
-    if (a.legal) a.legal[i] = (uint8_t)r.legal;
-    if (a.done) a.done[i] = r.done;
-    if (a.obs) {
+    if (present<kOutputs, 1>(a.score)) a.score[i] = s.score;
+    if (present<kOutputs, 1>(a.highest)) a.highest[i] = (uint8_t)s.highest;
+    if (present<kOutputs, 1>(a.spawn_ctr)) a.spawn_ctr[i] = s.spawn_ctr;
+    if (present<kOutputs, 1>(a.reward)) a.reward[i] = r.reward;
+    if (present<kOutputs, 1>(a.reward32)) a.reward32[i] = (float)r.reward;
+    if (present<kOutputs, 1>(a.score_delta)) a.score_delta[i] = (int32_t)r.score_delta;
+    if (present<kOutputs, 1>(a.valid)) a.valid[i] = r.valid;
+    if (present<kOutputs, 1>(a.legal)) a.legal[i] = (uint8_t)r.legal;
+    if (present<kOutputs, 1>(a.done)) a.done[i] = r.done;
+    if (present<kOutputs, 2>(a.obs)) {
         // float32[16] = log2(tile) / 15 of the board the policy acts on next (after a reset, if there was one), from
         // byte-indexed float2 lookups.  Lanes 2j and 2j+1 write their two envs together: every 16-byte store of the
         // even lane and the one of the odd lane next to it fill one 32-byte sector (a lane writing its own 64 bytes
@@ -856,29 +903,42 @@ static int env_step_launch(StepArgs a, void *stream)
 {
     const int64_t n = a.n;
     G2048_ENTER(a.boards && a.actions);
-    a.row = st->row; a.code = st->code; a.overflow = st->overflow; a.tables = st->step_tables;
-    // One block per SM, sized to the batch, up to 28 warps: a step costs ~900 instructions per warp and a launch is as
-    // long as its busiest SM, so 65,536 envs run as 147 blocks of 14 warps (the 2,048 warps spread evenly: 256 blocks
-    // of 8 warps would put 16 warps on most SMs and 8 on the others), and one copy of the tables per SM is enough.
-    // Larger batches run as blocks of 14 warps, several per SM.
+    a.row = st->row; a.code = st->code; a.overflow = st->overflow; a.tables = st->step_tables; a.tables_early = 0;
+    // Launch geometry (profiles/step_geometry.py; us per step as a CUDA graph, with / without the observation).
+    //  * Programmatic dependent launch lets the next step's blocks become resident and copy their tables while this
+    //    step still computes, which hides most of the ~1.1 us a link in a chain of dependent launches costs.  It pays
+    //    when the blocks are small enough to enter SMs that are still busy: ONE-WARP blocks up to 65,536 envs
+    //    (32,768 envs: 2.9 us against 4.2 us as 147 blocks of 7 warps without it; 16,384: 2.7 against 3.0) and blocks
+    //    of 7 warps from 196,608 envs on (1,048,576: 41 / 30 us against 50 / 34).
+    //  * In between, the waiting blocks of the next launch crowd the running one out (131,072 envs: 7.8 us with it,
+    //    6.9 without), so those launches run plain, as one block per SM sized to the batch (<= 28 warps, else 14).
     const int64_t warps = (n + 31) / 32;
     int64_t per_block = (warps + st->sm_count - 1) / st->sm_count;
     if (per_block > 28) per_block = 14;
+    const int pdl_knob = step_tuning(G2048_TUNE_PDL);
+    const bool pdl = pdl_knob < 0 ? (n <= 65536 || n >= 196608) : pdl_knob != 0;
+    if (pdl && pdl_knob < 0) per_block = n <= 65536 ? 1 : 7;
     const int forced = step_tuning(G2048_TUNE_STEP_BLOCK_WARPS);
     if (forced > 0 && forced <= kStepMaxThreads / 32) per_block = forced;
     const int threads = 32 * (int)per_block;
     const int grid = (int)((warps + per_block - 1) / per_block);
-    // Programmatic dependent launch lets the next step's blocks start (and copy their tables) while this one drains:
-    // -8 % at 16,384 envs per launch.  With more envs it hurts -- the early blocks of the next launch take SM slots
-    // unevenly (65,536 envs: 5.2 us per step with it, 4.5 us without) -- so only small batches use it.
-    const int pdl_knob = step_tuning(G2048_TUNE_PDL);
-    const bool pdl = pdl_knob < 0 ? n <= 32768 : pdl_knob != 0;
+    a.tables_early = pdl ? 1 : 0;
     cudaError_t e;
     // table-free move: 15 % faster up to 65,536 envs (no dependent table round trip on a latency-bound launch);
     // at a million envs the launch is ALU-bound and the table reads are hidden: row tables win by 8 %
     const int tables = step_tuning(G2048_TUNE_STEP_TABLES);
-    if (tables == 1 || (tables < 0 && n >= (1 << 18))) e = launch_pdl(pdl, env_step_fused_kernel<false>, grid, threads, s, a);
-    else                                     e = launch_pdl(pdl, env_step_fused_kernel<true>, grid, threads, s, a);
+    const bool swar = !(tables == 1 || (tables < 0 && n >= (1 << 18)));
+    // what the kernel may take for granted about the optional arrays (kOutputs of env_step_fused_kernel)
+    const bool core = a.score && a.highest && a.spawn_ctr && a.reward && a.reward32 && a.score_delta && a.valid && a.legal &&
+                      a.done && !a.inject;
+    const bool all = core && a.episodes && a.obs && a.stepped && a.final_score && a.final_highest;
+    const int known = all ? 2 : core ? 1 : 0, cap = step_tuning(G2048_TUNE_STEP_OUTPUTS);
+    const int outputs = cap >= 0 && cap < known ? cap : known;
+    auto go = [&](auto kernel) { return launch_pdl(pdl, kernel, grid, threads, s, a); };
+    if (swar) e = outputs == 2 ? go(env_step_fused_kernel<true, 2>) : outputs == 1 ? go(env_step_fused_kernel<true, 1>)
+                                                                                  : go(env_step_fused_kernel<true, 0>);
+    else      e = outputs == 2 ? go(env_step_fused_kernel<false, 2>) : outputs == 1 ? go(env_step_fused_kernel<false, 1>)
+                                                                                   : go(env_step_fused_kernel<false, 0>);
     count_launch();
     return check_cuda(e, __func__);
 }

@@ -267,13 +267,19 @@ int g2048_host_play_games(int64_t n, int32_t beam_width, int32_t search_depth,
  *                               move (team kernel): a test path, slow on games that stall up to the move cap
  *   G2048_TUNE_STEP_BLOCK_WARPS g2048_env_step*: warps per block (-1 = default: sized to the batch, see env_step_launch)
  *   G2048_TUNE_PDL              g2048_env_step*: 1 = launched with programmatic dependent launch, 0 = plain,
- *                               -1 = default: with it up to 32,768 envs per launch
+ *                               -1 = default: with it (and blocks of one / seven warps) up to 65,536 and from 196,608
+ *                               envs per launch on, plain in between (see env_step_launch)
  *   G2048_TUNE_PENDING_CAP      g2048_play_games: slots of the ring through which resumed / migrating games reach a
  *                               free team (-1 = default: games + 64, which can never fill up; tests shrink it to
- *                               exercise the wrap-around) */
+ *                               exercise the wrap-around; a ring smaller than the
+ *                               number of games can block for good when every consumer waits to push -- experiments only)
+ *   G2048_TUNE_STEP_OUTPUTS     g2048_env_step*: -1 = default: the host looks at the optional pointers once and launches
+ *                               the kernel variant that takes the set it found for granted (2 = all of them, 1 = the
+ *                               core set, see env_step_fused_kernel); 0 / 1 = use at most that variant (0 tests every
+ *                               optional array per thread).  A test path: every variant must give the same results */
 enum { G2048_TUNE_SEARCH_MODE = 0, G2048_TUNE_TEAM_DIRECT_MAX = 1, G2048_TUNE_TAIL_THRESHOLD = 2,
        G2048_TUNE_STEP_TABLES = 3, G2048_TUNE_SPLIT_STALLS = 4, G2048_TUNE_STEP_BLOCK_WARPS = 5, G2048_TUNE_PDL = 6,
-       G2048_TUNE_PENDING_CAP = 7, G2048_TUNE_COUNT = 8 };
+       G2048_TUNE_PENDING_CAP = 7, G2048_TUNE_STEP_OUTPUTS = 8, G2048_TUNE_COUNT = 9 };
 int g2048_set_tuning(int key, int value);
 
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */

@@ -4,8 +4,10 @@ import torch
 import g2048_b200 as G
 from g2048_b200 import _lib
 lib = _lib.use_device(0)
+if os.environ.get('STEP_OUTPUTS'): lib.g2048_set_tuning(8, int(os.environ['STEP_OUTPUTS']))
+sizes = [int(x) for x in os.environ.get('STEP_SIZES', '16384,65536,98304,131072').split(',')]
 res = {}
-for n in (16384, 65536, 98304, 131072):
+for n in sizes:
     env = G.BatchedGame2048Env(n, "cuda:0", seed=1)
     env.rollout(300)
     acts = torch.randint(0, 4, (64, n), device="cuda:0", dtype=torch.uint8)

@@ -9,11 +9,14 @@ lib = _lib.use_device(0)
 res = {}
 pdl = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 _lib.check(lib.g2048_set_tuning(6, pdl))
-for n in (16384, 65536, 131072):
+if os.environ.get('STEP_TABLES'): _lib.check(lib.g2048_set_tuning(3, int(os.environ['STEP_TABLES'])))
+sizes = [int(x) for x in os.environ.get('STEP_SIZES', '16384,65536,131072').split(',')]
+widths = [int(x) for x in os.environ.get('STEP_WIDTHS', '-1,1,2,4,7,8,14,16,28,32').split(',')]
+for n in sizes:
     env = G.BatchedGame2048Env(n, "cuda:0", seed=1)
     env.rollout(300)
     acts = torch.randint(0, 4, (64, n), device="cuda:0", dtype=torch.uint8)
-    for bw in (-1, 1, 2, 4, 7, 8, 14, 16, 28, 32):
+    for bw in widths:
         _lib.check(lib.g2048_set_tuning(5, bw))
         for name, obs in (("obs", True), ("noobs", False)):
             def sixty_four():
@@ -21,7 +24,7 @@ for n in (16384, 65536, 131072):
             g = env.graph(sixty_four)
             g.replay(); torch.cuda.synchronize()
             best = 1e9
-            for rep in range(3):
+            for rep in range(5):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
                 for _ in range(8): g.replay()

@@ -13,9 +13,9 @@ def lib():
     return _lib.use_device(0)
 
 
-TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD, TUNE_STEP_TABLES, TUNE_SPLIT_STALLS, TUNE_STEP_BLOCK_WARPS, TUNE_PDL, TUNE_PENDING_CAP = 0, 1, 2, 3, 4, 5, 6, 7
+TUNE_SEARCH_MODE, TUNE_TEAM_DIRECT_MAX, TUNE_TAIL_THRESHOLD, TUNE_STEP_TABLES, TUNE_SPLIT_STALLS, TUNE_STEP_BLOCK_WARPS, TUNE_PDL, TUNE_PENDING_CAP, TUNE_STEP_OUTPUTS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 _TUNE_DEFAULTS = {TUNE_SEARCH_MODE: 0, TUNE_TEAM_DIRECT_MAX: -1, TUNE_TAIL_THRESHOLD: -1, TUNE_STEP_TABLES: -1,
-                  TUNE_SPLIT_STALLS: 1, TUNE_STEP_BLOCK_WARPS: -1, TUNE_PDL: -1, TUNE_PENDING_CAP: -1}
+                  TUNE_SPLIT_STALLS: 1, TUNE_STEP_BLOCK_WARPS: -1, TUNE_PDL: -1, TUNE_PENDING_CAP: -1, TUNE_STEP_OUTPUTS: -1}
 
 
 class tuning:

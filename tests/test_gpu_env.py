@@ -372,11 +372,12 @@ def test_step_autoreset_equals_step_then_reset_done():
     assert torch.equal(a_env.legal, b_env.legal_masks())
 
 
-@pytest.mark.parametrize("tables", [0, 1], ids=["table-free", "row-tables"])
+@pytest.mark.parametrize("tables,outputs", [(0, -1), (1, -1), (0, 0)], ids=["table-free", "row-tables", "generic-outputs"])
 @pytest.mark.parametrize("n", [1, 31, 77, 1000, 4097])
-def test_step_fused_vs_oracle(orc, n, tables):
+def test_step_fused_vs_oracle(orc, n, tables, outputs):
     """g2048_env_step_fused: step + reset of finished games + legal mask + observation + pre-reset state in
-    one launch, at ragged sizes (the observation is written through warp shuffles), with both row-move forms."""
+    one launch, at ragged sizes (the observation is written through warp shuffles), with both row-move forms and
+    with the kernel variant that tests every optional array itself (the default one takes the full set for granted)."""
     import torch
     steps = 140 if n <= 1000 else 40
     env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=11)
@@ -387,7 +388,7 @@ def test_step_fused_vs_oracle(orc, n, tables):
     sample = sorted(set(range(min(n, 40))) | {n - 1, n // 2})
     rng = np.random.default_rng(2)
     episodes = np.zeros(n, np.int64)
-    with X.tuning({X.TUNE_STEP_TABLES: tables}):
+    with X.tuning({X.TUNE_STEP_TABLES: tables, X.TUNE_STEP_OUTPUTS: outputs}):
         for t in range(steps):
             a = rng.integers(0, 4, n).astype(np.uint8)
             obs, reward, done, info = env.step_fused(torch.from_numpy(a).cuda(), auto_reset=True)

@@ -411,3 +411,35 @@ def test_per_step_kernel_transition_bit_exact(emul, orc, golden, swar):
         assert bool(st.done) == k["done"] and bool(st.valid) == k["valid"] and e.score == k["score"]
         assert (1 << e.highest) == k["highest_after"] and e.spawn_ctr == 0
     assert emul.emul_overflow() == 0
+
+
+@pytest.mark.parametrize("swar", [1, 0], ids=["table-free", "row-tables"])
+def test_per_step_kernel_single_steps_on_synthetic_boards(emul, orc, swar):
+    """One step from boards a game rarely shows (dense, sparse, tile-less, all-32768 and other high-tile mixes) for
+    every action incl. an out-of-range one, with highest_tile equal to, above and below the board maximum: the step
+    derives the empty count, the new maximum and the legal mask from by-products of the table-free move."""
+    n = 0
+    for bi, b in enumerate(boards_for_test(orc, 150)):
+        b = np.minimum(b, 32768)
+        bmax = int(b.max())
+        for hi in {bmax, 2 * bmax if 0 < bmax < 32768 else 65536 if bmax else 4, bmax // 2 if bmax > 2 else 0}:
+            for a in (0, 1, 2, 3, 5):
+                o = orc.Env(SEED, bi, ctor_reset=False)
+                o.set_board(b, score=0, highest_tile=hi)
+                o.s.spawn_ctr = 3
+                hexp = 0 if hi == 0 else int(hi).bit_length() - 1
+                if hexp > 15:
+                    continue
+                e = EmulEnv(packing.pack_board(b), 0, hexp, 3)
+                ob, orw, od, oi = o.step(a)
+                if ob.max() > 32768:                       # 32768 + 32768 has no nibble: the kernel counts it as overflow
+                    continue
+                st = EmulStep(); legal = C.c_uint32(0)
+                emul.emul_env_step_pairs(C.byref(e), a, None, SEED, bi, swar, C.byref(st), C.byref(legal))
+                assert e.board == packing.pack_board(ob), (bi, a, hi)
+                assert st.reward == orw or (st.reward != st.reward and orw != orw), (bi, a, hi, st.reward, orw)   # 0/0 on a tile-less board
+                assert bool(st.done) == od and bool(st.valid) == oi["valid_move"] and st.score_delta == oi["score_delta"]
+                assert (1 << e.highest if e.highest else 0) == oi["highest_tile"] or (e.highest == 0 and oi["highest_tile"] in (0, 1)), (bi, a, hi, e.highest, oi["highest_tile"])
+                assert e.spawn_ctr == o.s.spawn_ctr and legal.value == orc.env_legal_mask(ob)
+                n += 1
+    assert n > 2000
