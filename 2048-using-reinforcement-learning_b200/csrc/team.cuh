@@ -23,7 +23,7 @@ constexpr uint32_t kTeamRing = 512;                  // spawn ordinals held per 
 struct __align__(16) TeamScratch {
     uint4 rng[kTeamRing / 2];       // spawn words of ordinals [ring_end - 512, ring_end): one Philox block per entry
     double score[kTeamThreads + 8]; // float64 scores of a full-evaluation level, generation order (+ padding of a chunk)
-    uint32_t key[kTeamThreads];     // sort keys by thread (action * 32 + parent rank); 0 = no child
+    uint32_t key[kTeamThreads];     // sort keys of the level's children in generation order, padded with 0 to a multiple of 16
     uint64_t beam[32];              // parents of the level, rank order
     uint32_t ballots[8];            // [a]: valid children of action a (bit = parent rank); [4 + a]: those that draw
     uint8_t meta[32];               // first action | largest exponent << 2 of beam[i]
@@ -87,19 +87,18 @@ __device__ __forceinline__ Board agent_child_uniform(Board b, uint32_t action, c
     }
 }
 
-// #keys of the level larger than `key`: the keys of action a sit at keys[32a .. 32a + holders),
-// unused slots are 0.  kGroups 16-byte groups per action, fully unrolled with four independent
-// accumulators: the loads are broadcasts, the compares independent, so a lone warp issues them
-// back to back instead of walking one dependent chain.
-template <int kGroups>
-__device__ __forceinline__ uint32_t count_larger_keys(const uint32_t *keys, uint32_t key)
+// #keys among keys[0 .. n) larger than `key`; keys[n .. n + 15] must hold 0 (chunks of 16).  The keys sit in
+// generation order without gaps (a level of width 20 has 80 slots by thread but ~55 valid children: only those are
+// compared).  Four independent accumulators: the loads are broadcasts, the compares independent, so a lone warp
+// issues them back to back instead of walking one dependent chain.
+__device__ __forceinline__ uint32_t count_larger_keys(const uint32_t *keys, int n, uint32_t key)
 {
     uint32_t r0 = 0u, r1 = 0u, r2 = 0u, r3 = 0u;
+#pragma unroll 1
+    for (int j = 0; j < n; j += 16) {
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + j);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + 32 * a);
-#pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
+        for (int g = 0; g < 4; ++g) {
             const uint4 k = k4[g];
             // keys are below 2^31, so the sign of key - k is "k is larger": a subtract and a shift-add
             // (LEA.HI) per key instead of compare / increment / select
@@ -243,7 +242,8 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
             const int fast = fast_eval_flags(b, nzl, nzh, n_empty, emax, corners);
             if (valid) key = ((uint32_t)fast << 9) | tail;
         }
-        ts.key[tid] = key;
+        if (valid) ts.key[pos] = key;                                   // generation order, no gaps
+        if (tid >= (uint32_t)n_valid && tid < (((uint32_t)n_valid + 15u) & ~15u)) ts.key[tid] = 0u;   // the last chunk's padding
         team_barrier(bar);                                              // (2) all keys of the level are visible
         TEAM_PROF_MARK(_pb);
         if (ring_end - spawn_base < 128u) {                             // the next level's spawn words (see above)
@@ -253,12 +253,7 @@ __device__ __forceinline__ BeamResult beam_search_team(Board root, int legal_giv
         }
 
         // ---- C: stable top-k by counting (agent:131-132,174-175) -----------------------------------------
-        const int groups = d == 0 ? 1 : (nb + 3) >> 2;                 // 16-byte key groups per action in use
-        uint32_t rank;
-        if (groups <= 4)      rank = count_larger_keys<4>(ts.key, key);
-        else if (groups == 5) rank = count_larger_keys<5>(ts.key, key);
-        else if (groups == 6) rank = count_larger_keys<6>(ts.key, key);
-        else                  rank = count_larger_keys<8>(ts.key, key);
+        const uint32_t rank = count_larger_keys(ts.key, n_valid, key);
         nb = min(P.width, n_valid);
         G2048_ASSERT(nb >= 1 && nb <= 32 && (!valid || rank < (uint32_t)n_valid));
         if (valid && (int)rank < nb) {

@@ -8,4 +8,5 @@ for c in rollout beam step lone; do
   timeout 60 python profiles/ncu_cases.py $c > /dev/null 2>&1 && timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -o gpurun_out/prof_${c}_r02 -f python profiles/ncu_cases.py $c > gpurun_out/ncu_$c.log 2>&1; echo "ncu $c rc $?"
 done
 timeout 400 ncu --set full --clock-control none --cache-control none --import-source on -k regex:env_step_fused -s 7 -c 1 -o gpurun_out/prof_step_warm_r02 -f python profiles/ncu_cases.py step > gpurun_out/ncu_step_warm.log 2>&1; echo "ncu step warm rc $?"
+timeout 400 ncu --set full --clock-control none --cache-control none --import-source on -k regex:env_step_fused -s 7 -c 1 -o gpurun_out/prof_step_plain_r02 -f python profiles/ncu_cases.py step_plain > gpurun_out/ncu_step_plain.log 2>&1; echo "ncu step plain rc $?"
 ls -la gpurun_out/*.ncu-rep

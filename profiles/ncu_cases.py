@@ -1,5 +1,5 @@
 """One short launch of a hot kernel, for `ncu --set full -k regex:<kernel>` (see profiles/README.md).
-usage: python profiles/ncu_cases.py rollout | beam | step | lone | games"""
+usage: python profiles/ncu_cases.py rollout | beam | step | step_plain | lone | games"""
 import os
 import sys
 
@@ -23,6 +23,13 @@ elif case == "beam":                        # beam_search_kernel: 10,000 roots, 
     s = G.BatchedBeamSearch(20, 40, dev, seed=1234)
     for c in range(3):
         s.get_actions(roots, call=c)
+elif case == "step_plain":                  # the same kernel without programmatic dependent launch (one block of 14 warps per SM)
+    _lib.check(lib.g2048_set_tuning(6, 0))
+    env = G.BatchedGame2048Env(65536, dev, seed=1234)
+    env.rollout(300)
+    acts = torch.randint(0, 4, (8, 65536), device=dev, dtype=torch.uint8)
+    for i in range(8):
+        env.step_fused(acts[i], auto_reset=True, want_obs=True)
 elif case == "step":                        # env_step_fused_kernel: 65,536 envs, all outputs incl. observation
     env = G.BatchedGame2048Env(65536, dev, seed=1234)
     env.rollout(300)                        # mid-game boards

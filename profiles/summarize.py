@@ -165,12 +165,25 @@ def main():
                           "source": f"profiles/ncu_summary_{tag}.md"}
     rep = os.path.join(OUT, f"prof_step_{tag}.ncu-rep")
     if os.path.exists(rep):
+        text += ["## note on the env_step_fused_kernel captures",
+                 "Up to 65,536 envs the product launches this kernel as ONE-WARP blocks with programmatic dependent launch: the",
+                 "blocks of step t+1 become resident and copy their 4 KiB of tables (seven dependent L2 round trips per warp)",
+                 "while step t still computes.  ncu serialises launches, so in the two default-policy captures below that",
+                 "prologue stands alone in front of every warp (long_scoreboard 3-9, 9-11 us per launch) although the stream",
+                 "never sees it: the same launch costs 4.0 us per step in a CUDA graph (bench.py `per_step_api`,",
+                 "profiles/step_sizes_r02.json).  The third capture runs the kernel in its plain form (G2048_TUNE_PDL = 0: one",
+                 "block of 14 warps per SM, tables published inside the step), which is what ncu can measure faithfully.", ""]
         lines, d = raw_summary(rep, "env_step_fused_kernel<table-free move> (per-step API, 65,536 envs per launch, all outputs incl. observation)")
         text += lines + [""]
     rep = os.path.join(OUT, f"prof_step_warm_{tag}.ncu-rep")
     if os.path.exists(rep):
         lines, d = raw_summary(rep, "env_step_fused_kernel, the same launch with --cache-control none (state and tables L2-resident, as inside "
                                     "a training loop / CUDA graph; the capture above starts from flushed caches)")
+        text += lines + [""]
+    rep = os.path.join(OUT, f"prof_step_plain_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        lines, d = raw_summary(rep, "env_step_fused_kernel in its plain launch form (G2048_TUNE_PDL = 0: 147 blocks of 14 warps, no programmatic "
+                                    "dependent launch), --cache-control none", ("warp-step (32 board-steps)", 65536 / 32, "65,536 envs per launch"))
         text += lines + [""]
     rep = os.path.join(OUT, f"prof_lone_{tag}.ncu-rep")
     if os.path.exists(rep):
