@@ -372,12 +372,18 @@ def test_step_autoreset_equals_step_then_reset_done():
     assert torch.equal(a_env.legal, b_env.legal_masks())
 
 
-@pytest.mark.parametrize("tables,outputs", [(0, -1), (1, -1), (0, 0)], ids=["table-free", "row-tables", "generic-outputs"])
+@pytest.mark.parametrize("tables,outputs,pdl,warps", [(0, -1, -1, -1), (1, -1, -1, -1), (0, 0, -1, -1), (0, -1, 0, 14), (0, 1, 0, 3),
+                                                     (1, -1, 0, 28), (0, -1, 1, 7)],
+                         ids=["table-free", "row-tables", "generic-outputs", "plain-14-warps", "plain-3-warps-core-outputs",
+                              "row-tables-plain-28-warps", "pdl-7-warps"])
 @pytest.mark.parametrize("n", [1, 31, 77, 1000, 4097])
-def test_step_fused_vs_oracle(orc, n, tables, outputs):
+def test_step_fused_vs_oracle(orc, n, tables, outputs, pdl, warps):
     """g2048_env_step_fused: step + reset of finished games + legal mask + observation + pre-reset state in
     one launch, at ragged sizes (the observation is written through warp shuffles), with both row-move forms and
-    with the kernel variant that tests every optional array itself (the default one takes the full set for granted)."""
+    with the kernel variant that tests every optional array itself (the default one takes the full set for granted), and
+    in the launch forms larger batches get (plain launches of multi-warp blocks, which publish their tables inside the
+    step and whose last block holds threads past the end of the batch; 7-warp blocks with programmatic dependent
+    launch): small batches default to one-warp blocks, so the knobs force the other forms here."""
     import torch
     steps = 140 if n <= 1000 else 40
     env = G.BatchedGame2048Env(n, "cuda:0", seed=SEED, game0=11)
@@ -388,7 +394,7 @@ def test_step_fused_vs_oracle(orc, n, tables, outputs):
     sample = sorted(set(range(min(n, 40))) | {n - 1, n // 2})
     rng = np.random.default_rng(2)
     episodes = np.zeros(n, np.int64)
-    with X.tuning({X.TUNE_STEP_TABLES: tables, X.TUNE_STEP_OUTPUTS: outputs}):
+    with X.tuning({X.TUNE_STEP_TABLES: tables, X.TUNE_STEP_OUTPUTS: outputs, X.TUNE_PDL: pdl, X.TUNE_STEP_BLOCK_WARPS: warps}):
         for t in range(steps):
             a = rng.integers(0, 4, n).astype(np.uint8)
             obs, reward, done, info = env.step_fused(torch.from_numpy(a).cuda(), auto_reset=True)
