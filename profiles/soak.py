@@ -33,6 +33,35 @@ for it in range(rounds):
     O.rollout(ob, osc, ohi, octr, ors, oep, steps, t_start, seed, game0)
     assert (b == G.pack_boards(ob)).all() and (s == osc).all() and (c == octr).all() and (rs == ors).all() and (ep == oep).all()
     tot["env_board_steps"] += n * steps
+    # ---- the per-step kernel (one launch per step, auto-reset) over the same envs, actions and step range, in a random
+    #      launch form (block size, programmatic dependent launch, row move, optional-array variant): it has to arrive
+    #      where the fused rollout and the oracle did, float64 reward sum in step order included
+    if it % 2 == 0:
+        import torch
+        ns = min(n, 1024); st = min(steps, 120)
+        knobs = {X.TUNE_STEP_TABLES: int(rng.choice([-1, 0, 1])), X.TUNE_STEP_OUTPUTS: int(rng.choice([-1, 0, 1])),
+                 X.TUNE_PDL: int(rng.choice([-1, 0, 1])), X.TUNE_STEP_BLOCK_WARPS: int(rng.choice([-1, 1, 3, 7, 14, 28, 32]))}
+        acts = np.array([[O.lib().orc_random_action(seed, game0 + i, t_start + t) for i in range(ns)] for t in range(st)], np.uint8)
+        env = G.BatchedGame2048Env(ns, "cuda:0", seed=seed, game0=game0)
+        env.reset()
+        dev_acts = torch.from_numpy(acts).cuda()
+        total = torch.zeros(ns, dtype=torch.float64, device="cuda:0")
+        fused = rng.random() < 0.5
+        with X.tuning(knobs):
+            for t in range(st):
+                if fused: env.step_fused(dev_acts[t], auto_reset=True, want_obs=bool(t & 1))
+                else: env.step(dev_acts[t], auto_reset=True)
+                total += env.reward
+        sb = np.zeros((ns, 16), np.int32); ssc = np.zeros(ns, np.int64); shi = np.zeros(ns, np.int32); sctr = np.zeros(ns, np.uint32)
+        for i in range(ns):
+            e = O.Env(seed, game0 + i, ctor_reset=False); e.reset()
+            sb[i] = e.board; shi[i] = e.s.highest_tile; sctr[i] = e.s.spawn_ctr
+        srs = np.zeros(ns); sep = np.zeros(ns, np.int32)
+        O.rollout(sb, ssc, shi, sctr, srs, sep, st, t_start, seed, game0)
+        assert (env.boards_u64() == G.pack_boards(sb)).all() and (env.score.cpu().numpy() == ssc).all(), (it, knobs)
+        assert (env.spawn_ctr.cpu().numpy().astype(np.uint32) == sctr).all() and (env.episodes.cpu().numpy() == sep).all(), (it, knobs)
+        assert (total.cpu().numpy() == srs).all(), (it, knobs)
+        tot["per_step_board_steps"] = tot.get("per_step_board_steps", 0) + ns * st
     # ---- beam: random width / depth / thresholds / caller-supplied legality on the boards just reached
     W = int(rng.integers(1, 33)) if rng.random() < 0.85 else int(rng.integers(33, 129))      # 15 %: wide-beam path
     D = int(rng.integers(1, 46))
