@@ -119,3 +119,22 @@ def test_plain_c_client_links_against_the_abi(built, tmp_path):
         assert out.returncode == 0 and out.stdout.count("score") == 4, out.stdout
     else:
         assert out.returncode == 3 and "no CUDA device" in out.stdout, out.stdout
+
+
+def test_tuning_keys_agree_between_header_library_and_tests(built):
+    """The G2048_TUNE_* enum of include/g2048.h, the defaults table of the library (csrc/beam.cu) and the constants the
+    GPU tests use (tests/gpu_common.py) name the same keys with the same defaults; set_tuning refuses unknown keys."""
+    from tests import gpu_common as X
+    header = open(os.path.join(ROOT, "include", "g2048.h")).read()
+    enum = dict((k, int(v)) for k, v in re.findall(r"G2048_TUNE_([A-Z_]+)\s*=\s*(\d+)", header))
+    count = enum.pop("COUNT")
+    assert sorted(enum.values()) == list(range(count))
+    for name, value in enum.items():
+        assert getattr(X, "TUNE_" + name) == value, name
+    src = open(os.path.join(ROOT, "2048-using-reinforcement-learning_b200", "csrc", "beam.cu")).read()
+    defaults = [int(v) for v in re.search(r"g_tuning\[G2048_TUNE_COUNT\]\s*=\s*\{([^}]*)\}", src).group(1).split(",")]
+    assert len(defaults) == count and defaults == [X._TUNE_DEFAULTS[k] for k in range(count)]
+    from g2048_b200 import _lib
+    lib = _lib.load()
+    assert lib.g2048_set_tuning(count, 0) != 0 and lib.g2048_set_tuning(-1, 0) != 0
+    assert lib.g2048_set_tuning(enum["PDL"], -1) == 0
