@@ -9,4 +9,6 @@ for c in rollout beam step lone; do
 done
 timeout 400 ncu --set full --clock-control none --cache-control none --import-source on -k regex:env_step_fused -s 7 -c 1 -o gpurun_out/prof_step_warm_r02 -f python profiles/ncu_cases.py step > gpurun_out/ncu_step_warm.log 2>&1; echo "ncu step warm rc $?"
 timeout 400 ncu --set full --clock-control none --cache-control none --import-source on -k regex:env_step_fused -s 7 -c 1 -o gpurun_out/prof_step_plain_r02 -f python profiles/ncu_cases.py step_plain > gpurun_out/ncu_step_plain.log 2>&1; echo "ncu step plain rc $?"
+# (a --set full capture of play_games_kernel at this size -- 0.44 s per pass, ~45 passes with source counters -- did not finish in 280 s; the team kernel does)
+for k in team; do timeout 400 ncu --set full --clock-control none --import-source on -k regex:${k}_games_kernel -c 1 -o gpurun_out/prof_games_${k}_r02 -f python profiles/ncu_cases.py games10k > gpurun_out/ncu_games_$k.log 2>&1; echo "ncu games $k rc $?"; done
 ls -la gpurun_out/*.ncu-rep

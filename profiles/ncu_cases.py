@@ -1,5 +1,5 @@
 """One short launch of a hot kernel, for `ncu --set full -k regex:<kernel>` (see profiles/README.md).
-usage: python profiles/ncu_cases.py rollout | beam | step | step_plain | lone | games"""
+usage: python profiles/ncu_cases.py rollout | beam | step | step_plain | lone | games | games10k"""
 import os
 import sys
 
@@ -39,6 +39,9 @@ elif case == "step":                        # env_step_fused_kernel: 65,536 envs
 elif case == "lone":                        # team_games_kernel: one game, one team, 400 moves
     s = G.BatchedBeamSearch(20, 40, dev, seed=1234)
     s.play_games(1, max_moves=400, game0=7, stats=False)
+elif case == "games10k":                    # cfg 5 on one GPU: play_games_kernel (one warp per game) then team_games_kernel
+    s = G.BatchedBeamSearch(20, 40, dev, seed=1234)
+    s.play_games(10000, max_moves=10000, game0=0, stats=False)
 elif case == "games":                       # team_games_kernel: the per-GPU share of cfg 5 at 8 GPUs
     s = G.BatchedBeamSearch(20, 40, dev, seed=1234)
     s.play_games(1250, max_moves=10000, game0=0, stats=False)

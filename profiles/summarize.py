@@ -185,6 +185,14 @@ def main():
         lines, d = raw_summary(rep, "env_step_fused_kernel in its plain launch form (G2048_TUNE_PDL = 0: 147 blocks of 14 warps, no programmatic "
                                     "dependent launch), --cache-control none", ("warp-step (32 board-steps)", 65536 / 32, "65,536 envs per launch"))
         text += lines + [""]
+    for kern, what in (("play", "play_games_kernel, cfg 5 on one GPU (10,000 games at 20/40, one warp per game, 24 warps per SM, until 888 games are "
+                                "left): the throughput phase of whole-game runs, 51 % of the bench's GPU time"),
+                       ("team", "team_games_kernel, the same run's tail (888 games and fewer, one team of four warps per game, stall ranges "
+                                "on the free SMs): chain-bound, so low average utilisation is the point (DESIGN.md 4.5)")):
+        rep = os.path.join(OUT, f"prof_games_{kern}_{tag}.ncu-rep")
+        if os.path.exists(rep):
+            lines, d = raw_summary(rep, what)
+            text += lines + [""]
     rep = os.path.join(OUT, f"prof_lone_{tag}.ncu-rep")
     if os.path.exists(rep):
         text += ["## team_games_kernel, ONE game (400 moves at 20/40): the sequential chain that bounds whole-game runs",
