@@ -2,14 +2,14 @@
 BASELINE.json widths (BeamSearchAgent 15/20 and 20/40), move by move.
 
 Run in the build container (needs /root/reference):   python oracle/make_golden_games.py
-TEST INFRASTRUCTURE ONLY.  Takes ~15 minutes on 4 cores: the reference is pure Python
+TEST INFRASTRUCTURE ONLY.  Takes ~20 minutes on 8 cores: the reference is pure Python
 (~0.15 s per get_action at 15/20, ~0.35 s at 20/40), one process per game.
 
 Each game is evaluate_beam_search.run_game (evaluate_beam_search.py:16-98) with the
 reference's own Game2048Env and BeamSearchAgent, unmodified, their module-level `random`
 replaced by the Philox StreamShim (env stream of game g; beam stream of (game g, call =
 move index)).  Every move is one reference `get_action(state)` call, so the file also
-holds > 4,000 single-call vectors on boards harvested from real play (<= 4 empties,
+holds > 13,000 single-call vectors on boards harvested from real play (<= 4 empties,
 mid and late phase, dead boards with the fake-valid DOWN of SURVEY Q1, stalls):
     boards[m]  packed board (hex) the agent saw before move m
     actions[m] the action the reference chose
@@ -35,7 +35,9 @@ from oracle import ref_harness as R       # noqa: E402
 SEED = 0x2048B200C0FFEE
 OUT = os.path.join(ROOT, "tests", "golden", "reference_games.json")
 # (beam_width, search_depth, game id, max_moves)
-GAMES = [(15, 20, 11, 10000), (15, 20, 33, 10000), (15, 20, 10, 10000), (20, 40, 16, 10000)]
+GAMES = [(15, 20, 11, 10000), (15, 20, 33, 10000), (15, 20, 10, 10000), (20, 40, 16, 10000),
+         # second batch: > 10,000 reference get_action calls in total, a 20/40 game with a stall of ~1,000 calls that ends
+         (15, 20, 48, 10000), (15, 20, 59, 10000), (15, 20, 58, 10000), (15, 20, 66, 10000), (20, 40, 47, 10000)]
 MILESTONES = (64, 128, 256, 512, 1024, 2048, 4096, 8192)
 
 
