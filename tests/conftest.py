@@ -55,6 +55,13 @@ def golden_games():
 
 
 @pytest.fixture(scope="session")
+def golden_rollouts():
+    """2,000-step random-policy rollouts of the live reference env, summarised per env (oracle/make_golden_rollouts.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_rollouts.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def orc():
     from oracle import pyoracle
     pyoracle.lib()

@@ -536,3 +536,45 @@ def test_hybrid_beam_driver_vs_reference_goldens_and_oracle(orc, golden):
             ranked = sorted(scores.values(), reverse=True)
             if len(ranked) == 1 or ranked[0] - ranked[1] > 1e-4 * max(1.0, abs(ranked[0])):     # not a near-tie
                 assert a[i] == want, (i, sc[i], scores)
+
+
+def test_reference_rollouts_of_the_headline_shape(orc, golden_rollouts):
+    """128,000 steps of the LIVE reference env (oracle/make_golden_rollouts.py: 64 envs x 2,000 random-policy steps,
+    finished games reset at once -- BASELINE cfg 2's shape per env).  The fused rollout kernel arrives at the
+    reference's final board, score, highest tile, spawn count, number of finished games and float64 reward sum; the
+    per-step kernel additionally reproduces every single reward (SHA-256 over the float64 rewards in step order)."""
+    import hashlib
+    import torch
+    seed, steps, game0, envs = (golden_rollouts[k] for k in ("seed", "steps", "game0", "envs"))
+    n = len(envs)
+    # ---- g2048_host_env_rollout (env_rollout_kernel), one launch
+    b, s, h, c = X.host_reset(n, seed, game0)                    # constructor reset
+    b, s, h, c = X.host_reset(n, seed, game0, spawn_ctr=c)       # explicit reset
+    assert [int(x) for x in b] == [int(e["start"], 16) for e in envs]
+    rs = np.zeros(n); ep = np.zeros(n, np.int32)
+    X.host_rollout(b, s, h, c, rs, ep, steps, 0, seed, game0)
+    for i, e in enumerate(envs):
+        assert int(b[i]) == int(e["final"], 16) and s[i] == e["score"] and (1 << int(h[i])) == e["highest_tile"], i
+        assert c[i] == e["spawns"] and ep[i] == e["episodes"] and rs[i] == float.fromhex(e["reward_sum"]), i
+    # ---- g2048_env_step_fused (env_step_fused_kernel), one launch per step
+    env = G.BatchedGame2048Env(n, "cuda:0", seed=seed, game0=game0)      # the constructor resets
+    env.reset(restart_streams=False)
+    acts = np.array([[orc.lib().orc_random_action(seed, game0 + i, t) for i in range(n)] for t in range(steps)], np.uint8)
+    dev_acts = torch.from_numpy(acts).cuda()
+    rewards = torch.empty(steps, n, dtype=torch.float64, device="cuda:0")
+    valid = torch.zeros(n, dtype=torch.int64, device="cuda:0")
+    for t in range(steps):
+        env.step_fused(dev_acts[t], auto_reset=True, want_obs=bool(t & 1))
+        rewards[t] = env.reward
+        valid += env.valid
+    rewards = rewards.cpu().numpy()
+    total = np.zeros(n)
+    for t in range(steps):
+        total += rewards[t]                                       # float64 sum in step order, as the reference's loop
+    boards = env.boards_u64(); score = env.score.cpu().numpy(); ctr = env.spawn_ctr.cpu().numpy().astype(np.uint32)
+    episodes = env.episodes.cpu().numpy(); hexp = env.highest_exp.cpu().numpy(); valid = valid.cpu().numpy()
+    for i, e in enumerate(envs):
+        assert int(boards[i]) == int(e["final"], 16) and score[i] == e["score"] and (1 << int(hexp[i])) == e["highest_tile"], i
+        assert ctr[i] == e["spawns"] and episodes[i] == e["episodes"] and valid[i] == e["valid"], i
+        assert total[i] == float.fromhex(e["reward_sum"]), i
+        assert hashlib.sha256(np.ascontiguousarray(rewards[:, i]).astype("<f8").tobytes()).hexdigest() == e["rewards_sha256"], i

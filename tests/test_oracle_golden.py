@@ -157,3 +157,37 @@ def test_hybrid_beam_search(orc, golden):
     for rec in golden["hybrid_beam"]:
         got, _ = H.beam_search(rec["board"], model, golden["seed"], rec["game"], rec["call"])
         assert got == rec["action"], rec
+
+
+def test_reference_rollouts_of_the_headline_shape(orc, golden_rollouts):
+    """128,000 steps of the live reference env (64 envs x 2,000 random-policy steps, finished games reset at once:
+    BASELINE cfg 2's shape per env): the oracle's rollout reproduces every env's final board, score, highest tile,
+    spawn count, number of finished games and float64 reward sum, and its step() every single reward (SHA-256 over
+    the float64 rewards in step order)."""
+    import hashlib
+    import struct
+    import g2048_b200 as G
+    seed, steps, game0, envs = (golden_rollouts[k] for k in ("seed", "steps", "game0", "envs"))
+    n = len(envs)
+    assert n * steps >= 100000 and sum(e["episodes"] for e in envs) >= 500
+    boards = np.zeros((n, 16), np.int32); score = np.zeros(n, np.int64); hi = np.zeros(n, np.int32); ctr = np.zeros(n, np.uint32)
+    for i, e in enumerate(envs):
+        assert e["game"] == game0 + i
+        o = orc.Env(seed, game0 + i)              # the constructor resets ...
+        o.reset()                                 # ... and the loop resets again
+        boards[i] = o.board; hi[i] = o.s.highest_tile; ctr[i] = o.s.spawn_ctr
+        assert G.pack_board(o.board) == int(e["start"], 16)
+    rs = np.zeros(n); ep = np.zeros(n, np.int32)
+    orc.rollout(boards, score, hi, ctr, rs, ep, steps, 0, seed, game0)
+    for i, e in enumerate(envs):
+        assert G.pack_board(boards[i]) == int(e["final"], 16) and score[i] == e["score"] and hi[i] == e["highest_tile"], i
+        assert ctr[i] == e["spawns"] and ep[i] == e["episodes"] and rs[i] == float.fromhex(e["reward_sum"]), i
+    for i, e in enumerate(envs[:16]):             # every single reward, through step()
+        o = orc.Env(seed, game0 + i); o.reset()
+        h = hashlib.sha256(); valid = 0
+        for t in range(steps):
+            _, r, d, info = o.step(orc.lib().orc_random_action(seed, game0 + i, t))
+            h.update(struct.pack("<d", r)); valid += info["valid_move"]
+            if d:
+                o.reset()
+        assert h.hexdigest() == e["rewards_sha256"] and valid == e["valid"], i
